@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Headline benchmark: VAE train samples/sec on synthetic 1x128xT piano-rolls.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU arm
+
+A "step" is one pass of the hot path over one batch: forward (models.py:185-188)
++ ELBO (:190-225) + backward (train.py:650) + gradient all-reduce when N > 1 +
+the reference's AdamW step over its encoder/decoder groups (train.py:210-228,656).
+Workload at every N: BASELINE.json configs[1] -- default widths [32,64,128,256],
+L = 10, batch 512 PER GPU (weak scaling), bf16 activations / fp32 master weights.
+
+Prints ONE JSON line (rank 0).  See README / DESIGN.md for the field meanings.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN = [32, 64, 128, 256]
+LATENT = 10
+METRIC = "vae_train_samples_per_sec"
+UNIT = "samples/s"
+FLOPS_PER_SAMPLE_TRAIN = {(128, 128): 0.9419e9}  # BASELINE.md §2 (FlopCounterMode on the reference)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
+    ap.add_argument("--height", type=int, default=128)
+    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=64)
+    ap.add_argument("--profile-json", default=None, help="write the per-kernel CUDA-event breakdown here")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"VanillaVAE widths {HIDDEN} L={LATENT}, synthetic 1x{a.height}x{a.width} piano-rolls, batch {a.batch}/GPU"
+
+
+# ----------------------------------------------------------------------------
+# clocks: sampled DURING the timed region (B200_PROFILING.md "clocks line")
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# algorithmic bytes / flops of one C-ABI launch (DESIGN.md "kernels" table)
+# ----------------------------------------------------------------------------
+def _sz(code):
+    return 2 if code == 1 else 4
+
+
+def algorithmic_cost(name, tag):
+    """-> (bytes, flops) one launch must move / compute, from its integer args."""
+    t = list(tag)
+    if name == "vae_conv_fprop":
+        B, Hi, Wi, Ci, Co, s, di, do = t[:8]
+        Ho, Wo = Hi // s, Wi // s
+        return (B * Hi * Wi * Ci * _sz(di) + B * Ho * Wo * Co * _sz(do) + 9 * Ci * Co * _sz(do), 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name == "vae_conv_dgrad":
+        B, Hi, Wi, Ci, Co, s, d = t[:7]
+        Ho, Wo = Hi // s, Wi // s
+        return (B * Hi * Wi * Ci * _sz(d) + B * Ho * Wo * Co * _sz(d) + 9 * Ci * Co * _sz(d), 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name == "vae_conv_wgrad":
+        B, Hi, Wi, Ci, Co, s, dx, dy = t[:8]
+        Ho, Wo = Hi // s, Wi // s
+        return (B * Hi * Wi * Ci * _sz(dx) + B * Ho * Wo * Co * _sz(dy) + 9 * Ci * Co * 4, 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name == "vae_bn_apply_lrelu":
+        n, C, d = t[:3]
+        return (2 * n * C * _sz(d), 3 * n * C)
+    if name == "vae_bn_lrelu_bwd_reduce":
+        n, C, d = t[:3]
+        return (2 * n * C * _sz(d), 8 * n * C)
+    if name == "vae_bn_lrelu_bwd_apply":
+        n, C = t[:2]
+        d = t[3] if len(t) > 3 else 0
+        return (3 * n * C * _sz(d), 10 * n * C)
+    if name in ("vae_elbo_fwd", "vae_elbo_bwd"):
+        n, B, L, d = t[0], t[1], t[2], t[3]
+        per = (_sz(d) + 4) if name == "vae_elbo_fwd" else (2 * _sz(d) + 4)
+        return (n * per + 6 * B * L * 4, 20 * n)
+    if name == "vae_sigmoid":
+        n, d = t[:2]
+        return (n * (_sz(d) + 4), 4 * n)
+    if name in ("vae_nhwc_to_nchw", "vae_nchw_to_nhwc"):
+        B, HW, C, ds, dd = t[:5]
+        return (B * HW * C * (_sz(ds) + _sz(dd)), 0)
+    if name == "vae_gemm":
+        M, N, K = t[:3]
+        return (4 * (M * K + K * N + M * N), 2 * M * N * K)
+    return (0, 0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------
+# CPU arms
+# ----------------------------------------------------------------------------
+def cpu_reference_run(a, steps, warmup, batch):
+    """The reference's CPU train step (oracle port of train.py:635-656) on all host cores."""
+    from oracle import vae_oracle as vo
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    params = vo.xavier_params(1, LATENT, a.height, a.width, HIDDEN, seed=0)
+    trainer = vo.CpuTrainStep(params, batch)
+    x, _ = vo.synthetic_batch(batch, a.height, a.width, LATENT)
+    for _ in range(warmup):
+        trainer(x)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        trainer(x)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of batch {batch} fp32 1x{a.height}x{a.width} (median {statistics.median(times)*1e3:.0f} ms/step), "
+                      "oracle/vae_oracle.CpuTrainStep = reference train.py:635-656 with ATen CPU ops",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(a.steps, 30)), max(1, min(a.warmup, 5))
+    r = cpu_reference_run(a, steps, warmup, a.cpu_batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": f"CPU arm runs a bounded sample: batch {a.cpu_batch} per step on {r['cores']} host cores"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------
+def b200_arm(a):
+    import torch.distributed as dist
+
+    import torch_vae_b200 as tv
+    from torch_vae_b200 import ops
+    from torch_vae_b200.parallel import GradientBuckets
+    from oracle import vae_oracle as vo  # synthetic-input generator + CPU baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; torch_vae_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tv.load_library()
+
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    B, H, W = a.batch, a.height, a.width
+    torch.manual_seed(0)
+    model = tv.VanillaVAE(1, LATENT, (H, W), hidden_dims=list(HIDDEN), compute_dtype=dtype).to(dev)
+    model.manual_seed(0, rank)
+    model.train()
+    lr = 0.01 * (B * world) / 128  # train.py:201
+    opt = torch.optim.AdamW(
+        [{"params": model.encoder.parameters(), "lr": lr, "name": "encoder"},
+         {"params": model.decoder.parameters(), "lr": lr, "name": "decoder"}], lr=lr, weight_decay=0.0, capturable=not a.no_graph)
+    buckets = None
+    if world > 1:
+        buckets = GradientBuckets(model)
+        buckets.broadcast_parameters(0)
+
+    x_host, _ = vo.synthetic_batch(B, H, W, LATENT, seed=1234 + rank)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    losses_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def train_step(x):
+        out = model.forward(x)  # train.py:635
+        opt.zero_grad(set_to_none=True)  # :642
+        losses = model.loss(out)  # :644
+        if buckets is not None:
+            buckets.begin()
+        losses["loss"].backward()  # :650
+        if buckets is not None:
+            buckets.finish()
+        opt.step()  # :656
+        return losses
+
+    # -- per-kernel breakdown (eager, untimed): find the dominant kernel -----
+    for _ in range(2):
+        train_step(x_dev)
+    torch.cuda.synchronize()
+    tl = ops.Timeline()
+    ops.set_timeline(tl)
+    n_prof = 3
+    l0 = ops.LAUNCHES
+    for _ in range(n_prof):
+        train_step(x_dev)
+    torch.cuda.synchronize()
+    launches_per_step = (ops.LAUNCHES - l0) // n_prof
+    ops.set_timeline(None)
+    summ = tl.summary()
+    rows = sorted(((k, n, ms) for k, (n, ms) in summ.items()), key=lambda r: -r[2])
+    total_kernel_ms = sum(r[2] for r in rows) / n_prof
+    top_key = rows[0][0]
+    if a.profile_json and rank == 0:
+        with open(a.profile_json, "w") as f:
+            json.dump({"per_step_kernel_ms": total_kernel_ms, "launches_per_step": launches_per_step,
+                       "kernels": [{"name": k[0], "args": list(k[1]), "launches_per_step": n / n_prof,
+                                    "ms_per_step": ms / n_prof, "share": ms / n_prof / total_kernel_ms,
+                                    "alg_bytes": algorithmic_cost(*k)[0], "alg_flops": algorithmic_cost(*k)[1]} for k, n, ms in rows]}, f, indent=1)
+
+    # -- optional CUDA-graph capture of the whole step -------------------------
+    use_graph = not a.no_graph and world == 1
+    graph = None
+    static_x = x_dev.clone()
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    train_step(static_x)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                static_losses = train_step(static_x)
+            torch.cuda.synchronize()
+        except Exception as e:  # report, do not hide
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed, running eagerly: {e}", file=sys.stderr)
+            graph = None
+            use_graph = False
+
+    def run_step(x):
+        if graph is not None:
+            static_x.copy_(x, non_blocking=True)
+            graph.replay()
+            return static_losses
+        return train_step(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # -- device-resident timing (value) -----------------------------------------
+    for _ in range(max(3, a.warmup)):
+        run_step(x_dev)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.LAUNCHES
+    ms_total = timed(lambda: run_step(x_dev), a.steps)
+    eager_launches = ops.LAUNCHES - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = ms_total / a.steps
+    value = B * world * a.steps / (ms_total / 1e3)
+
+    # -- dominant kernel, bracketed live (eager so the events land on the launch stream)
+    tl2 = ops.Timeline(only=top_key)
+    ops.set_timeline(tl2)
+    for _ in range(max(3, min(a.steps, 10))):
+        train_step(x_dev)
+    torch.cuda.synchronize()
+    ops.set_timeline(None)
+    n_top, ms_top = tl2.summary()[top_key]
+    top_bytes, top_flops = algorithmic_cost(*top_key)
+    peaks = load_peaks()
+    avg_s = ms_top / n_top / 1e3
+    hbm_bound = top_bytes / (peaks["hbm_gbs"] * 1e9) >= top_flops / (peaks["bf16_tflops_sustained"] * 1e12)
+    if hbm_bound:
+        achieved, peak, unit = top_bytes / avg_s / 1e9, peaks["hbm_gbs"], "GB/s"
+    else:
+        achieved, peak, unit = top_flops / avg_s / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
+    roofline = {"bound": "hbm" if hbm_bound else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak, "traffic": None, "kernel": top_key[0], "kernel_args": list(top_key[1]),
+                "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": top_bytes, "alg_flops_per_launch": top_flops,
+                "share_of_step_kernel_time": rows[0][2] / n_prof / total_kernel_ms, "peak_source": peaks["source"]}
+
+    # -- end to end through the public API with HOST buffers (e2e) ---------------
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        losses = run_step(xd)
+        losses_host[0:1].copy_(losses["loss"].detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (train.py:672)
+        return float(losses_host[0])
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    e2e_value = B * world * a.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "height": H, "width": W, "batch_per_gpu": B, "global_batch": B * world,
+                       "hidden_dims": HIDDEN, "latent": LATENT, "parallelism": f"dp{world}", "cuda_graph": bool(graph is not None),
+                       "optimizer": "torch.optim.AdamW over encoder+decoder groups (train.py:210-228), inside the timed step",
+                       "l2": f"per-step working set {(4.13e6*3*B)/1e6:.0f} MB of activations >> 126 MB L2 (inputs larger than L2)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches_per_step * a.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "step_tflops": FLOPS_PER_SAMPLE_TRAIN.get((H, W), 0) * value / 1e12 if (H, W) in FLOPS_PER_SAMPLE_TRAIN else None,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_reference_run(a, 10, 2, a.cpu_batch)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+/*
+ * vae_b200.h -- C ABI of the B200-native VanillaVAE train-step kernels.
+ *
+ * The reference (finlaymiller/torch-vae) has no FFI: its hot path is the Python
+ * surface of midi_autoencoder/models.py executed by ATen.  Each entry point
+ * below replaces the ATen op(s) that a reference line dispatches to; the
+ * "replaces" note on every prototype cites that line (file:line relative to
+ * /root/reference/midi_autoencoder/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    it says "host"; `stream` is a cudaStream_t passed as void*.
+ *  - activations are NHWC ("channels last"), dtype code VAE_F32 or VAE_BF16;
+ *    parameters, BatchNorm vectors, latents and gradients of parameters are
+ *    always fp32 in the reference's own layouts (OIHW / [out,in]).
+ *  - return value: 0 on success, <0 on error (VAE_ERR_*); vae_last_error()
+ *    gives a host string.  No C++ exception crosses this boundary; the Python
+ *    host raises RuntimeError, the reference's own error convention.
+ *  - nothing here allocates device memory: workspaces are caller-provided
+ *    (the host side takes them from torch's caching allocator).
+ */
+#ifndef VAE_B200_H_
+#define VAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAE_ABI_VERSION 1
+
+#define VAE_F32 0
+#define VAE_BF16 1
+
+#define VAE_OK 0
+#define VAE_ERR_ARG (-1)
+#define VAE_ERR_CUDA (-2)
+#define VAE_ERR_UNSUPPORTED (-3)
+
+typedef void* vae_stream_t;
+
+int vae_abi_version(void);
+const char* vae_last_error(void);
+/* 1 if the library was built with the tcgen05/TMEM (UMMA) conv kernels. */
+int vae_has_umma(void);
+
+/* ------------------------------------------------------------------------
+ * Convolution engine (3x3, pad 1, stride 1 or 2).
+ *
+ * One gather-GEMM kernel family serves Conv2d forward, ConvTranspose2d
+ * forward (= data gradient of the equivalent Conv2d) and both data gradients;
+ * one split-K kernel family serves every weight gradient.  In "equivalent
+ * conv" terms a layer maps X[B,Hi,Wi,Ci] -> Y[B,Hi/s,Wi/s,Co] with weight
+ * W[Co,Ci,3,3]; ConvTranspose2d(cin,cout,k3,s2,p1,op1) (models.py:66-68,77)
+ * is the same thing read backwards (Co=cin, Ci=cout, same memory layout).
+ * ---------------------------------------------------------------------- */
+
+/* Repack an fp32 OIHW weight into the two K-major operand layouts:
+ *   wp[Co][3][3][Ci]  ("fprop" operand)   and   wt[Ci][3][3][Co] ("dgrad" operand)
+ * in dtype `dtype`.  Either destination may be NULL.
+ * replaces: the weight layout cuDNN/MKLDNN pick internally for models.py:45,66,77,80 */
+int vae_pack_conv_weight(const float* w_oihw, void* wp, void* wt, int Co, int Ci, int dtype,
+                         vae_stream_t stream);
+
+/* y = conv(x, w) + bias; optionally accumulates per-channel sum / sum-of-squares
+ * of y into stats[2*Co] (double; zeroed by this call) for train-mode BatchNorm.
+ * dt_in may differ from dt_out (the fp32 piano-roll feeds a bf16 network).
+ * replaces: aten::convolution at models.py:45 (encoder) and :80 (final conv) */
+int vae_conv_fprop(const void* x, const void* wp, const float* bias, void* y, double* stats,
+                   int B, int Hi, int Wi, int Ci, int Co, int stride, int dt_in, int dt_out,
+                   vae_stream_t stream);
+
+/* dx = conv_data_grad(dy, w) (+ bias, + stats over dx when used as the
+ * ConvTranspose2d forward).  dy[B,Hi/s,Wi/s,Co], wt[Ci][3][3][Co], dx[B,Hi,Wi,Ci].
+ * replaces: aten::convolution (transposed) at models.py:66-68,77 and the
+ * data-gradient half of aten::convolution_backward (train.py:650) */
+int vae_conv_dgrad(const void* dy, const void* wt, const float* bias, void* dx, double* stats,
+                   int B, int Hi, int Wi, int Ci, int Co, int stride, int dtype,
+                   vae_stream_t stream);
+
+/* dw[Co][Ci][3][3] (fp32, OIHW, overwritten) = sum over pixels of dy (x) patches(x).
+ * replaces: the weight-gradient half of aten::convolution_backward (train.py:650) */
+int vae_conv_wgrad(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Ci,
+                   int Co, int stride, int dt_x, int dt_dy, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * BatchNorm2d (train and eval) + LeakyReLU.   models.py:46-47,69-70,78-79
+ * ---------------------------------------------------------------------- */
+
+/* From stats[2C] (sum, sumsq over `count` values per channel) produce
+ * mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, and update the
+ * running buffers (momentum, unbiased variance) when `training`.  With
+ * training == 0 the running buffers are used instead of stats (eval mode).
+ * replaces: the statistics half of aten::native_batch_norm */
+int vae_bn_finalize(const double* stats, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* rstd, int C, long long count, float momentum, float eps,
+                    int training, vae_stream_t stream);
+
+/* act = leaky_relu(scale[c]*y + shift[c]).
+ * replaces: the normalise half of aten::native_batch_norm + aten::leaky_relu */
+int vae_bn_apply_lrelu(const void* y, const float* scale, const float* shift, void* act,
+                       long long n_pix, int C, float slope, int dtype, vae_stream_t stream);
+
+/* Pass 1 of the backward: du = dact * lrelu'(scale*y+shift);
+ * dstats[0:C] += sum du, dstats[C:2C] += sum du * xhat (double; zeroed by this call).
+ * replaces: aten::leaky_relu_backward + the reductions of native_batch_norm_backward */
+int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const float* scale,
+                            const float* shift, const float* mean, const float* rstd,
+                            double* dstats, long long n_pix, int C, float slope, int dtype,
+                            vae_stream_t stream);
+
+/* Pass 2: dy = gamma*rstd*(du - dbeta/M - xhat*dgamma/M) (training) or
+ * dy = du*scale (eval); writes dgamma[C], dbeta[C] and dbias[C] = sum dy (the
+ * gradient of the conv bias that feeds this BatchNorm).
+ * replaces: aten::native_batch_norm_backward */
+int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
+                           const float* shift, const float* mean, const float* rstd,
+                           const float* gamma, const double* dstats, void* dy, float* dgamma,
+                           float* dbeta, float* dbias, long long n_pix, int C, float slope,
+                           int training, int dtype, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Layout glue between the NHWC conv stack and the reference's C-major
+ * flatten / view (models.py:133 and :166).
+ * ---------------------------------------------------------------------- */
+int vae_nhwc_to_nchw(const void* src, void* dst, int B, int HW, int C, int dt_src, int dt_dst,
+                     vae_stream_t stream);
+int vae_nchw_to_nhwc(const void* src, void* dst, int B, int HW, int C, int dt_src, int dt_dst,
+                     vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Linear layers fc_mu / fc_var / decoder_input (models.py:55-59,137,141,162)
+ * and their gradients: one strided GEMM  C[M,N] (+)= A[M,K] * B[K,N] (+ bias[N]).
+ * Element (i,j) of an operand lives at base + i*s_row + j*s_col (in elements).
+ * replaces: aten::addmm and its two backward matmuls
+ * ---------------------------------------------------------------------- */
+int vae_gemm(const void* A, const void* Bm, void* C, const float* bias, int M, int N, int K,
+             long long sam, long long sak, long long sbk, long long sbn, long long scm,
+             long long scn, int dtA, int dtB, int dtC, int accumulate, vae_stream_t stream);
+
+/* out[n] = sum_m A[m,n]  (bias gradients).  replaces: aten::sum in addmm backward */
+int vae_colsum(const void* A, float* out, int M, int N, int dtype, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Reparameterisation (models.py:177-183) with Philox4x32-10 RNG.
+ * ---------------------------------------------------------------------- */
+/* eps ~ N(0,1), reproducible in (seed, offset); element i uses counter offset+i/4. */
+int vae_philox_randn(float* out, long long n, unsigned long long seed,
+                     unsigned long long offset, vae_stream_t stream);
+/* z = mu + eps*exp(0.5*logvar).  eps_in != NULL injects eps (parity tests);
+ * otherwise eps is drawn from Philox and written to eps_out for the backward.
+ * dev_offset (nullable) is a device counter added to `offset`, so a captured
+ * CUDA graph draws fresh noise on every replay. */
+int vae_reparam_fwd(const float* mu, const float* logvar, const float* eps_in, float* eps_out,
+                    float* z, long long n, unsigned long long seed, unsigned long long offset,
+                    const long long* dev_offset, vae_stream_t stream);
+/* dmu = dz ; dlogvar = dz*eps*0.5*exp(0.5*logvar)   (accumulate flag adds). */
+int vae_reparam_bwd(const float* dz, const float* eps, const float* logvar, float* dmu,
+                    float* dlogvar, long long n, int accumulate, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused ELBO (models.py:190-225): mean BCE on sigmoid(logits) with the
+ * reference's log clamp at -100, KL term, and all three LossOutput scalars.
+ * losses[0]=loss, [1]=reconstruction_loss, [2]=kld_loss (sign-flipped, :224).
+ * `scratch` = 4 doubles of workspace (zeroed by this call).
+ * input_is_prob != 0: `logits` holds probabilities (a hand-built ModelOutput).
+ * replaces: aten::sigmoid (:81), aten::binary_cross_entropy (:208), the
+ * sum/mean/exp/pow chain (:214) and the add (:216)
+ * ---------------------------------------------------------------------- */
+int vae_elbo_fwd(const void* logits, const float* target, const float* mu, const float* logvar,
+                 float* losses, double* scratch, long long n_elem, int B, int L,
+                 float kld_weight, int dtype, int input_is_prob, vae_stream_t stream);
+/* Gradient of losses[0] scaled by *gscale (device scalar, the upstream grad):
+ * dlogits = g*(p-x)/n_elem (clamp/saturation emulated), dmu = g*kw*mu/B,
+ * dlogvar = g*kw*0.5*(exp(lv)-1)/B. */
+int vae_elbo_bwd(const void* logits, const float* target, const float* mu, const float* logvar,
+                 const float* gscale, void* dlogits, float* dmu, float* dlogvar,
+                 long long n_elem, int B, int L, float kld_weight, int dtype, int input_is_prob,
+                 vae_stream_t stream);
+
+/* probs(fp32) = sigmoid(logits).  replaces: aten::sigmoid at models.py:81 */
+int vae_sigmoid(const void* logits, float* probs, long long n, int dtype, vae_stream_t stream);
+/* dlogits (+)= dprobs * p * (1-p)  (for user losses defined on probabilities). */
+int vae_sigmoid_bwd(const float* dprobs, const float* probs, void* dlogits, long long n,
+                    int dtype, int accumulate, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Device-side piano-roll transforms (data_transformations.py:48-72 "midi"
+ * stack: crop -> ToDtype(scale 1/255) -> Normalize(mean,std); plus the
+ * binarise / pitch-transpose augmentation north_star item (3) adds).
+ * rolls: uint8 [B, Hs, Ws]; out: fp32 [B,1,H,W].
+ * crop_mode 0 = center (test transform, :64), 1 = random (train, :54) drawn
+ * from Philox(seed, offset); max_pitch_shift > 0 rolls pitches by a random
+ * amount in [-max, max] (zero fill); binarize_threshold >= 0 maps the scaled
+ * value to {0,1} before normalisation.
+ * ---------------------------------------------------------------------- */
+int vae_roll_transform(const uint8_t* rolls, float* out, int B, int Hs, int Ws, int H, int W,
+                       int crop_mode, int max_pitch_shift, float binarize_threshold, float mean,
+                       float std, unsigned long long seed, unsigned long long offset,
+                       vae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAE_B200_H_ */

@@ -351,3 +351,38 @@ def xavier_params(
         else:
             out[name] = torch.zeros(shp)
     return out
+
+
+# --------------------------------------------------------------------------
+# the reference's CPU training step, for the timed CPU baseline of bench.py
+# --------------------------------------------------------------------------
+class CpuTrainStep:
+    """train.py:635,642,644,650,656 in that order on the host CPU: forward,
+    zero_grad, loss, backward, optimizer.step -- AdamW over the encoder and
+    decoder parameter groups ONLY (train.py:210-228, "quirk A" in SURVEY.md
+    §3.1), lr = 0.01 * batch / 128 (train.py:201), weight decay 0 as in the
+    reference CLI default.  Functional ops from this file, persistent leaf
+    parameters, fresh eps from torch.randn like models.py:182."""
+
+    def __init__(self, params: Dict[str, Tensor], batch: int, kld_weight: float = 1.0, lr_relative: float = 0.01):
+        self.P = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+        self.Bf = fresh_buffers(params)
+        self.kld_weight = kld_weight
+        lr = lr_relative * batch / 128
+        enc = [v for k, v in self.P.items() if k.startswith("encoder.")]
+        dec = [v for k, v in self.P.items() if k.startswith("decoder.")]
+        self.opt = torch.optim.AdamW(
+            [{"params": enc, "lr": lr, "name": "encoder"}, {"params": dec, "lr": lr, "name": "decoder"}],
+            lr=lr, weight_decay=0.0,
+        )
+
+    def __call__(self, x: Tensor):
+        mu, log_var, pre, feat_shape = encode(self.P, self.Bf, x, True)
+        z = reparameterize(mu, log_var, torch.randn_like(mu))
+        output = torch.sigmoid(decode_logits(self.P, self.Bf, z, feat_shape, True))
+        for p in self.P.values():
+            p.grad = None
+        loss, recon, kld = elbo(output, x, mu, log_var, self.kld_weight)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()

@@ -1,0 +1,275 @@
+"""Per-kernel parity: every C-ABI entry point against a CPU fp64 restatement of
+the same ATen op the reference dispatches to, fp32 and bf16.
+
+Tolerances (norm-wise relative error, written here on purpose):
+  fp32 kernels : 1e-5  (north_star bound for fp32)
+  bf16 kernels : 6e-3 per op against fp64 math on the bf16-rounded inputs
+                 (one bf16 output rounding is 2^-9 = 2e-3 per element)
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.vae_oracle import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 6e-3}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+@pytest.fixture(scope="module")
+def tv():
+    import torch_vae_b200 as m
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.load_library()
+    return m
+
+
+def dev(t):
+    return t.cuda()
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def q(t, dtype):
+    """Round to the compute dtype and come back to fp64 (what the kernel sees)."""
+    return t.to(dtype).double()
+
+
+CONV_CASES = [
+    # B, H, W, Ci, Co, stride
+    (2, 16, 16, 32, 64, 2),
+    (3, 8, 24, 64, 128, 2),
+    (2, 8, 8, 128, 256, 2),
+    (2, 16, 16, 8, 16, 2),
+    (2, 12, 20, 24, 40, 2),  # channel counts that are not powers of two
+    (2, 32, 32, 1, 32, 2),  # enc.conv0 edge kernel
+    (2, 16, 16, 3, 16, 2),  # multi-channel image through the generic kernel
+    (2, 16, 24, 32, 1, 1),  # final conv edge kernel
+    (1, 8, 8, 16, 16, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(tv, case, dtype):
+    B, H, W, Ci, Co, s = case
+    ops = tv.ops
+    x = rnd(B, Ci, H, W, seed=1)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))
+    b = rnd(Co, seed=3, scale=0.1)
+    in_dtype = torch.float32 if Ci in (1, 3) else dtype  # the image itself is always fp32
+    xq, wq = q(x, in_dtype), q(w, dtype)
+    y_ref = F.conv2d(xq, wq, b.double(), stride=s, padding=1)
+
+    wp, wt = ops.pack_conv_weight(dev(w), dtype)
+    stats = torch.empty(2 * Co, dtype=torch.float64, device="cuda")
+    x_dev = dev(nhwc(x)).to(in_dtype)
+    y = ops.conv_fprop(x_dev, wp, dev(b), s, dtype, stats if Co > 1 else None, Ci=Ci)
+    assert y.shape == (B, H // s, W // s, Co)
+    assert rel_err(nchw(y.float().cpu()), y_ref) < TOL[dtype]
+    if Co > 1:
+        st = stats.cpu()
+        assert rel_err(st[:Co], y_ref.sum(dim=(0, 2, 3))) < 1e-3 + TOL[dtype]
+        assert rel_err(st[Co:], (y_ref**2).sum(dim=(0, 2, 3))) < 1e-3 + TOL[dtype]
+
+    # data gradient == conv_transpose2d of dy with the same weight
+    dy = rnd(B, Co, H // s, W // s, seed=4)
+    dyq = q(dy, dtype)
+    dx_ref = F.conv_transpose2d(dyq, wq, None, stride=s, padding=1, output_padding=s - 1)
+    bias_t = rnd(Ci, seed=5, scale=0.1)
+    stats2 = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
+    dx = ops.conv_dgrad(dev(nhwc(dy)).to(dtype), wt, dev(bias_t), s, stats2)
+    dx_ref_b = dx_ref + bias_t.double().view(1, -1, 1, 1)
+    assert dx.shape == (B, H, W, Ci)
+    assert rel_err(nchw(dx.float().cpu()), dx_ref_b) < TOL[dtype]
+    assert rel_err(stats2.cpu()[:Ci], dx_ref_b.sum(dim=(0, 2, 3))) < 1e-3 + TOL[dtype]
+
+    # weight gradient
+    xr = xq.clone().requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, stride=s, padding=1).backward(dyq)
+    dw = ops.conv_wgrad(x_dev, dev(nhwc(dy)).to(dtype), s, Ci, Co, H, W)
+    assert dw.shape == (Co, Ci, 3, 3) and dw.dtype == torch.float32
+    assert rel_err(dw.cpu(), wr.grad) < (1e-5 if dtype == torch.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,n_pix_shape", [(32, (4, 16, 16)), (8, (2, 8, 8)), (24, (3, 4, 6)), (20, (2, 4, 4))])
+def test_batchnorm_lrelu_forward_backward(tv, C, n_pix_shape, dtype):
+    ops = tv.ops
+    B, H, W = n_pix_shape
+    y = rnd(B, C, H, W, seed=1, scale=2.0) + 0.3
+    gamma, beta = rnd(C, seed=2) * 0.2 + 1.0, rnd(C, seed=3) * 0.1
+    dact = rnd(B, C, H, W, seed=4)
+    yq, dq = q(y, dtype), q(dact, dtype)
+    rm, rv = torch.zeros(C), torch.ones(C)
+
+    yr = yq.clone().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = rm.double().clone(), rv.double().clone()
+    a_ref = F.leaky_relu(F.batch_norm(yr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5), 0.01)
+    a_ref.backward(dq)
+
+    y_dev = dev(nhwc(y)).to(dtype)
+    stats = torch.stack([yq.sum(dim=(0, 2, 3)), (yq**2).sum(dim=(0, 2, 3))]).flatten().cuda()
+    rm_d, rv_d = dev(rm), dev(rv)
+    vec = ops.bn_finalize(stats, dev(gamma), dev(beta), rm_d, rv_d, B * H * W, True)
+    assert rel_err(rm_d.cpu(), rm_ref) < 1e-5 and rel_err(rv_d.cpu(), rv_ref) < 1e-5
+    act = ops.bn_apply_lrelu(y_dev, vec)
+    assert rel_err(nchw(act.float().cpu()), a_ref) < TOL[dtype]
+    dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(dev(nhwc(dact)).to(dtype), y_dev, vec, dev(gamma), True)
+    assert rel_err(nchw(dy.float().cpu()), yr.grad) < max(TOL[dtype], 2e-5)
+    assert rel_err(dgamma.cpu(), gr.grad) < 2e-5 and rel_err(dbeta.cpu(), br.grad) < 2e-5
+    assert float(dbias.abs().max()) < 1e-3 * float(yr.grad.abs().sum())
+
+    # eval mode: running statistics
+    vec_e = ops.bn_finalize(None, dev(gamma), dev(beta), rm_d, rv_d, B * H * W, False)
+    a_eval = F.leaky_relu(F.batch_norm(yq, rm_ref, rv_ref, gamma.double(), beta.double(), False, 0.1, 1e-5), 0.01)
+    assert rel_err(nchw(ops.bn_apply_lrelu(y_dev, vec_e).float().cpu()), a_eval) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layout_transposes(tv, dtype):
+    ops = tv.ops
+    x = rnd(3, 40, 6, 10, seed=1).to(dtype)
+    flat = ops.nhwc_to_nchw(dev(nhwc(x)))
+    assert torch.equal(flat.cpu(), x.flatten(1))
+    back = ops.nchw_to_nhwc(dev(x.flatten(1)), 40, 6, 10)
+    assert torch.equal(back.cpu(), nhwc(x))
+    assert torch.equal(ops.nhwc_to_nchw(dev(nhwc(x)), torch.float32).cpu(), x.flatten(1).float())
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,K,N", [(8, 1024, 10), (64, 16384, 10), (5, 300, 33), (16, 10, 1024)])
+def test_linear_forward_backward(tv, dtype, B, K, N):
+    ops = tv.ops
+    x, w, b = rnd(B, K, seed=1), rnd(N, K, seed=2, scale=1 / math.sqrt(K)), rnd(N, seed=3)
+    dout = rnd(B, N, seed=4)
+    xq = q(x, dtype)
+    y = ops.linear_fwd(dev(x).to(dtype), dev(w), dev(b), torch.float32)
+    assert rel_err(y.cpu(), F.linear(xq, w.double(), b.double())) < 1e-5
+    y2 = ops.linear_fwd(dev(x), dev(w), dev(b), dtype)  # fp32 in, compute-dtype out (decoder_input)
+    assert rel_err(y2.float().cpu(), F.linear(x.double(), w.double(), b.double())) < TOL[dtype]
+    dx = ops.linear_bwd_input(dev(dout), dev(w), out_dtype=dtype)
+    assert rel_err(dx.float().cpu(), dout.double() @ w.double()) < TOL[dtype]
+    ops.linear_bwd_input(dev(dout), dev(w), out=dx, accumulate=True)
+    assert rel_err(dx.float().cpu(), 2 * (dout.double() @ w.double())) < 2 * TOL[dtype]
+    dw = ops.linear_bwd_weight(dev(dout), dev(x).to(dtype))
+    assert rel_err(dw.cpu(), dout.double().t() @ xq) < 1e-5
+    assert rel_err(ops.colsum(dev(dout)).cpu(), dout.double().sum(0)) < 1e-5
+    assert rel_err(ops.colsum(dev(x).to(dtype)).cpu(), xq.sum(0)) < 1e-5
+
+
+def test_reparam_injected_and_philox(tv):
+    ops = tv.ops
+    mu, lv, eps = rnd(7, 10, seed=1), rnd(7, 10, seed=2), rnd(7, 10, seed=3)
+    z, e = ops.reparam_fwd(dev(mu), dev(lv), dev(eps))
+    assert rel_err(z.cpu(), eps.double() * torch.exp(0.5 * lv.double()) + mu.double()) < 1e-6
+    dz = rnd(7, 10, seed=4)
+    dmu, dlv = ops.reparam_bwd(dev(dz), dev(eps), dev(lv))
+    assert torch.equal(dmu.cpu(), dz)
+    assert rel_err(dlv.cpu(), dz.double() * eps.double() * 0.5 * torch.exp(0.5 * lv.double())) < 1e-6
+
+    n = 1 << 20
+    a = ops.philox_randn(n, 1234, 0, "cuda")
+    b = ops.philox_randn(n, 1234, 0, "cuda")
+    c = ops.philox_randn(n, 1234, n // 4, "cuda")
+    d = ops.philox_randn(n, 1235, 0, "cuda")
+    assert torch.equal(a, b), "(seed, offset) must reproduce the stream"
+    assert not torch.equal(a, c) and not torch.equal(a, d)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1.0) < 5e-3
+    assert abs(float((a**4).mean()) - 3.0) < 0.05  # kurtosis of N(0,1)
+    assert abs(float((a * c).mean())) < 5e-3  # consecutive blocks uncorrelated
+    # device-side offset (CUDA-graph replays) equals the host-side offset
+    off = torch.tensor([n // 4], dtype=torch.int64, device="cuda")
+    zero = torch.zeros(n, device="cuda")
+    z_off, _ = ops.reparam_fwd(zero, zero, None, seed=1234, offset=0, dev_offset=off)
+    assert torch.equal(z_off, c)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kldw", [1.0, 0.00025])
+def test_fused_elbo_matches_reference_semantics(tv, dtype, kldw):
+    ops = tv.ops
+    B, L, H, W = 6, 10, 16, 24
+    logits = rnd(B, 1, H, W, seed=1, scale=3.0)
+    logits[0, 0, 0, :4] = torch.tensor([25.0, -25.0, 110.0, -110.0])  # saturation / clamp edge
+    x = (torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(2)) < 0.3).float()
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.0, 1.0])
+    mu, lv = rnd(B, L, seed=3), rnd(B, L, seed=4) * 0.5
+    lq = logits.to(dtype).float()
+
+    # reference semantics in fp32 ATen on the CPU: sigmoid -> binary_cross_entropy (+ KL)
+    lr = lq.clone().requires_grad_(True)
+    mr, vr = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    recon = F.binary_cross_entropy(torch.sigmoid(lr), x)
+    kld = -0.5 * torch.mean(torch.sum(1 + vr - mr**2 - torch.exp(vr), dim=-1))
+    loss = recon + kldw * kld
+    (loss * 1.7).backward()
+
+    ld = dev(logits).to(dtype)
+    losses = ops.elbo_fwd(ld, dev(x), dev(mu), dev(lv), kldw, False).cpu()
+    assert abs(float(losses[0]) - float(loss)) <= 2e-6 * abs(float(loss)) + 1e-7
+    assert abs(float(losses[1]) - float(recon)) <= 2e-6 * abs(float(recon)) + 1e-7
+    assert abs(float(losses[2]) + float(kld)) <= 2e-6 * abs(float(kld)) + 1e-7  # sign-flipped
+    g = torch.tensor(1.7, device="cuda")
+    dl, dmu, dlv = ops.elbo_bwd(ld, dev(x), dev(mu), dev(lv), g, kldw, False)
+    assert rel_err(dl.float().cpu(), lr.grad) < TOL[dtype]
+    assert rel_err(dmu.cpu(), mr.grad) < 1e-5 and rel_err(dlv.cpu(), vr.grad) < 1e-5
+
+    # probabilities path (hand-built ModelOutput): BCE on p directly
+    p = torch.sigmoid(lq)
+    pr = p.clone().requires_grad_(True)
+    (F.binary_cross_entropy(pr, x) * 1.7).backward()
+    lp = ops.elbo_fwd(dev(p), dev(x), dev(mu), dev(lv), kldw, True).cpu()
+    assert abs(float(lp[1]) - float(recon)) <= 2e-6 * abs(float(recon)) + 1e-7
+    dp, _, _ = ops.elbo_bwd(dev(p), dev(x), dev(mu), dev(lv), g, kldw, True)
+    assert rel_err(dp.cpu(), pr.grad) < 1e-5
+
+
+def test_sigmoid_and_backward(tv):
+    ops = tv.ops
+    l = rnd(4, 1, 8, 8, seed=1, scale=4.0)
+    p = ops.sigmoid(dev(l))
+    assert rel_err(p.cpu(), torch.sigmoid(l.double())) < 1e-6
+    dp = rnd(4, 1, 8, 8, seed=2)
+    dl = ops.sigmoid_bwd(dev(dp), p)
+    pd = torch.sigmoid(l.double())
+    assert rel_err(dl.cpu(), dp.double() * pd * (1 - pd)) < 1e-5
+
+
+def test_roll_transform_matches_midi_stack(tv):
+    """data_transformations.py:48-72: crop -> /255 -> Normalize(0.5, 1.0)."""
+    ops = tv.ops
+    g = torch.Generator().manual_seed(0)
+    rolls = ((torch.rand(5, 128, 160, generator=g) < 0.1) * 255).to(torch.uint8)
+    out = ops.roll_transform(dev(rolls), 128, 128, 0, 0, -1.0, 0.5, 1.0, 0, 0).cpu()
+    ref = rolls[:, :, 16:144].float().div(255).sub(0.5).unsqueeze(1)  # CenterCrop: left = round(32/2)
+    assert torch.equal(out, ref)
+    # random crop: every sample is SOME window of its source; reproducible in (seed, offset)
+    o1 = ops.roll_transform(dev(rolls), 128, 128, 1, 0, 0.5, 0.0, 1.0, 7, 3).cpu()
+    o2 = ops.roll_transform(dev(rolls), 128, 128, 1, 0, 0.5, 0.0, 1.0, 7, 3).cpu()
+    assert torch.equal(o1, o2)
+    for b in range(5):
+        wins = rolls[b].unfold(1, 128, 1).permute(1, 0, 2)  # [33,128,128]
+        assert any(torch.equal(o1[b, 0], (w > 127).float()) for w in wins)
+    # pitch transpose keeps the note count inside the window or drops rows off the edge
+    o3 = ops.roll_transform(dev(rolls), 128, 128, 0, 6, 0.5, 0.0, 1.0, 11, 0).cpu()
+    assert set(o3.unique().tolist()) <= {0.0, 1.0}
+    assert float(o3.sum()) <= float((rolls[:, :, 16:144] > 127).sum()) + 1e-3

@@ -1,0 +1,17 @@
+"""Public surface of the B200-native VanillaVAE training path."""
+
+from . import engine, ops  # noqa: F401
+from ._lib import LIB_PATH, load as load_library  # noqa: F401
+from .models import VanillaVAE
+from .types_helpers import EncoderOutput, LossOutput, ModelOutput
+
+__all__ = [
+    "VanillaVAE",
+    "EncoderOutput",
+    "ModelOutput",
+    "LossOutput",
+    "ops",
+    "engine",
+    "load_library",
+    "LIB_PATH",
+]

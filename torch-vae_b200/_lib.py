@@ -1,0 +1,74 @@
+"""ctypes binding of the C-ABI library ``libvae_b200.so`` (include/vae_b200.h).
+
+There is no CPU fallback: if the library is missing, or an op is called
+without a CUDA device, a RuntimeError is raised (the reference's own error
+convention for bad shapes is torch's RuntimeError).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvae_b200.so")
+
+_vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+PROTOTYPES = {
+    "vae_abi_version": [],
+    "vae_last_error": [],
+    "vae_has_umma": [],
+    "vae_pack_conv_weight": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "vae_conv_fprop": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_conv_dgrad": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_bn_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp],
+    "vae_bn_apply_lrelu": [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
+    "vae_bn_lrelu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
+    "vae_bn_lrelu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp],
+    "vae_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vae_nchw_to_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vae_gemm": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp],
+    "vae_colsum": [_vp, _vp, _i, _i, _i, _vp],
+    "vae_philox_randn": [_vp, _ll, _ull, _ull, _vp],
+    "vae_reparam_fwd": [_vp, _vp, _vp, _vp, _vp, _ll, _ull, _ull, _vp, _vp],
+    "vae_reparam_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
+    "vae_elbo_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _i, _vp],
+    "vae_elbo_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _i, _vp],
+    "vae_sigmoid": [_vp, _vp, _ll, _i, _vp],
+    "vae_sigmoid_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp],
+    "vae_roll_transform": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _ull, _ull, _vp],
+}
+_RESTYPES = {"vae_last_error": C.c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or torch-vae_b200/csrc/build.sh). "
+            "torch_vae_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.vae_abi_version() != 1:
+        raise RuntimeError("libvae_b200.so ABI version mismatch; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().vae_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

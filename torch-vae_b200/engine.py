@@ -1,0 +1,262 @@
+"""Forward / backward schedules of the VAE hot path as autograd Functions.
+
+The reference runs ``models.py:185-188`` (forward), ``:190-225`` (loss) and
+autograd's backward (``train.py:650``) as ~120 ATen ops.  Here each of the four
+pieces -- encode, reparameterize, decode, ELBO -- is ONE autograd node whose
+forward and backward are explicit schedules of the sm_100a kernels behind
+``include/vae_b200.h``:
+
+  activations NHWC in the compute dtype (fp32 or bf16), accumulators fp32,
+  BatchNorm statistics fp64, parameters and their gradients fp32 in the
+  reference layouts (OIHW / [out,in]).
+
+ConvTranspose2d(k3,s2,p1,op1) forward IS the data-gradient of the equivalent
+Conv2d(k3,s2,p1), so three kernel families (fprop, dgrad,
+wgrad) cover all nine conv layers in both directions.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+
+class ConvBlockSpec:
+    """Static description of one conv(+BN+LeakyReLU) block."""
+
+    __slots__ = ("transposed", "ci", "co", "bn")
+
+    def __init__(self, transposed: bool, ci: int, co: int, bn):
+        self.transposed = transposed  # True: ConvTranspose2d (runs the dgrad kernel forward)
+        self.ci = ci  # channels on the HIGH-resolution side of the equivalent conv
+        self.co = co  # channels on the LOW-resolution side
+        self.bn = bn  # nn.BatchNorm2d holding running stats (buffers are not autograd inputs)
+
+
+def _bn_forward(y, stats, gamma, beta, bn, training: bool):
+    count = y.numel() // y.shape[-1]
+    use_batch = training or bn.running_mean is None
+    vec = ops.bn_finalize(
+        stats if use_batch else None, gamma, beta, bn.running_mean, bn.running_var, count, use_batch,
+        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps,
+    )
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return vec, ops.bn_apply_lrelu(y, vec)
+
+
+class EncodeFn(torch.autograd.Function):
+    """encoder convs -> flatten -> fc_mu / fc_var  (models.py:107-145)."""
+
+    @staticmethod
+    def forward(ctx, specs: List[ConvBlockSpec], dtype, training, sink, x, w_mu, b_mu, w_var, b_var, *conv_params):
+        ctx.set_materialize_grads(False)
+        ctx.sink = sink
+        B, Cin = x.shape[0], x.shape[1]
+        h = x.contiguous()
+        if h.dtype != torch.float32:
+            h = h.float()
+        Hi, Wi = h.shape[2], h.shape[3]
+        if Cin > 1:  # NCHW image -> NHWC; with one channel the two layouts coincide
+            h = ops.nchw_to_nhwc(h.view(B, -1), Cin, Hi, Wi)
+        saved = []
+        for i, sp in enumerate(specs):
+            w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
+            wp, wt = ops.pack_conv_weight(w, dtype, want_wp=True, want_wt=True)
+            stats = torch.empty(2 * sp.co, dtype=torch.float64, device=h.device) if training else None
+            y = ops.conv_fprop(h, wp, b, 2, dtype, stats, Ci=sp.ci)
+            vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
+            saved.append((h, y, vec, wt, Hi, Wi))
+            h = act
+            Hi, Wi = Hi // 2, Wi // 2
+        pre = ops.nhwc_to_nchw(h)  # [B, C*h*w], C-major like x.flatten(1) (models.py:133)
+        mu = ops.linear_fwd(pre, w_mu, b_mu, torch.float32)
+        log_var = ops.linear_fwd(pre, w_var, b_var, torch.float32)
+        ctx.specs, ctx.training, ctx.saved, ctx.feat = specs, training, saved, (specs[-1].co, Hi, Wi)
+        ctx.save_for_backward(pre, w_mu, w_var, b_mu, b_var, *conv_params)
+        ctx.x_needs_grad = x.requires_grad
+        return mu, log_var, pre
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dmu, dlv, dpre):
+        pre, w_mu, w_var, b_mu, b_var, *conv_params = ctx.saved_tensors
+        specs, saved, sink = ctx.specs, ctx.saved, ctx.sink
+        dev = pre.device
+        B, L = pre.shape[0], w_mu.shape[0]
+        if dmu is None:
+            dmu = torch.zeros((B, L), dtype=torch.float32, device=dev)
+        if dlv is None:
+            dlv = torch.zeros((B, L), dtype=torch.float32, device=dev)
+        dmu, dlv = dmu.contiguous(), dlv.contiguous()
+        d_pre = ops.linear_bwd_input(dmu, w_mu, out_dtype=pre.dtype)
+        ops.linear_bwd_input(dlv, w_var, out=d_pre, accumulate=True)
+        if dpre is not None:
+            d_pre = d_pre + dpre.to(d_pre.dtype)
+        g_w_mu, g_b_mu = ops.linear_bwd_weight(dmu, pre), ops.colsum(dmu)
+        g_w_var, g_b_var = ops.linear_bwd_weight(dlv, pre), ops.colsum(dlv)
+        if sink is not None:
+            for p_, g_ in ((w_mu, g_w_mu), (b_mu, g_b_mu), (w_var, g_w_var), (b_var, g_b_var)):
+                sink.push(p_, g_)
+        C, h, w = ctx.feat
+        d_act = ops.nchw_to_nhwc(d_pre, C, h, w)
+        conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
+        dx = None
+        for i in range(len(specs) - 1, -1, -1):
+            sp = specs[i]
+            h_in, y, vec, wt, Hi, Wi = saved[i]
+            gamma = conv_params[4 * i + 2]
+            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
+            conv_grads[4 * i] = ops.conv_wgrad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
+            conv_grads[4 * i + 1] = dbias
+            conv_grads[4 * i + 2] = dgamma
+            conv_grads[4 * i + 3] = dbeta
+            if sink is not None:
+                for k in range(4):
+                    sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
+            if i > 0:
+                d_act = ops.conv_dgrad(dy, wt, None, 2)
+            elif ctx.x_needs_grad:
+                dx = ops.nhwc_to_nchw(ops.conv_dgrad(dy, wt, None, 2), torch.float32).view(B, sp.ci, Hi, Wi)
+        ctx.saved = None
+        return (None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
+
+
+class ReparamFn(torch.autograd.Function):
+    """z = mu + eps * exp(0.5 * log_var)  (models.py:177-183)."""
+
+    @staticmethod
+    def forward(ctx, mu, log_var, eps, seed, dev_offset):
+        mu, log_var = mu.contiguous(), log_var.contiguous()
+        if eps is not None:
+            eps = eps.to(device=mu.device, dtype=torch.float32).contiguous()
+        z, eps_used = ops.reparam_fwd(mu, log_var, eps, seed=seed, offset=0, dev_offset=dev_offset)
+        if dev_offset is not None and eps is None:
+            dev_offset.add_((mu.numel() + 3) // 4)  # advance the Philox counter (graph-capturable)
+        ctx.save_for_backward(eps_used, log_var)
+        return z
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dz):
+        eps, log_var = ctx.saved_tensors
+        dmu, dlv = ops.reparam_bwd(dz.contiguous(), eps, log_var)
+        return dmu, dlv, None, None, None
+
+
+class DecodeFn(torch.autograd.Function):
+    """decoder_input -> view -> ConvT blocks -> final ConvT/BN/LReLU/Conv -> sigmoid
+    (models.py:147-175).  Returns (probabilities fp32, logits in compute dtype)."""
+
+    @staticmethod
+    def forward(ctx, specs: List[ConvBlockSpec], feat, dtype, training, sink, z, w_in, b_in, w_last, b_last, *conv_params):
+        ctx.set_materialize_grads(False)
+        ctx.sink = sink
+        z = z.contiguous()
+        if z.dtype != torch.float32:
+            z = z.float()
+        B = z.shape[0]
+        C, h0, w0 = feat
+        d = ops.linear_fwd(z, w_in, b_in, dtype)  # [B, C*h*w], C-major
+        h = ops.nchw_to_nhwc(d, C, h0, w0)
+        saved = []
+        for i, sp in enumerate(specs):
+            w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
+            wp, wt = ops.pack_conv_weight(w, dtype, want_wp=True, want_wt=True)
+            stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
+            y = ops.conv_dgrad(h, wt, b, 2, stats)  # ConvTranspose2d forward
+            vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
+            saved.append((h, y, vec, wp))
+            h = act
+        wp3, wt3 = ops.pack_conv_weight(w_last, dtype, want_wp=True, want_wt=True)
+        logits = ops.conv_fprop(h, wp3, b_last, 1, dtype)  # [B,H,W,1]
+        H, W = logits.shape[1], logits.shape[2]
+        probs = ops.sigmoid(logits).view(B, 1, H, W)
+        logits = logits.view(B, 1, H, W)
+        ctx.specs, ctx.training, ctx.saved, ctx.last = specs, training, saved, (h, wt3)
+        ctx.save_for_backward(z, w_in, probs, b_in, w_last, b_last, *conv_params)
+        ctx.z_needs_grad = z.requires_grad
+        return probs, logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dprobs, dlogits):
+        z, w_in, probs, b_in, w_last, b_last, *conv_params = ctx.saved_tensors
+        specs, saved, sink = ctx.specs, ctx.saved, ctx.sink
+        act_last, wt3 = ctx.last
+        B, _, H, W = probs.shape
+        dtype = act_last.dtype
+        if dlogits is not None:
+            dlog = dlogits.contiguous()
+            if dprobs is not None:
+                dlog = ops.sigmoid_bwd(dprobs.contiguous(), probs, dlogits=dlog.clone())
+        elif dprobs is not None:
+            dlog = ops.sigmoid_bwd(dprobs.contiguous(), probs, dtype=dtype)
+        else:
+            dlog = torch.zeros((B, 1, H, W), dtype=dtype, device=probs.device)
+        dlog = dlog.view(B, H, W, 1)
+        c_last = act_last.shape[-1]
+        # final Conv2d(C -> 1): bias grad is a plain sum, done as two column sums
+        n = dlog.numel()
+        cols = 256 if n % 256 == 0 else 1
+        g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1))
+        g_w_last = ops.conv_wgrad(act_last, dlog, 1, c_last, 1, H, W)
+        if sink is not None:
+            sink.push(w_last, g_w_last)
+            sink.push(b_last, g_b_last)
+        d_act = ops.conv_dgrad(dlog, wt3, None, 1)
+        conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
+        for i in range(len(specs) - 1, -1, -1):
+            sp = specs[i]
+            h_in, y, vec, wp = saved[i]
+            gamma = conv_params[4 * i + 2]
+            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
+            Hi, Wi = y.shape[1], y.shape[2]
+            # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
+            conv_grads[4 * i] = ops.conv_wgrad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)
+            conv_grads[4 * i + 1] = dbias
+            conv_grads[4 * i + 2] = dgamma
+            conv_grads[4 * i + 3] = dbeta
+            if sink is not None:
+                for k in range(4):
+                    sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
+            d_act = ops.conv_fprop(dy, wp, None, 2, dtype)  # gradient w.r.t. the ConvT input
+        d_d = ops.nhwc_to_nchw(d_act)  # [B, F] C-major, matching decoder_input's output
+        g_w_in = ops.linear_bwd_weight(d_d, z)
+        g_b_in = ops.colsum(d_d)
+        if sink is not None:
+            sink.push(w_in, g_w_in)
+            sink.push(b_in, g_b_in)
+        dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32) if ctx.z_needs_grad else None
+        ctx.saved = None
+        ctx.last = None
+        return (None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
+
+
+class ElboFn(torch.autograd.Function):
+    """loss = mean BCE(sigmoid(logits), x) + kld_weight * KL  (models.py:190-225)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mu, log_var, kld_weight: float, input_is_prob: bool):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        if target.dtype != torch.float32:
+            target = target.float()
+        mu, log_var = mu.contiguous(), log_var.contiguous()
+        losses = ops.elbo_fwd(pred, target, mu, log_var, kld_weight, input_is_prob)
+        ctx.save_for_backward(pred, target, mu, log_var)
+        ctx.kld_weight, ctx.input_is_prob = kld_weight, input_is_prob
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _unused):
+        pred, target, mu, log_var = ctx.saved_tensors
+        g = g.to(torch.float32).contiguous()
+        dpred, dmu, dlv = ops.elbo_bwd(pred, target, mu, log_var, g, ctx.kld_weight, ctx.input_is_prob)
+        return dpred, None, dmu, dlv, None, None

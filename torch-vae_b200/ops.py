@@ -1,0 +1,362 @@
+"""Thin torch-tensor wrappers over the C ABI (include/vae_b200.h).
+
+Every wrapper checks device / dtype / contiguity, passes raw device pointers
+and the CURRENT torch CUDA stream, and raises RuntimeError on failure.  Device
+memory always comes from torch's caching allocator (SURVEY.md §8b "Ownership").
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+_CODES = {torch.float32: F32, torch.bfloat16: BF16}
+LRELU_SLOPE = 0.01  # nn.LeakyReLU() default, models.py:47
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# ---------------------------------------------------------------- call plumbing
+LAUNCHES = 0  # number of C-ABI kernel launches issued by this process
+_TRACE = None  # optional Timeline
+
+
+class Timeline:
+    """CUDA-event timing of individual C-ABI launches on the launching stream.
+
+    ``only`` restricts the bracketing to one (name, tag) so the timed region of
+    bench.py is perturbed by two event records per step, not hundreds."""
+
+    def __init__(self, only=None):
+        self.only = only
+        self.records = {}  # (name, tag) -> list[(start, end)]
+
+    def run(self, name, fn, args):
+        tag = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool) and -1 <= a < (1 << 31))
+        key = (name, tag)
+        if self.only is not None and key != self.only:
+            return fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        self.records.setdefault(key, []).append((s, e))
+        return rc
+
+    def summary(self):
+        """-> {(name, tag): (n_launches, total_ms)} ; call after a synchronize."""
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in self.records.items()}
+
+
+def set_timeline(tl):
+    global _TRACE
+    _TRACE = tl
+
+
+class _Proxy:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+
+        def call(*args):
+            global LAUNCHES
+            LAUNCHES += 1
+            tr = _TRACE
+            return fn(*args) if tr is None else tr.run(name, fn, args)
+
+        setattr(self, name, call)
+        return call
+
+
+_PROXY = None
+
+
+def _L():
+    global _PROXY
+    if _PROXY is None:
+        _PROXY = _Proxy(_lib.load())
+    return _PROXY
+
+
+def code(t) -> int:
+    dt = t if isinstance(t, torch.dtype) else t.dtype
+    try:
+        return _CODES[dt]
+    except KeyError:
+        raise RuntimeError(f"torch_vae_b200: unsupported dtype {dt} (float32 / bfloat16 only)")
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("torch_vae_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("torch_vae_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: Optional[torch.Tensor], what: str):
+    if t is not None and t.dtype != torch.float32:
+        raise RuntimeError(f"{what} must be float32, got {t.dtype}")
+    return _p(t)
+
+
+# ------------------------------------------------------------------ conv engine
+def pack_conv_weight(w: torch.Tensor, dtype: torch.dtype, want_wp=True, want_wt=True):
+    """OIHW fp32 -> (wp[Co,3,3,Ci], wt[Ci,3,3,Co]) in ``dtype``."""
+    Co, Ci = w.shape[0], w.shape[1]
+    wp = torch.empty((Co, 3, 3, Ci), dtype=dtype, device=w.device) if want_wp else None
+    wt = torch.empty((Ci, 3, 3, Co), dtype=dtype, device=w.device) if want_wt else None
+    rc = _L().vae_pack_conv_weight(_f32(w, "conv weight"), _p(wp), _p(wt), Co, Ci, code(dtype), _stream())
+    _lib.check(rc, "vae_pack_conv_weight")
+    return wp, wt
+
+
+def conv_fprop(x, wp, bias, stride: int, out_dtype, stats=None, Ci: Optional[int] = None):
+    """x NHWC [B,Hi,Wi,Ci] (or [B,1,H,W]/[B,H,W] when Ci == 1) -> y NHWC."""
+    if Ci is None:
+        Ci = x.shape[-1]
+    if Ci == 1 and x.dim() == 4 and x.shape[1] == 1 and x.shape[-1] != 1:
+        B, Hi, Wi = x.shape[0], x.shape[2], x.shape[3]  # NCHW with C == 1 is NHWC
+    else:
+        B, Hi, Wi = x.shape[0], x.shape[1], x.shape[2]
+    Co = wp.shape[0]
+    y = torch.empty((B, Hi // stride, Wi // stride, Co), dtype=out_dtype, device=x.device)
+    rc = _L().vae_conv_fprop(
+        _p(x), _p(wp), _f32(bias, "bias"), _p(y), _p(stats), B, Hi, Wi, Ci, Co, stride,
+        code(x), code(out_dtype), _stream(),
+    )
+    _lib.check(rc, "vae_conv_fprop")
+    return y
+
+
+def conv_dgrad(dy, wt, bias, stride: int, stats=None):
+    """dy NHWC [B,Ho,Wo,Co], wt [Ci,3,3,Co] -> dx NHWC [B,Ho*s,Wo*s,Ci]."""
+    B, Ho, Wo, Co = dy.shape
+    Ci = wt.shape[0]
+    dx = torch.empty((B, Ho * stride, Wo * stride, Ci), dtype=dy.dtype, device=dy.device)
+    rc = _L().vae_conv_dgrad(
+        _p(dy), _p(wt), _f32(bias, "bias"), _p(dx), _p(stats), B, Ho * stride, Wo * stride, Ci, Co,
+        stride, code(dy), _stream(),
+    )
+    _lib.check(rc, "vae_conv_dgrad")
+    return dx
+
+
+def conv_wgrad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int):
+    """-> dw [Co,Ci,3,3] fp32 (reference OIHW layout)."""
+    B = dy.shape[0]
+    dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+    rc = _L().vae_conv_wgrad(_p(x), _p(dy), _p(dw), B, Hi, Wi, Ci, Co, stride, code(x), code(dy), _stream())
+    _lib.check(rc, "vae_conv_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------- batch norm
+def bn_finalize(stats, gamma, beta, running_mean, running_var, count: int, training: bool,
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS):
+    C = gamma.numel()
+    vec = torch.empty((4, C), dtype=torch.float32, device=gamma.device)  # scale, shift, mean, rstd
+    rc = _L().vae_bn_finalize(
+        _p(stats), _f32(gamma, "bn weight"), _f32(beta, "bn bias"), _f32(running_mean, "running_mean"),
+        _f32(running_var, "running_var"), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(),
+        vec[3].data_ptr(), C, count, momentum, eps, 1 if training else 0, _stream(),
+    )
+    _lib.check(rc, "vae_bn_finalize")
+    return vec
+
+
+def bn_apply_lrelu(y, vec, slope: float = LRELU_SLOPE):
+    C = y.shape[-1]
+    act = torch.empty_like(y)
+    rc = _L().vae_bn_apply_lrelu(
+        _p(y), vec[0].data_ptr(), vec[1].data_ptr(), _p(act), y.numel() // C, C, slope, code(y), _stream()
+    )
+    _lib.check(rc, "vae_bn_apply_lrelu")
+    return act
+
+
+def bn_lrelu_backward(dact, y, vec, gamma, training: bool, slope: float = LRELU_SLOPE):
+    """-> (dy, dgamma, dbeta, dbias)."""
+    C = y.shape[-1]
+    n_pix = y.numel() // C
+    lib = _L()
+    dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    rc = lib.vae_bn_lrelu_bwd_reduce(
+        _p(dact), _p(y), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(),
+        _p(dstats), n_pix, C, slope, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_bn_lrelu_bwd_reduce")
+    dy = torch.empty_like(y)
+    small = torch.empty((3, C), dtype=torch.float32, device=y.device)
+    rc = lib.vae_bn_lrelu_bwd_apply(
+        _p(dact), _p(y), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(),
+        _f32(gamma, "bn weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
+        small[2].data_ptr(), n_pix, C, slope, 1 if training else 0, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_bn_lrelu_bwd_apply")
+    return dy, small[0], small[1], small[2]
+
+
+# ---------------------------------------------------------------- layout glue
+def nhwc_to_nchw(src, out_dtype=None):
+    """[B,H,W,C] -> [B, C*H*W] (the reference's C-major flatten, models.py:133)."""
+    B, H, W, Cc = src.shape
+    out_dtype = out_dtype or src.dtype
+    dst = torch.empty((B, Cc * H * W), dtype=out_dtype, device=src.device)
+    rc = _L().vae_nhwc_to_nchw(_p(src), _p(dst), B, H * W, Cc, code(src), code(out_dtype), _stream())
+    _lib.check(rc, "vae_nhwc_to_nchw")
+    return dst
+
+
+def nchw_to_nhwc(src, C: int, H: int, W: int, out_dtype=None):
+    """[B, C*H*W] -> [B,H,W,C] (the reference's view, models.py:166)."""
+    B = src.shape[0]
+    out_dtype = out_dtype or src.dtype
+    dst = torch.empty((B, H, W, C), dtype=out_dtype, device=src.device)
+    rc = _L().vae_nchw_to_nhwc(_p(src), _p(dst), B, H * W, C, code(src), code(out_dtype), _stream())
+    _lib.check(rc, "vae_nchw_to_nhwc")
+    return dst
+
+
+# ---------------------------------------------------------------------- linear
+def gemm(A, Bm, out, M, N, K, sa, sb, sc, bias=None, accumulate=False):
+    """out[M,N] (+)= A[M,K] @ B[K,N] with explicit (row, col) element strides."""
+    rc = _L().vae_gemm(
+        _p(A), _p(Bm), _p(out), _f32(bias, "bias"), M, N, K, sa[0], sa[1], sb[0], sb[1], sc[0], sc[1],
+        code(A), code(Bm), code(out), 1 if accumulate else 0, _stream(),
+    )
+    _lib.check(rc, "vae_gemm")
+    return out
+
+
+def linear_fwd(x, w, b, out_dtype):
+    """x[B,K] @ w[N,K]^T + b -> [B,N]   (aten::addmm, models.py:137,141,162)."""
+    Bn, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((Bn, N), dtype=out_dtype, device=x.device)
+    return gemm(x, w, out, Bn, N, K, (K, 1), (1, K), (N, 1), bias=b)
+
+
+def linear_bwd_input(dout, w, out=None, out_dtype=torch.float32, accumulate=False):
+    """dout[B,N] @ w[N,K] -> dx[B,K]."""
+    Bn, N = dout.shape
+    K = w.shape[1]
+    if out is None:
+        out = torch.empty((Bn, K), dtype=out_dtype, device=dout.device)
+    return gemm(dout, w, out, Bn, K, N, (N, 1), (K, 1), (K, 1), accumulate=accumulate)
+
+
+def linear_bwd_weight(dout, x):
+    """dout[B,N]^T @ x[B,K] -> dw[N,K] fp32."""
+    Bn, N = dout.shape
+    K = x.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    return gemm(dout, x, dw, N, K, Bn, (1, N), (K, 1), (K, 1))
+
+
+def colsum(A):
+    M, N = A.shape
+    out = torch.empty(N, dtype=torch.float32, device=A.device)
+    rc = _L().vae_colsum(_p(A), _p(out), M, N, code(A), _stream())
+    _lib.check(rc, "vae_colsum")
+    return out
+
+
+# --------------------------------------------------------------- reparam / rng
+def philox_randn(n: int, seed: int, offset: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    rc = _L().vae_philox_randn(_p(out), n, seed, offset, _stream())
+    _lib.check(rc, "vae_philox_randn")
+    return out
+
+
+def reparam_fwd(mu, logvar, eps, seed: int = 0, offset: int = 0, dev_offset=None):
+    z = torch.empty_like(mu)
+    eps_out = None if eps is not None else torch.empty_like(mu)
+    rc = _L().vae_reparam_fwd(
+        _f32(mu, "mu"), _f32(logvar, "log_var"), _f32(eps, "eps"), _p(eps_out), _p(z), mu.numel(),
+        seed, offset, _p(dev_offset), _stream(),
+    )
+    _lib.check(rc, "vae_reparam_fwd")
+    return z, (eps if eps is not None else eps_out)
+
+
+def reparam_bwd(dz, eps, logvar):
+    dmu = torch.empty_like(dz)
+    dlv = torch.empty_like(dz)
+    rc = _L().vae_reparam_bwd(_f32(dz, "dz"), _p(eps), _p(logvar), _p(dmu), _p(dlv), dz.numel(), 0, _stream())
+    _lib.check(rc, "vae_reparam_bwd")
+    return dmu, dlv
+
+
+# ------------------------------------------------------------------------ ELBO
+def elbo_fwd(logits, target, mu, logvar, kld_weight: float, input_is_prob: bool):
+    losses = torch.empty(3, dtype=torch.float32, device=logits.device)
+    scratch = torch.empty(4, dtype=torch.float64, device=logits.device)
+    B, L = mu.shape
+    rc = _L().vae_elbo_fwd(
+        _p(logits), _f32(target, "input"), _f32(mu, "mu"), _f32(logvar, "log_var"), _p(losses),
+        _p(scratch), logits.numel(), B, L, kld_weight, code(logits), 1 if input_is_prob else 0, _stream(),
+    )
+    _lib.check(rc, "vae_elbo_fwd")
+    return losses
+
+
+def elbo_bwd(logits, target, mu, logvar, gscale, kld_weight: float, input_is_prob: bool):
+    dlogits = torch.empty_like(logits)
+    dmu = torch.empty_like(mu)
+    dlv = torch.empty_like(mu)
+    B, L = mu.shape
+    rc = _L().vae_elbo_bwd(
+        _p(logits), _f32(target, "input"), _p(mu), _p(logvar), _f32(gscale, "grad"), _p(dlogits),
+        _p(dmu), _p(dlv), logits.numel(), B, L, kld_weight, code(logits), 1 if input_is_prob else 0,
+        _stream(),
+    )
+    _lib.check(rc, "vae_elbo_bwd")
+    return dlogits, dmu, dlv
+
+
+def sigmoid(logits):
+    probs = torch.empty(logits.shape, dtype=torch.float32, device=logits.device)
+    rc = _L().vae_sigmoid(_p(logits), _p(probs), logits.numel(), code(logits), _stream())
+    _lib.check(rc, "vae_sigmoid")
+    return probs
+
+
+def sigmoid_bwd(dprobs, probs, dlogits=None, dtype=torch.float32):
+    acc = dlogits is not None
+    if dlogits is None:
+        dlogits = torch.empty(probs.shape, dtype=dtype, device=probs.device)
+    rc = _L().vae_sigmoid_bwd(
+        _f32(dprobs, "grad of output"), _f32(probs, "output"), _p(dlogits), probs.numel(),
+        code(dlogits), 1 if acc else 0, _stream(),
+    )
+    _lib.check(rc, "vae_sigmoid_bwd")
+    return dlogits
+
+
+# ------------------------------------------------------------------ transforms
+def roll_transform(rolls, H: int, W: int, crop_mode: int, max_pitch_shift: int,
+                   binarize_threshold: float, mean: float, std: float, seed: int, offset: int):
+    if rolls.dtype != torch.uint8 or rolls.dim() != 3:
+        raise RuntimeError("roll_transform expects uint8 rolls of shape [B, Hs, Ws]")
+    B, Hs, Ws = rolls.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=rolls.device)
+    rc = _L().vae_roll_transform(
+        _p(rolls), _p(out), B, Hs, Ws, H, W, crop_mode, max_pitch_shift, binarize_threshold, mean, std,
+        seed, offset, _stream(),
+    )
+    _lib.check(rc, "vae_roll_transform")
+    return out
