@@ -84,6 +84,22 @@ int vae_conv_dgrad(const void* dy, const void* wt, const float* bias, void* dx, 
 int vae_conv_wgrad(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Ci,
                    int Co, int stride, int dt_x, int dt_dy, vae_stream_t stream);
 
+/* ---- tcgen05 / TMEM path (bf16; Cin_gemm % 32 == 0, 16 <= N <= 256, N % 16 == 0) ----
+ * mode 0 = conv forward, mode 1 = data gradient (== ConvTranspose2d forward).
+ * Weights are pre-packed once per optimizer step into the exact 128B-swizzled
+ * shared-memory images the kernel's bulk-TMA copies fetch. */
+int vae_set_umma(int enable); /* returns the previous setting; tests use it to cross-check */
+long long vae_umma_packed_elems(int Ci, int Co, int stride, int mode); /* 0: shape not served */
+int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
+                         vae_stream_t stream);
+/* in/out NHWC bf16.  Hi, Wi: HIGH-resolution extents (as in vae_conv_fprop/dgrad).
+ * pro_scale/pro_shift (nullable, fp32[C of `in`]) apply the PREVIOUS layer's
+ * BatchNorm+LeakyReLU to the operand while it is gathered (padding stays zero).
+ * replaces: aten::convolution / transposed convolution, models.py:45,66-68,77 */
+int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
+                  const float* pro_scale, const float* pro_shift, float slope, int B, int Hi, int Wi,
+                  int Ci, int Co, int stride, int mode, vae_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * BatchNorm2d (train and eval) + LeakyReLU.   models.py:46-47,69-70,78-79
  * ---------------------------------------------------------------------- */

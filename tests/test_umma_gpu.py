@@ -1,0 +1,112 @@
+"""tcgen05 / TMEM conv kernels against a CPU fp64 restatement (F.conv2d /
+F.conv_transpose2d on the bf16-rounded operands) and against the CUDA-core
+kernels of the same library.  Tolerance 6e-3 norm-wise (bf16 output rounding)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.vae_oracle import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 6e-3
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch_vae_b200 as tv
+
+    tv.load_library()
+    assert tv.ops.umma_available()
+    return tv.ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+CASES = [
+    # B, H, W, Ci, Co, stride   (H, W = high-resolution side)
+    (2, 16, 16, 32, 64, 2),
+    (3, 8, 24, 64, 128, 2),
+    (2, 8, 8, 128, 256, 2),
+    (2, 32, 32, 32, 32, 2),
+    (5, 16, 16, 64, 32, 2),
+    (1, 8, 8, 32, 64, 1),
+    (7, 48, 16, 96, 48, 2),  # not powers of two; M not a multiple of 128
+    (64, 64, 64, 32, 64, 2),  # many tiles per CTA: exercises the persistent loop + TMEM double buffer
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_umma_fprop(ops, case):
+    B, H, W, Ci, Co, s = case
+    x = rnd(B, Ci, H, W, seed=1)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))
+    b = rnd(Co, seed=3, scale=0.1)
+    xq, wq = x.bfloat16().double(), w.bfloat16().double()
+    ref = F.conv2d(xq, wq, b.double(), stride=s, padding=1)
+    wpk = ops.umma_pack_weight(w.cuda(), s, 0)
+    assert wpk is not None
+    stats = torch.empty(2 * Co, dtype=torch.float64, device="cuda")
+    y = ops.conv_umma(nhwc(x).cuda().bfloat16(), wpk, b.cuda(), stats, Ci, Co, s, 0)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(y.float().cpu()), ref) < TOL
+    assert rel_err(stats.cpu()[:Co], ref.sum(dim=(0, 2, 3))) < 2e-3
+    assert rel_err(stats.cpu()[Co:], (ref**2).sum(dim=(0, 2, 3))) < 2e-3
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_umma_dgrad_is_conv_transpose(ops, case):
+    B, H, W, Ci, Co, s = case
+    dy = rnd(B, Co, H // s, W // s, seed=4)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Co))
+    b = rnd(Ci, seed=5, scale=0.1)
+    ref = F.conv_transpose2d(dy.bfloat16().double(), w.bfloat16().double(), b.double(), stride=s, padding=1,
+                             output_padding=s - 1)
+    wpk = ops.umma_pack_weight(w.cuda(), s, 1)
+    assert wpk is not None
+    stats = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
+    dx = ops.conv_umma(nhwc(dy).cuda().bfloat16(), wpk, b.cuda(), stats, Ci, Co, s, 1)
+    torch.cuda.synchronize()
+    assert dx.shape == (B, H, W, Ci)
+    assert rel_err(nchw(dx.float().cpu()), ref) < TOL
+    assert rel_err(stats.cpu()[:Ci], ref.sum(dim=(0, 2, 3))) < 2e-3
+
+
+def test_umma_fused_bn_lrelu_prologue(ops):
+    B, H, W, Ci, Co, s = 4, 16, 16, 64, 128, 2
+    x = rnd(B, Ci, H, W, seed=1)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))
+    scale, shift = rnd(Ci, seed=6) * 0.3 + 1.0, rnd(Ci, seed=7) * 0.2
+    xq = x.bfloat16().double()
+    act = F.leaky_relu(xq * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1), 0.01)
+    ref = F.conv2d(act.bfloat16().double(), w.bfloat16().double(), None, stride=s, padding=1)
+    wpk = ops.umma_pack_weight(w.cuda(), s, 0)
+    vec = torch.stack([scale, shift, torch.zeros(Ci), torch.ones(Ci)]).cuda()
+    y = ops.conv_umma(nhwc(x).cuda().bfloat16(), wpk, None, None, Ci, Co, s, 0, pro=vec)
+    assert rel_err(nchw(y.float().cpu()), ref) < TOL
+
+
+def test_umma_matches_cuda_core_kernels_at_layer_sizes(ops):
+    """Same library, two kernel families, layer shapes of the default model."""
+    for (B, H, W, Ci, Co) in [(8, 64, 64, 32, 64), (8, 16, 16, 128, 256), (4, 128, 128, 32, 32)]:
+        x = rnd(B, H, W, Ci, seed=1).cuda().bfloat16()
+        w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci)).cuda()
+        wp, wt = ops.pack_conv_weight(w, torch.bfloat16)
+        y_simt = ops.conv_fprop(x, wp, None, 2, torch.bfloat16)
+        y_umma = ops.conv_umma(x, ops.umma_pack_weight(w, 2, 0), None, None, Ci, Co, 2, 0)
+        assert rel_err(y_umma.float(), y_simt.float()) < TOL
+        dy = rnd(B, H // 2, W // 2, Co, seed=3).cuda().bfloat16()
+        d_simt = ops.conv_dgrad(dy, wt, None, 2)
+        d_umma = ops.conv_umma(dy, ops.umma_pack_weight(w, 2, 1), None, None, Ci, Co, 2, 1)
+        assert rel_err(d_umma.float(), d_simt.float()) < TOL

@@ -24,6 +24,10 @@ PROTOTYPES = {
     "vae_conv_fprop": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_conv_dgrad": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_set_umma": [_i],
+    "vae_umma_packed_elems": [_i, _i, _i, _i],
+    "vae_umma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_bn_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp],
     "vae_bn_apply_lrelu": [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
@@ -41,7 +45,7 @@ PROTOTYPES = {
     "vae_sigmoid_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "vae_roll_transform": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _ull, _ull, _vp],
 }
-_RESTYPES = {"vae_last_error": C.c_char_p}
+_RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong}
 
 _lib = None
 

@@ -1,7 +1,462 @@
-// tcgen05 / TMEM implicit-GEMM convolution kernels (bf16).  Placeholder until
-// the UMMA path lands: reports "not handled" so the CUDA-core kernels run.
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 x bf16 -> fp32).
+//
+// One persistent, warp-specialised kernel runs every "gather-GEMM" of the hot
+// path -- Conv2d(k3,s2,p1) forward, ConvTranspose2d(k3,s2,p1,op1) forward (the
+// data-gradient of the equivalent conv, as 4 output-parity phases with 1/2/2/4
+// taps) and both data gradients (geometry: conv_geom.cuh):
+//
+//   D[128 pixels x N channels] (TMEM, fp32) += A[128 x 64] (smem) * B[N x 64]^T (smem)
+//
+//   warps 0-3  A producers: one output pixel (GEMM row) per thread; per k-block
+//              the thread gathers its row's 64 input channels (8 x 16 B, one tap
+//              of the 3x3 window, zero for padding) from NHWC global memory into
+//              registers -- optionally applying the PREVIOUS layer's
+//              BatchNorm+LeakyReLU on the fly -- and stores them into the
+//              128B-swizzled K-major tile UMMA expects (conflict-free st.shared.v4).
+//              The weight tile of the k-block is a pre-swizzled contiguous image
+//              in global memory and arrives by ONE bulk-TMA copy (cp.async.bulk)
+//              signalling the same mbarrier.
+//   warp  8    MMA issuer: one elected thread issues 4 x tcgen05.mma (K=16 each)
+//              per k-block and commits to the stage's "empty" mbarrier; after the
+//              last k-block it commits to the accumulator's "full" mbarrier.
+//   warps 4-7  epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM,
+//              so the epilogue of tile i overlaps the main loop of tile i+1), add
+//              bias, accumulate per-channel sum / sum-of-squares for the following
+//              train-mode BatchNorm (warp transpose-reduce -> smem -> one fp64
+//              atomic per channel per CTA at the very end), convert to bf16, store.
+//
+// Grid = #SMs (persistent, static round-robin tile schedule), 1 CTA / SM.
 #include "common.cuh"
+#include "conv_geom.cuh"
+#include "umma.cuh"
 
+namespace vae {
+
+using namespace umma;
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
+constexpr int kThreads = 288;
+
+struct UmmaGatherParams {
+  GatherGeom g;
+  int nkb[4];        // k-blocks per phase
+  int b_off[4];      // element offset of the phase's first weight image
+  int tiles_per_phase;
+  int total_tiles;
+  int cpt;           // 16-byte chunks per tap = Cin / 8
+  int N;             // output channels (multiple of 16, <= 256)
+  int b_stage_bytes; // N * 128 rounded up to 1024
+  int tmem_cols;     // power of two >= 2 * N
+  const bf16* in;
+  const bf16* wpk;
+  const float* bias;
+  bf16* out;
+  double* stats;
+  const float* pro_scale;  // optional fused BatchNorm+LeakyReLU on the gathered operand
+  const float* pro_shift;
+  float slope;
+};
+
+// --------------------------------------------------------------------------
+// weight images: for phase p, k-block kb: [N rows][64 k] bf16, 128B-swizzled,
+// element (n, e) = W(n, tap(q), c) with chunk q = kb*8 + e/8 -> tap = q / cpt,
+// c = (q % cpt)*8 + e%8; zero beyond the phase's taps.
+// mode 0 (fprop):  W(n, t, c) = w[co=n][ci=c][t]     (Nout = Co, Cin_gemm = Ci)
+// mode 1 (dgrad):  W(n, t, c) = w[co=c][ci=n][t]     (Nout = Ci, Cin_gemm = Co)
+// --------------------------------------------------------------------------
+__global__ void pack_umma_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out,
+                                        const __grid_constant__ UmmaGatherParams P, int Co, int Ci,
+                                        int mode) {
+  const int phase = blockIdx.y;
+  const TapTable& tt = P.g.phase[phase];
+  const long long n_elem = (long long)P.nkb[phase] * P.N * 64;
+  bf16* dst = out + P.b_off[phase];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem;
+       i += (long long)gridDim.x * blockDim.x) {
+    int e = (int)(i & 63);
+    int n = (int)((i >> 6) % P.N);
+    int kb = (int)((i >> 6) / P.N);
+    int q = kb * 8 + (e >> 3);
+    int tap_i = q / P.cpt;
+    float v = 0.0f;
+    if (tap_i < tt.ntaps) {
+      int c = (q - tap_i * P.cpt) * 8 + (e & 7);
+      int t = tt.wt[tap_i];
+      int co = mode == 0 ? n : c, ci = mode == 0 ? c : n;
+      v = w[((long long)co * Ci + ci) * 9 + t];
+    }
+    long long off = (long long)kb * P.N * 64 + (long long)n * 64 + ((((e >> 3) ^ (n & 7)) << 3) | (e & 7));
+    dst[off] = __float2bfloat16_rn(v);
+  }
+}
+
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint4 bn_lrelu_8(uint4 raw, const float* __restrict__ sc, const float* __restrict__ sh,
+                                            int c0, float slope) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    float u0 = fmaf(f.x, sc[c0 + 2 * i], sh[c0 + 2 * i]);
+    float u1 = fmaf(f.y, sc[c0 + 2 * i + 1], sh[c0 + 2 * i + 1]);
+    u0 = u0 > 0.0f ? u0 : u0 * slope;
+    u1 = u1 > 0.0f ? u1 : u1 * slope;
+    h[i] = __floats2bfloat162_rn(u0, u1);
+  }
+  return raw;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B b_stage_bytes] | barriers | tmem ptr | stats | prologue vectors
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = kABytes + P.b_stage_bytes;
+  uint8_t* tail = smem + kStages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
+  float* s_pro = s_stats + 2 * 256;                         // [2][Cin] (scale, shift)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GatherGeom& g = P.g;
+  const int N = P.N;
+
+  for (int i = threadIdx.x; i < 2 * N; i += kThreads) s_stats[i] = 0.0f;
+  if (P.pro_scale != nullptr)
+    for (int i = threadIdx.x; i < g.Cin; i += kThreads) {
+      s_pro[i] = P.pro_scale[i];
+      s_pro[g.Cin + i] = P.pro_shift[i];
+    }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full_bar[s], 128 + 1);  // 128 producer threads + the expect_tx arrive
+        mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, (uint32_t)P.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const long long M_total = (long long)g.B * g.Hj * g.Wj;
+
+  if (warp < 4) {
+    // =========================== A/B producers ===========================
+    const int r = threadIdx.x;  // GEMM row owned by this thread
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t xr = (uint32_t)(r & 7);
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int phase = tile / P.tiles_per_phase;
+      const int mt = tile - phase * P.tiles_per_phase;
+      const TapTable& tt = g.phase[phase];
+      const long long m = (long long)mt * kTileM + r;
+      const bool valid = m < M_total;
+      int b = 0, bh = 0, bw = 0;
+      if (valid) {
+        int jw = (int)(m % g.Wj);
+        long long t2 = m / g.Wj;
+        bh = (int)(t2 % g.Hj) * g.in_mul;
+        b = (int)(t2 / g.Hj);
+        bw = jw * g.in_mul;
+      }
+      const bf16* in_b = P.in + (long long)b * g.Hin * g.Win * g.Cin;
+      const int nkb = P.nkb[phase];
+      const int ntaps = tt.ntaps;
+      const bf16* wsrc = P.wpk + P.b_off[phase];
+
+      uint4 cur[8], nxt[8];
+      auto gather = [&](int kb, uint4* v) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = kb * 8 + j;
+          const int tap_i = q / P.cpt;
+          const int c8 = q - tap_i * P.cpt;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (valid && tap_i < ntaps) {
+            const int ih = bh + tt.dh[tap_i], iw = bw + tt.dw[tap_i];
+            if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) {
+              val = ldg_nc_v4(in_b + ((long long)ih * g.Win + iw) * g.Cin + c8 * 8);
+              if (P.pro_scale != nullptr) val = bn_lrelu_8(val, s_pro, s_pro + g.Cin, c8 * 8, P.slope);
+            }
+          }
+          v[j] = val;
+        }
+      };
+      gather(0, cur);
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb + 1 < nkb) gather(kb + 1, nxt);
+        mbar_wait(&empty_bar[stage], ph ^ 1u);
+        uint8_t* a_st = smem + stage * stage_bytes;
+        if (r == 0) {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
+          bulk_g2s(a_st + kABytes, wsrc + (long long)kb * N * 64, (uint32_t)(N * 128), &full_bar[stage]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(a_st + row_off + (((uint32_t)j ^ xr) << 4)) = cur[j];
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[stage]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        if (++stage == kStages) { stage = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 8) {
+    // ============================ MMA issuer =============================
+    const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)N, 0, 0);
+    int stage = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int phase = tile / P.tiles_per_phase;
+      const int nkb = P.nkb[phase];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+            mma_bf16_ss(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit(&empty_bar[stage]);              // smem stage reusable once these MMAs finish
+          if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ============================= epilogue ==============================
+    const int ew = warp - 4;             // TMEM lane group = warp % 4
+    const int r = ew * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int phase = tile / P.tiles_per_phase;
+      const int mt = tile - phase * P.tiles_per_phase;
+      const TapTable& tt = g.phase[phase];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const long long m = (long long)mt * kTileM + r;
+      const bool valid = m < M_total;
+      bf16* dst = nullptr;
+      if (valid) {
+        int jw = (int)(m % g.Wj);
+        long long t2 = m / g.Wj;
+        int jh = (int)(t2 % g.Hj);
+        int b = (int)(t2 / g.Hj);
+        int oh = jh * g.out_mul + tt.ph, ow = jw * g.out_mul + tt.pw;
+        dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * g.Nout;
+      }
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        const int ncol = min(32, N - c0);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float bvl = (P.bias != nullptr && i < ncol) ? P.bias[c0 + i] : 0.0f;
+          v[i] = (valid && i < ncol) ? v[i] + bvl : 0.0f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (i < ncol) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+              *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+            }
+          }
+        }
+        if (P.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+          warp_transpose_reduce32(v, lane);
+          warp_transpose_reduce32(sq, lane);
+          if (lane < ncol) {
+            atomicAdd(&s_stats[c0 + lane], v[0]);
+            atomicAdd(&s_stats[N + c0 + lane], sq[0]);
+          }
+        }
+      }
+    }
+    if (P.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      for (int i = threadIdx.x - 128; i < 2 * N; i += 128) atomicAdd(&P.stats[i], (double)s_stats[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+static bool g_umma_enabled = true;
+
+static bool umma_shape_ok(int Cin_gemm, int Nout) {
+  return g_umma_enabled && Cin_gemm % 32 == 0 && Nout % 16 == 0 && Nout >= 16 && Nout <= 256 && Cin_gemm <= 2048;
+}
+
+static void fill_params(UmmaGatherParams& P, const GatherGeom& g) {
+  P.g = g;
+  P.cpt = g.Cin / 8;
+  P.N = g.Nout;
+  P.b_stage_bytes = (g.Nout * 128 + 1023) / 1024 * 1024;
+  int cols = 32;
+  while (cols < 2 * g.Nout) cols *= 2;
+  P.tmem_cols = cols;
+  long long M = (long long)g.B * g.Hj * g.Wj;
+  P.tiles_per_phase = (int)((M + kTileM - 1) / kTileM);
+  P.total_tiles = P.tiles_per_phase * g.nphase;
+  int off = 0;
+  for (int p = 0; p < 4; ++p) {
+    if (p < g.nphase) {
+      P.nkb[p] = (g.phase[p].ntaps * P.cpt + 7) / 8;
+      P.b_off[p] = off;
+      off += P.nkb[p] * g.Nout * 64;
+    } else {
+      P.nkb[p] = 0;
+      P.b_off[p] = off;
+    }
+  }
+}
+
+static long long packed_elems(const UmmaGatherParams& P) {
+  long long n = 0;
+  for (int p = 0; p < P.g.nphase; ++p) n += (long long)P.nkb[p] * P.N * 64;
+  return n;
+}
+
+static int launch_umma(UmmaGatherParams& P, cudaStream_t st) {
+  size_t smem = 1024 + (size_t)kStages * (kABytes + P.b_stage_bytes) + 128 + 16 + 2 * 256 * 4 + 2 * 2048 * 4;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("umma: smem attribute: %s", cudaGetErrorString(e));
+      return VAE_ERR_CUDA;
+    }
+    attr_bytes = 227 * 1024;
+  }
+  if (smem > 227 * 1024) {
+    set_error("umma: tile needs %zu bytes of shared memory", smem);
+    return VAE_ERR_UNSUPPORTED;
+  }
+  int grid = sm_count();
+  if (grid > P.total_tiles) grid = P.total_tiles;
+  umma_gather_gemm_kernel<<<grid, kThreads, smem, st>>>(P);
+  return check_launch("umma_gather_gemm");
+}
+
+}  // namespace vae
+
+using namespace vae;
+
+extern "C" int vae_has_umma(void) { return 1; }
+
+extern "C" int vae_set_umma(int enable) {
+  int old = g_umma_enabled ? 1 : 0;
+  g_umma_enabled = enable != 0;
+  return old;
+}
+
+/* number of bf16 elements vae_umma_pack_weight writes (0 if the shape is not
+ * served by the tcgen05 path) */
+extern "C" long long vae_umma_packed_elems(int Ci, int Co, int stride, int mode) {
+  GatherGeom g = mode == 0 ? geom_fprop(1, 2 * stride, 2 * stride, Ci, Co, stride)
+                           : geom_dgrad(1, 2 * stride, 2 * stride, Ci, Co, stride);
+  if (!umma_shape_ok(g.Cin, g.Nout)) return 0;
+  UmmaGatherParams P{};
+  fill_params(P, g);
+  return packed_elems(P);
+}
+
+extern "C" int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
+                                    vae_stream_t stream) {
+  VAE_REQUIRE(w_oihw && out && (mode == 0 || mode == 1) && (stride == 1 || stride == 2), "umma_pack_weight: bad argument");
+  GatherGeom g = mode == 0 ? geom_fprop(1, 2 * stride, 2 * stride, Ci, Co, stride)
+                           : geom_dgrad(1, 2 * stride, 2 * stride, Ci, Co, stride);
+  VAE_REQUIRE(umma_shape_ok(g.Cin, g.Nout), "umma_pack_weight: shape not served by the tcgen05 path");
+  UmmaGatherParams P{};
+  fill_params(P, g);
+  dim3 grid(64, g.nphase);
+  pack_umma_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (bf16*)out, P, Co, Ci, mode);
+  return check_launch("pack_umma_weight");
+}
+
+/* Conv forward (mode 0) / data gradient == ConvTranspose forward (mode 1) on the
+ * tcgen05 path.  `in`, `out` NHWC bf16; wpk from vae_umma_pack_weight(same Ci, Co,
+ * stride, mode).  Hi, Wi are the HIGH-resolution (conv input side) extents as in
+ * vae_conv_fprop / vae_conv_dgrad.  pro_scale/pro_shift (nullable, fp32 [C_in_gemm])
+ * fuse the previous layer's BatchNorm + LeakyReLU into the operand load. */
+extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
+                             const float* pro_scale, const float* pro_shift, float slope, int B, int Hi,
+                             int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
+                  (mode == 0 || mode == 1) && ((pro_scale == nullptr) == (pro_shift == nullptr)),
+              "conv_umma: bad argument");
+  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
+  VAE_REQUIRE(umma_shape_ok(g.Cin, g.Nout), "conv_umma: shape (Cin=%d, N=%d) not served by the tcgen05 path", g.Cin, g.Nout);
+  cudaStream_t st = as_stream(stream);
+  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
+  UmmaGatherParams P{};
+  fill_params(P, g);
+  P.in = (const bf16*)in; P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  P.pro_scale = pro_scale; P.pro_shift = pro_shift; P.slope = slope;
+  return launch_umma(P, st);
+}
+
+// hooks used by conv_simt.cu's generic entry points: the packed-weight tcgen05
+// path has its own entry point (vae_conv_umma), so these never take over.
 namespace vae {
 int umma_conv_fprop(const void*, const void*, const float*, void*, double*, int, int, int, int, int,
                     int, cudaStream_t, bool* handled) { *handled = false; return VAE_OK; }
@@ -10,5 +465,3 @@ int umma_conv_dgrad(const void*, const void*, const float*, void*, double*, int,
 int umma_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t,
                     bool* handled) { *handled = false; return VAE_OK; }
 }  // namespace vae
-
-extern "C" int vae_has_umma(void) { return 0; }

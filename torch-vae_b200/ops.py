@@ -360,3 +360,55 @@ def roll_transform(rolls, H: int, W: int, crop_mode: int, max_pitch_shift: int,
     )
     _lib.check(rc, "vae_roll_transform")
     return out
+
+
+# ------------------------------------------------------- tcgen05 / TMEM conv path
+def umma_available() -> bool:
+    return bool(_L().vae_has_umma())
+
+
+def set_umma(enable: bool) -> bool:
+    """Enable/disable the tcgen05 path (tests cross-check it against the CUDA-core
+    kernels).  Returns the previous setting."""
+    return bool(_L().vae_set_umma(1 if enable else 0))
+
+
+def umma_packed_elems(Ci: int, Co: int, stride: int, mode: int) -> int:
+    return int(_L().vae_umma_packed_elems(Ci, Co, stride, mode))
+
+
+def umma_pack_weight(w: torch.Tensor, stride: int, mode: int) -> Optional[torch.Tensor]:
+    """fp32 OIHW weight -> pre-swizzled bf16 smem images for vae_conv_umma
+    (mode 0: forward conv, mode 1: data gradient / ConvTranspose forward).
+    Returns None when the shape is not served by the tcgen05 path."""
+    Co, Ci = w.shape[0], w.shape[1]
+    n = umma_packed_elems(Ci, Co, stride, mode)
+    if n == 0:
+        return None
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    rc = _L().vae_umma_pack_weight(_f32(w, "conv weight"), _p(out), Ci, Co, stride, mode, _stream())
+    _lib.check(rc, "vae_umma_pack_weight")
+    return out
+
+
+def conv_umma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int, pro=None,
+              slope: float = LRELU_SLOPE):
+    """mode 0: inp = x [B,Hi,Wi,Ci] -> y [B,Hi/s,Wi/s,Co];
+    mode 1: inp = dy [B,Hi/s,Wi/s,Co] -> dx [B,Hi,Wi,Ci].
+    pro = BatchNorm vec (scale, shift, ...) of the layer that produced ``inp``: its
+    BN+LeakyReLU is applied while the operand is gathered."""
+    if inp.dtype != torch.bfloat16:
+        raise RuntimeError("conv_umma: bf16 activations only")
+    B = inp.shape[0]
+    if mode == 0:
+        Hi, Wi = inp.shape[1], inp.shape[2]
+        out = torch.empty((B, Hi // stride, Wi // stride, Co), dtype=torch.bfloat16, device=inp.device)
+    else:
+        Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
+        out = torch.empty((B, Hi, Wi, Ci), dtype=torch.bfloat16, device=inp.device)
+    ps = pro[0].data_ptr() if pro is not None else None
+    pf = pro[1].data_ptr() if pro is not None else None
+    rc = _L().vae_conv_umma(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), _p(stats), ps, pf, slope,
+                            B, Hi, Wi, Ci, Co, stride, mode, _stream())
+    _lib.check(rc, "vae_conv_umma")
+    return out
