@@ -74,6 +74,9 @@ def test_umma_dgrad_is_conv_transpose(ops, case):
     ref = F.conv_transpose2d(dy.bfloat16().double(), w.bfloat16().double(), b.double(), stride=s, padding=1,
                              output_padding=s - 1)
     wpk = ops.umma_pack_weight(w.cuda(), s, 1)
+    if Co % 32 != 0:  # the data gradient contracts over Co: not a tcgen05 shape -> CUDA-core kernel serves it
+        assert wpk is None
+        return
     assert wpk is not None
     stats = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
     dx = ops.conv_umma(nhwc(dy).cuda().bfloat16(), wpk, b.cuda(), stats, Ci, Co, s, 1)

@@ -82,6 +82,13 @@ gather_gemm_kernel(const __grid_constant__ GatherGeom g, const TI* __restrict__ 
       Bs[k_l][r_l + 8 * i] = v;
     }
     __syncthreads();
+    // two-level summation: a fresh 32-term partial per k-block, then one add into the
+    // running total -- shortens the fp32 rounding chains from K to 32 + K/32 terms
+    float part[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) part[r][cc] = 0.0f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -90,8 +97,12 @@ gather_gemm_kernel(const __grid_constant__ GatherGeom g, const TI* __restrict__ 
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(av[r], bv[cc], acc[r][cc]);
+        for (int cc = 0; cc < 4; ++cc) part[r][cc] = fmaf(av[r], bv[cc], part[r][cc]);
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[r][cc] += part[r][cc];
     __syncthreads();
   }
 
@@ -217,6 +228,13 @@ wgrad_kernel(const TX* __restrict__ X, const TY* __restrict__ dY, float* __restr
       Bs[p][col] = vb;
     }
     __syncthreads();
+    // two-level summation: a fresh 32-term partial per k-block, then one add into the
+    // running total -- shortens the fp32 rounding chains from K to 32 + K/32 terms
+    float part[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) part[r][cc] = 0.0f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -225,8 +243,12 @@ wgrad_kernel(const TX* __restrict__ X, const TY* __restrict__ dY, float* __restr
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(av[r], bv[cc], acc[r][cc]);
+        for (int cc = 0; cc < 4; ++cc) part[r][cc] = fmaf(av[r], bv[cc], part[r][cc]);
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[r][cc] += part[r][cc];
     __syncthreads();
   }
 #pragma unroll

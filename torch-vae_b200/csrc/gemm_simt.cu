@@ -54,6 +54,13 @@ gemm_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __restrict_
       Bs[kk][nn] = v;
     }
     __syncthreads();
+    // two-level summation: a fresh 32-term partial per k-block, then one add into the
+    // running total -- shortens the fp32 rounding chains from K to 32 + K/32 terms
+    float part[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) part[r][cc] = 0.0f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -62,8 +69,12 @@ gemm_kernel(const TA* __restrict__ A, const TB* __restrict__ Bm, TC* __restrict_
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) acc[r][cc] = fmaf(av[r], bv[cc], acc[r][cc]);
+        for (int cc = 0; cc < 4; ++cc) part[r][cc] = fmaf(av[r], bv[cc], part[r][cc]);
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) acc[r][cc] += part[r][cc];
     __syncthreads();
   }
 #pragma unroll

@@ -66,11 +66,11 @@ class EncodeFn(torch.autograd.Function):
         saved = []
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
-            wp, wt = ops.pack_conv_weight(w, dtype, want_wp=True, want_wt=True)
+            cw = ops.ConvWeights(w, dtype, 2)
             stats = torch.empty(2 * sp.co, dtype=torch.float64, device=h.device) if training else None
-            y = ops.conv_fprop(h, wp, b, 2, dtype, stats, Ci=sp.ci)
+            y = ops.conv_forward(h, cw, b, stats, Ci=sp.ci)
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
-            saved.append((h, y, vec, wt, Hi, Wi))
+            saved.append((h, y, vec, cw, Hi, Wi))
             h = act
             Hi, Wi = Hi // 2, Wi // 2
         pre = ops.nhwc_to_nchw(h)  # [B, C*h*w], C-major like x.flatten(1) (models.py:133)
@@ -108,7 +108,7 @@ class EncodeFn(torch.autograd.Function):
         dx = None
         for i in range(len(specs) - 1, -1, -1):
             sp = specs[i]
-            h_in, y, vec, wt, Hi, Wi = saved[i]
+            h_in, y, vec, cw, Hi, Wi = saved[i]
             gamma = conv_params[4 * i + 2]
             dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
             conv_grads[4 * i] = ops.conv_wgrad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
@@ -119,9 +119,9 @@ class EncodeFn(torch.autograd.Function):
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
             if i > 0:
-                d_act = ops.conv_dgrad(dy, wt, None, 2)
+                d_act = ops.conv_data_grad(dy, cw)
             elif ctx.x_needs_grad:
-                dx = ops.nhwc_to_nchw(ops.conv_dgrad(dy, wt, None, 2), torch.float32).view(B, sp.ci, Hi, Wi)
+                dx = ops.nhwc_to_nchw(ops.conv_data_grad(dy, cw), torch.float32).view(B, sp.ci, Hi, Wi)
         ctx.saved = None
         return (None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
 
@@ -166,18 +166,18 @@ class DecodeFn(torch.autograd.Function):
         saved = []
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
-            wp, wt = ops.pack_conv_weight(w, dtype, want_wp=True, want_wt=True)
+            cw = ops.ConvWeights(w, dtype, 2)
             stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
-            y = ops.conv_dgrad(h, wt, b, 2, stats)  # ConvTranspose2d forward
+            y = ops.conv_data_grad(h, cw, b, stats)  # ConvTranspose2d forward
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
-            saved.append((h, y, vec, wp))
+            saved.append((h, y, vec, cw))
             h = act
-        wp3, wt3 = ops.pack_conv_weight(w_last, dtype, want_wp=True, want_wt=True)
-        logits = ops.conv_fprop(h, wp3, b_last, 1, dtype)  # [B,H,W,1]
+        cw3 = ops.ConvWeights(w_last, dtype, 1)
+        logits = ops.conv_forward(h, cw3, b_last)  # [B,H,W,1]
         H, W = logits.shape[1], logits.shape[2]
         probs = ops.sigmoid(logits).view(B, 1, H, W)
         logits = logits.view(B, 1, H, W)
-        ctx.specs, ctx.training, ctx.saved, ctx.last = specs, training, saved, (h, wt3)
+        ctx.specs, ctx.training, ctx.saved, ctx.last = specs, training, saved, (h, cw3)
         ctx.save_for_backward(z, w_in, probs, b_in, w_last, b_last, *conv_params)
         ctx.z_needs_grad = z.requires_grad
         return probs, logits
@@ -187,7 +187,7 @@ class DecodeFn(torch.autograd.Function):
     def backward(ctx, dprobs, dlogits):
         z, w_in, probs, b_in, w_last, b_last, *conv_params = ctx.saved_tensors
         specs, saved, sink = ctx.specs, ctx.saved, ctx.sink
-        act_last, wt3 = ctx.last
+        act_last, cw3 = ctx.last
         B, _, H, W = probs.shape
         dtype = act_last.dtype
         if dlogits is not None:
@@ -208,11 +208,11 @@ class DecodeFn(torch.autograd.Function):
         if sink is not None:
             sink.push(w_last, g_w_last)
             sink.push(b_last, g_b_last)
-        d_act = ops.conv_dgrad(dlog, wt3, None, 1)
+        d_act = ops.conv_data_grad(dlog, cw3)
         conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
         for i in range(len(specs) - 1, -1, -1):
             sp = specs[i]
-            h_in, y, vec, wp = saved[i]
+            h_in, y, vec, cw = saved[i]
             gamma = conv_params[4 * i + 2]
             dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
             Hi, Wi = y.shape[1], y.shape[2]
@@ -224,7 +224,7 @@ class DecodeFn(torch.autograd.Function):
             if sink is not None:
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
-            d_act = ops.conv_fprop(dy, wp, None, 2, dtype)  # gradient w.r.t. the ConvT input
+            d_act = ops.conv_forward(dy, cw, None)  # gradient w.r.t. the ConvT input
         d_d = ops.nhwc_to_nchw(d_act)  # [B, F] C-major, matching decoder_input's output
         g_w_in = ops.linear_bwd_weight(d_d, z)
         g_b_in = ops.colsum(d_d)

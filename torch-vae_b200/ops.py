@@ -412,3 +412,53 @@ def conv_umma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int, p
                             B, Hi, Wi, Ci, Co, stride, mode, _stream())
     _lib.check(rc, "vae_conv_umma")
     return out
+
+
+class ConvWeights:
+    """Per-step operand layouts of one 3x3 conv weight (fp32 OIHW master copy).
+
+    bf16 layers whose shape suits the tensor cores get pre-swizzled tcgen05 weight
+    images; everything else gets the CUDA-core K-major packs.  Layouts are built
+    lazily, once per forward (the optimizer changes the master copy every step)."""
+
+    __slots__ = ("w", "dtype", "stride", "Co", "Ci", "_simt", "_umma")
+
+    def __init__(self, w: torch.Tensor, dtype: torch.dtype, stride: int):
+        self.w, self.dtype, self.stride = w, dtype, stride
+        self.Co, self.Ci = w.shape[0], w.shape[1]
+        self._simt = None
+        self._umma = {}
+
+    def simt(self):
+        if self._simt is None:
+            self._simt = pack_conv_weight(self.w, self.dtype)
+        return self._simt
+
+    def umma(self, mode: int):
+        if self.dtype != torch.bfloat16 or not umma_available():
+            return None
+        if mode not in self._umma:
+            self._umma[mode] = umma_pack_weight(self.w, self.stride, mode)
+        return self._umma[mode]
+
+
+def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None):
+    """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies."""
+    if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == cw.Ci:
+        wpk = cw.umma(0)
+        if wpk is not None:
+            return conv_umma(x, wpk, bias, stats, cw.Ci, cw.Co, cw.stride, 0, pro=pro)
+    if pro is not None:
+        raise RuntimeError("fused BatchNorm prologue needs the tcgen05 path")
+    return conv_fprop(x, cw.simt()[0], bias, cw.stride, cw.dtype, stats, Ci=Ci if Ci is not None else cw.Ci)
+
+
+def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
+    """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward."""
+    if dy.dtype == torch.bfloat16:
+        wpk = cw.umma(1)
+        if wpk is not None:
+            return conv_umma(dy, wpk, bias, stats, cw.Ci, cw.Co, cw.stride, 1, pro=pro)
+    if pro is not None:
+        raise RuntimeError("fused BatchNorm prologue needs the tcgen05 path")
+    return conv_dgrad(dy, cw.simt()[1], bias, cw.stride, stats)
