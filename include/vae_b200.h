@@ -100,6 +100,14 @@ int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out,
                   const float* pro_scale, const float* pro_shift, float slope, int B, int Hi, int Wi,
                   int Ci, int Co, int stride, int mode, vae_stream_t stream);
 
+/* Weight gradient on the tcgen05 path (both operands MN-major, split over pixels,
+ * fp32 red.global.add into dw).  x, dy NHWC bf16; dw [Co][Ci][3][3] fp32, overwritten.
+ * replaces: the weight-gradient half of aten::convolution_backward (train.py:650) */
+int vae_set_umma_wgrad(int enable);
+int vae_umma_wgrad_supported(int Ci, int Co);
+int vae_conv_wgrad_umma(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Ci,
+                        int Co, int stride, vae_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * BatchNorm2d (train and eval) + LeakyReLU.   models.py:46-47,69-70,78-79
  * ---------------------------------------------------------------------- */

@@ -113,3 +113,38 @@ def test_umma_matches_cuda_core_kernels_at_layer_sizes(ops):
         d_simt = ops.conv_dgrad(dy, wt, None, 2)
         d_umma = ops.conv_umma(dy, ops.umma_pack_weight(w, 2, 1), None, None, Ci, Co, 2, 1)
         assert rel_err(d_umma.float(), d_simt.float()) < TOL
+
+
+WG_CASES = [
+    # B, H, W, Ci, Co, stride
+    (2, 16, 16, 32, 64, 2),
+    (3, 8, 24, 64, 128, 2),
+    (4, 8, 8, 128, 256, 2),
+    (2, 32, 32, 32, 32, 2),
+    (5, 16, 16, 64, 32, 2),
+    (1, 8, 8, 32, 64, 1),
+    (7, 48, 16, 96, 48, 2),
+    (32, 64, 64, 32, 64, 2),  # many k-blocks per CTA
+    (2, 16, 16, 256, 64, 2),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_umma_wgrad(ops, case):
+    B, H, W, Ci, Co, s = case
+    x = rnd(B, Ci, H, W, seed=1)
+    dy = rnd(B, Co, H // s, W // s, seed=4)
+    xr = x.bfloat16().double()
+    wr = torch.zeros(Co, Ci, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xr, wr, None, stride=s, padding=1).backward(dy.bfloat16().double())
+    dw = ops.conv_weight_grad(nhwc(x).cuda().bfloat16(), nhwc(dy).cuda().bfloat16(), s, Ci, Co, H, W)
+    torch.cuda.synchronize()
+    assert dw.shape == (Co, Ci, 3, 3) and dw.dtype == torch.float32
+    assert rel_err(dw.cpu(), wr.grad) < 1e-4
+    # and the CUDA-core kernel of the same library agrees
+    ops._L().vae_set_umma_wgrad(0)
+    try:
+        dw2 = ops.conv_weight_grad(nhwc(x).cuda().bfloat16(), nhwc(dy).cuda().bfloat16(), s, Ci, Co, H, W)
+    finally:
+        ops._L().vae_set_umma_wgrad(1)
+    assert rel_err(dw, dw2) < 1e-4

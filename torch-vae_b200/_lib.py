@@ -28,6 +28,9 @@ PROTOTYPES = {
     "vae_umma_packed_elems": [_i, _i, _i, _i],
     "vae_umma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
     "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_set_umma_wgrad": [_i],
+    "vae_umma_wgrad_supported": [_i, _i],
+    "vae_conv_wgrad_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "vae_bn_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp],
     "vae_bn_apply_lrelu": [_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],

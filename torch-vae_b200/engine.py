@@ -111,7 +111,7 @@ class EncodeFn(torch.autograd.Function):
             h_in, y, vec, cw, Hi, Wi = saved[i]
             gamma = conv_params[4 * i + 2]
             dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
-            conv_grads[4 * i] = ops.conv_wgrad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
+            conv_grads[4 * i] = ops.conv_weight_grad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
             conv_grads[4 * i + 3] = dbeta
@@ -204,7 +204,7 @@ class DecodeFn(torch.autograd.Function):
         n = dlog.numel()
         cols = 256 if n % 256 == 0 else 1
         g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1))
-        g_w_last = ops.conv_wgrad(act_last, dlog, 1, c_last, 1, H, W)
+        g_w_last = ops.conv_weight_grad(act_last, dlog, 1, c_last, 1, H, W)
         if sink is not None:
             sink.push(w_last, g_w_last)
             sink.push(b_last, g_b_last)
@@ -217,7 +217,7 @@ class DecodeFn(torch.autograd.Function):
             dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
             Hi, Wi = y.shape[1], y.shape[2]
             # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
-            conv_grads[4 * i] = ops.conv_wgrad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)
+            conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
             conv_grads[4 * i + 3] = dbeta

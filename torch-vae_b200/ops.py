@@ -462,3 +462,15 @@ def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
     if pro is not None:
         raise RuntimeError("fused BatchNorm prologue needs the tcgen05 path")
     return conv_dgrad(dy, cw.simt()[1], bias, cw.stride, stats)
+
+
+def conv_weight_grad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int):
+    """dW [Co,Ci,3,3] fp32: tcgen05 kernel for bf16 tensor-core shaped layers, the
+    CUDA-core kernels otherwise (fp32 path, single-channel edge layers)."""
+    if x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and _L().vae_umma_wgrad_supported(Ci, Co):
+        B = dy.shape[0]
+        dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+        rc = _L().vae_conv_wgrad_umma(_p(x), _p(dy), _p(dw), B, Hi, Wi, Ci, Co, stride, _stream())
+        _lib.check(rc, "vae_conv_wgrad_umma")
+        return dw
+    return conv_wgrad(x, dy, stride, Ci, Co, Hi, Wi)
