@@ -122,16 +122,18 @@ int vae_bn_finalize(const double* stats, const float* gamma, const float* beta,
                     float* mean, float* rstd, int C, long long count, float momentum, float eps,
                     int training, vae_stream_t stream);
 
-/* act = leaky_relu(scale[c]*y + shift[c]).
+/* act = leaky_relu((y - mean[c]) * scale[c] + beta[c])  (ATen's operation order, so the
+ * LeakyReLU branch agrees with the reference down to |u| ~ 1e-7).
  * replaces: the normalise half of aten::native_batch_norm + aten::leaky_relu */
-int vae_bn_apply_lrelu(const void* y, const float* scale, const float* shift, void* act,
-                       long long n_pix, int C, float slope, int dtype, vae_stream_t stream);
+int vae_bn_apply_lrelu(const void* y, const float* scale, const float* mean, const float* beta,
+                       void* act, long long n_pix, int C, float slope, int dtype,
+                       vae_stream_t stream);
 
-/* Pass 1 of the backward: du = dact * lrelu'(scale*y+shift);
+/* Pass 1 of the backward: du = dact * lrelu'((y-mean)*scale+beta);
  * dstats[0:C] += sum du, dstats[C:2C] += sum du * xhat (double; zeroed by this call).
  * replaces: aten::leaky_relu_backward + the reductions of native_batch_norm_backward */
 int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const float* scale,
-                            const float* shift, const float* mean, const float* rstd,
+                            const float* beta, const float* mean, const float* rstd,
                             double* dstats, long long n_pix, int C, float slope, int dtype,
                             vae_stream_t stream);
 
@@ -140,7 +142,7 @@ int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const float* scale,
  * gradient of the conv bias that feeds this BatchNorm).
  * replaces: aten::native_batch_norm_backward */
 int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
-                           const float* shift, const float* mean, const float* rstd,
+                           const float* beta, const float* mean, const float* rstd,
                            const float* gamma, const double* dstats, void* dy, float* dgamma,
                            float* dbeta, float* dbias, long long n_pix, int C, float slope,
                            int training, int dtype, vae_stream_t stream);

@@ -32,6 +32,6 @@ for C, npix, mean in [(64, 32768, 0.0), (64, 32768, 5.0), (32, 131072, 5.0), (25
     yd = y.cuda().view(1, npix, 1, C).contiguous()
     stats = torch.stack([y.double().sum(0), (y.double() ** 2).sum(0)]).flatten().cuda()
     vec = ops.bn_finalize(stats, gamma.cuda(), beta.cuda(), None, None, npix, True)
-    dy, dg, db, dbias = ops.bn_lrelu_backward(d.cuda().view(1, npix, 1, C).contiguous(), yd, vec, gamma.cuda(), True)
+    dy, dg, db, dbias = ops.bn_lrelu_backward(d.cuda().view(1, npix, 1, C).contiguous(), yd, vec, gamma.cuda(), beta.cuda(), True)
     ref_dy = yr.grad.reshape(C, npix).t()
     print(f"BN bwd C={C} npix={npix} mean={mean}: dy {vo.rel_err(dy.view(npix, C).cpu(), ref_dy):.2e} dgamma {vo.rel_err(dg.cpu(), gr.grad):.2e} dbeta {vo.rel_err(db.cpu(), br.grad):.2e}")

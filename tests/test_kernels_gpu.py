@@ -131,9 +131,9 @@ def test_batchnorm_lrelu_forward_backward(tv, C, n_pix_shape, dtype):
     rm_d, rv_d = dev(rm), dev(rv)
     vec = ops.bn_finalize(stats, dev(gamma), dev(beta), rm_d, rv_d, B * H * W, True)
     assert rel_err(rm_d.cpu(), rm_ref) < 1e-5 and rel_err(rv_d.cpu(), rv_ref) < 1e-5
-    act = ops.bn_apply_lrelu(y_dev, vec)
+    act = ops.bn_apply_lrelu(y_dev, vec, dev(beta))
     assert rel_err(nchw(act.float().cpu()), a_ref) < TOL[dtype]
-    dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(dev(nhwc(dact)).to(dtype), y_dev, vec, dev(gamma), True)
+    dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(dev(nhwc(dact)).to(dtype), y_dev, vec, dev(gamma), dev(beta), True)
     assert rel_err(nchw(dy.float().cpu()), yr.grad) < max(TOL[dtype], 2e-5)
     assert rel_err(dgamma.cpu(), gr.grad) < 2e-5 and rel_err(dbeta.cpu(), br.grad) < 2e-5
     assert float(dbias.abs().max()) < 1e-3 * float(yr.grad.abs().sum())
@@ -141,7 +141,7 @@ def test_batchnorm_lrelu_forward_backward(tv, C, n_pix_shape, dtype):
     # eval mode: running statistics
     vec_e = ops.bn_finalize(None, dev(gamma), dev(beta), rm_d, rv_d, B * H * W, False)
     a_eval = F.leaky_relu(F.batch_norm(yq, rm_ref, rv_ref, gamma.double(), beta.double(), False, 0.1, 1e-5), 0.01)
-    assert rel_err(nchw(ops.bn_apply_lrelu(y_dev, vec_e).float().cpu()), a_eval) < TOL[dtype]
+    assert rel_err(nchw(ops.bn_apply_lrelu(y_dev, vec_e, dev(beta)).float().cpu()), a_eval) < TOL[dtype]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -46,23 +46,31 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
   rstd_out[c] = rstd;
 }
 
+// u = (y - mean) * (gamma * rstd) + beta, in ATen's order of operations: the
+// subtraction comes first and is exact where u changes sign (y ~ mean when beta ~ 0),
+// so LeakyReLU's branch agrees with the reference's even for |u| ~ 1e-7.
+__device__ __forceinline__ float bn_affine(float y, float mean, float scale, float beta) {
+  return fmaf(y - mean, scale, beta);
+}
+
 // ------------------------------------------------------------ BN apply + lrelu
 template <typename T>
 __global__ void bn_apply_lrelu_vec8(const T* __restrict__ y, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, T* __restrict__ act,
-                                    long long n_vec, int C, float slope) {
+                                    const float* __restrict__ mean, const float* __restrict__ beta,
+                                    T* __restrict__ act, long long n_vec, int C, float slope) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
     long long e = i * 8;
     int c = (int)(e % C);
     Vec8<T> v;
     v.load(y + e);
-    Vec8<float> s, b;
+    Vec8<float> s, m, b;
     s.load(scale + c);
-    b.load(shift + c);
+    m.load(mean + c);
+    b.load(beta + c);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float u = fmaf(v.v[k], s.v[k], b.v[k]);
+      float u = bn_affine(v.v[k], m.v[k], s.v[k], b.v[k]);
       v.v[k] = u > 0.0f ? u : u * slope;
     }
     v.store(act + e);
@@ -71,12 +79,12 @@ __global__ void bn_apply_lrelu_vec8(const T* __restrict__ y, const float* __rest
 
 template <typename T>
 __global__ void bn_apply_lrelu_scalar(const T* __restrict__ y, const float* __restrict__ scale,
-                                      const float* __restrict__ shift, T* __restrict__ act,
-                                      long long n, int C, float slope) {
+                                      const float* __restrict__ mean, const float* __restrict__ beta,
+                                      T* __restrict__ act, long long n, int C, float slope) {
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int c = (int)(i % C);
-    float u = fmaf(to_f(y[i]), scale[c], shift[c]);
+    float u = bn_affine(to_f(y[i]), mean[c], scale[c], beta[c]);
     act[i] = from_f<T>(u > 0.0f ? u : u * slope);
   }
 }
@@ -113,7 +121,7 @@ struct ChanVec {
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
-                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ scale, const float* __restrict__ beta,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      double* __restrict__ dstats, long long n_pix, int C, float slope) {
   extern __shared__ float red[];  // [lanes][G][2V]
@@ -128,7 +136,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       sc[k] = scale[g * V + k];
-      sh[k] = shift[g * V + k];
+      sh[k] = beta[g * V + k];
       mu[k] = mean[g * V + k];
       rs[k] = rstd[g * V + k];
     }
@@ -139,7 +147,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
       yy.load(y + p * C + g * V);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float u = fmaf(yy.v[k], sc[k], sh[k]);
+        float u = bn_affine(yy.v[k], mu[k], sc[k], sh[k]);
         float du = u > 0.0f ? d.v[k] : d.v[k] * slope;
         float xh = (yy.v[k] - mu[k]) * rs[k];
         s1[k] += du;
@@ -166,7 +174,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
-                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ scale, const float* __restrict__ beta,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const double* __restrict__ dstats,
                     T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -191,7 +199,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
     for (int k = 0; k < V; ++k) {
       int c = g * V + k;
       sc[k] = scale[c];
-      sh[k] = shift[c];
+      sh[k] = beta[c];
       mu[k] = mean[c];
       rs[k] = rstd[c];
       a[k] = gamma[c] * rs[k];
@@ -205,7 +213,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
       yy.load(y + p * C + g * V);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float u = fmaf(yy.v[k], sc[k], sh[k]);
+        float u = bn_affine(yy.v[k], mu[k], sc[k], sh[k]);
         float du = u > 0.0f ? d.v[k] : d.v[k] * slope;
         float xh = (yy.v[k] - mu[k]) * rs[k];
         float r = a[k] * (du - c1[k] - xh * c2[k]);
@@ -414,25 +422,25 @@ extern "C" int vae_bn_finalize(const double* stats, const float* gamma, const fl
   return check_launch("bn_finalize");
 }
 
-extern "C" int vae_bn_apply_lrelu(const void* y, const float* scale, const float* shift, void* act,
-                                  long long n_pix, int C, float slope, int dtype,
-                                  vae_stream_t stream) {
-  VAE_REQUIRE(y && act && scale && shift && n_pix > 0 && C > 0, "bn_apply_lrelu: bad argument");
+extern "C" int vae_bn_apply_lrelu(const void* y, const float* scale, const float* mean,
+                                  const float* beta, void* act, long long n_pix, int C, float slope,
+                                  int dtype, vae_stream_t stream) {
+  VAE_REQUIRE(y && act && scale && mean && beta && n_pix > 0 && C > 0, "bn_apply_lrelu: bad argument");
   long long n = n_pix * C;
   cudaStream_t st = as_stream(stream);
   if (C % 8 == 0) {
     long long nv = n / 8;
     int grid = grid_for(nv, 256);
     if (dtype == VAE_BF16)
-      bn_apply_lrelu_vec8<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, shift, (bf16*)act, nv, C, slope);
+      bn_apply_lrelu_vec8<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, mean, beta, (bf16*)act, nv, C, slope);
     else
-      bn_apply_lrelu_vec8<float><<<grid, 256, 0, st>>>((const float*)y, scale, shift, (float*)act, nv, C, slope);
+      bn_apply_lrelu_vec8<float><<<grid, 256, 0, st>>>((const float*)y, scale, mean, beta, (float*)act, nv, C, slope);
   } else {
     int grid = grid_for(n, 256);
     if (dtype == VAE_BF16)
-      bn_apply_lrelu_scalar<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, shift, (bf16*)act, n, C, slope);
+      bn_apply_lrelu_scalar<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, mean, beta, (bf16*)act, n, C, slope);
     else
-      bn_apply_lrelu_scalar<float><<<grid, 256, 0, st>>>((const float*)y, scale, shift, (float*)act, n, C, slope);
+      bn_apply_lrelu_scalar<float><<<grid, 256, 0, st>>>((const float*)y, scale, mean, beta, (float*)act, n, C, slope);
   }
   return check_launch("bn_apply_lrelu");
 }
@@ -454,10 +462,10 @@ static bool bwd_cfg(long long n_pix, int C, BwdCfg* cfg) {
 }  // namespace
 
 extern "C" int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const float* scale,
-                                       const float* shift, const float* mean, const float* rstd,
+                                       const float* beta, const float* mean, const float* rstd,
                                        double* dstats, long long n_pix, int C, float slope,
                                        int dtype, vae_stream_t stream) {
-  VAE_REQUIRE(dact && y && scale && shift && mean && rstd && dstats && n_pix > 0 && C > 0,
+  VAE_REQUIRE(dact && y && scale && beta && mean && rstd && dstats && n_pix > 0 && C > 0,
               "bn_lrelu_bwd_reduce: bad argument");
   BwdCfg cfg;
   VAE_REQUIRE(bwd_cfg(n_pix, C, &cfg), "bn_lrelu_bwd_reduce: unsupported channel count %d", C);
@@ -466,7 +474,7 @@ extern "C" int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const fl
   size_t smem = sizeof(float) * cfg.lanes * cfg.G * 2 * cfg.V;
 #define LAUNCH(T, V)                                                                       \
   bn_bwd_reduce_kernel<T, V><<<cfg.grid, 256, smem, st>>>((const T*)dact, (const T*)y, scale, \
-                                                          shift, mean, rstd, dstats, n_pix, C, slope)
+                                                          beta, mean, rstd, dstats, n_pix, C, slope)
   if (dtype == VAE_BF16) {
     if (cfg.V == 8) LAUNCH(bf16, 8); else LAUNCH(bf16, 1);
   } else {
@@ -477,12 +485,12 @@ extern "C" int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const fl
 }
 
 extern "C" int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
-                                      const float* shift, const float* mean, const float* rstd,
+                                      const float* beta, const float* mean, const float* rstd,
                                       const float* gamma, const double* dstats, void* dy,
                                       float* dgamma, float* dbeta, float* dbias,
                                       long long n_pix, int C, float slope, int training, int dtype,
                                       vae_stream_t stream) {
-  VAE_REQUIRE(dact && y && scale && shift && mean && rstd && gamma && dstats && dy && dgamma &&
+  VAE_REQUIRE(dact && y && scale && beta && mean && rstd && gamma && dstats && dy && dgamma &&
                   dbeta && dbias && n_pix > 0 && C > 0,
               "bn_lrelu_bwd_apply: bad argument");
   BwdCfg cfg;
@@ -492,7 +500,7 @@ extern "C" int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const flo
   size_t smem = sizeof(float) * cfg.lanes * cfg.G * cfg.V;
 #define LAUNCH(T, V)                                                                          \
   bn_bwd_apply_kernel<T, V><<<cfg.grid, 256, smem, st>>>((const T*)dact, (const T*)y, scale,    \
-                                                         shift, mean, rstd, gamma, dstats,     \
+                                                         beta, mean, rstd, gamma, dstats,      \
                                                          (T*)dy, dgamma, dbeta, dbias, n_pix, C, \
                                                          slope, training)
   if (dtype == VAE_BF16) {

@@ -46,7 +46,7 @@ def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     )
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return vec, ops.bn_apply_lrelu(y, vec)
+    return vec, ops.bn_apply_lrelu(y, vec, beta)
 
 
 class EncodeFn(torch.autograd.Function):
@@ -109,8 +109,8 @@ class EncodeFn(torch.autograd.Function):
         for i in range(len(specs) - 1, -1, -1):
             sp = specs[i]
             h_in, y, vec, cw, Hi, Wi = saved[i]
-            gamma = conv_params[4 * i + 2]
-            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
+            gamma, beta = conv_params[4 * i + 2], conv_params[4 * i + 3]
+            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
             conv_grads[4 * i] = ops.conv_weight_grad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
@@ -213,8 +213,8 @@ class DecodeFn(torch.autograd.Function):
         for i in range(len(specs) - 1, -1, -1):
             sp = specs[i]
             h_in, y, vec, cw = saved[i]
-            gamma = conv_params[4 * i + 2]
-            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, ctx.training)
+            gamma, beta = conv_params[4 * i + 2], conv_params[4 * i + 3]
+            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
             Hi, Wi = y.shape[1], y.shape[2]
             # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
             conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)

@@ -177,31 +177,32 @@ def bn_finalize(stats, gamma, beta, running_mean, running_var, count: int, train
     return vec
 
 
-def bn_apply_lrelu(y, vec, slope: float = LRELU_SLOPE):
+def bn_apply_lrelu(y, vec, beta, slope: float = LRELU_SLOPE):
     C = y.shape[-1]
     act = torch.empty_like(y)
     rc = _L().vae_bn_apply_lrelu(
-        _p(y), vec[0].data_ptr(), vec[1].data_ptr(), _p(act), y.numel() // C, C, slope, code(y), _stream()
+        _p(y), vec[0].data_ptr(), vec[2].data_ptr(), _f32(beta, "bn bias"), _p(act), y.numel() // C, C, slope,
+        code(y), _stream()
     )
     _lib.check(rc, "vae_bn_apply_lrelu")
     return act
 
 
-def bn_lrelu_backward(dact, y, vec, gamma, training: bool, slope: float = LRELU_SLOPE):
+def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = LRELU_SLOPE):
     """-> (dy, dgamma, dbeta, dbias)."""
     C = y.shape[-1]
     n_pix = y.numel() // C
     lib = _L()
     dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
     rc = lib.vae_bn_lrelu_bwd_reduce(
-        _p(dact), _p(y), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(),
+        _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
         _p(dstats), n_pix, C, slope, code(y), _stream(),
     )
     _lib.check(rc, "vae_bn_lrelu_bwd_reduce")
     dy = torch.empty_like(y)
     small = torch.empty((3, C), dtype=torch.float32, device=y.device)
     rc = lib.vae_bn_lrelu_bwd_apply(
-        _p(dact), _p(y), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(),
+        _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
         _f32(gamma, "bn weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
         small[2].data_ptr(), n_pix, C, slope, 1 if training else 0, code(y), _stream(),
     )
