@@ -93,12 +93,13 @@ long long vae_umma_packed_elems(int Ci, int Co, int stride, int mode); /* 0: sha
 int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
                          vae_stream_t stream);
 /* in/out NHWC bf16.  Hi, Wi: HIGH-resolution extents (as in vae_conv_fprop/dgrad).
- * pro_scale/pro_shift (nullable, fp32[C of `in`]) apply the PREVIOUS layer's
- * BatchNorm+LeakyReLU to the operand while it is gathered (padding stays zero).
+ * pro_scale/pro_mean/pro_beta (nullable, fp32[C of `in`]) apply the PREVIOUS layer's
+ * BatchNorm+LeakyReLU, leaky_relu((x-mean)*scale+beta), to the operand while it is
+ * gathered (padding stays zero).
  * replaces: aten::convolution / transposed convolution, models.py:45,66-68,77 */
 int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
-                  const float* pro_scale, const float* pro_shift, float slope, int B, int Hi, int Wi,
-                  int Ci, int Co, int stride, int mode, vae_stream_t stream);
+                  const float* pro_scale, const float* pro_mean, const float* pro_beta, float slope,
+                  int B, int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream);
 
 /* Weight gradient on the tcgen05 path (both operands MN-major, split over pixels,
  * fp32 red.global.add into dw).  x, dy NHWC bf16; dw [Co][Ci][3][3] fp32, overwritten.

@@ -90,13 +90,13 @@ def test_umma_fused_bn_lrelu_prologue(ops):
     B, H, W, Ci, Co, s = 4, 16, 16, 64, 128, 2
     x = rnd(B, Ci, H, W, seed=1)
     w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))
-    scale, shift = rnd(Ci, seed=6) * 0.3 + 1.0, rnd(Ci, seed=7) * 0.2
+    scale, mean, beta = rnd(Ci, seed=6) * 0.3 + 1.0, rnd(Ci, seed=8) * 0.5, rnd(Ci, seed=7) * 0.2
     xq = x.bfloat16().double()
-    act = F.leaky_relu(xq * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1), 0.01)
+    act = F.leaky_relu((xq - mean.double().view(1, -1, 1, 1)) * scale.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1), 0.01)
     ref = F.conv2d(act.bfloat16().double(), w.bfloat16().double(), None, stride=s, padding=1)
     wpk = ops.umma_pack_weight(w.cuda(), s, 0)
-    vec = torch.stack([scale, shift, torch.zeros(Ci), torch.ones(Ci)]).cuda()
-    y = ops.conv_umma(nhwc(x).cuda().bfloat16(), wpk, None, None, Ci, Co, s, 0, pro=vec)
+    vec = torch.stack([scale, torch.zeros(Ci), mean, torch.ones(Ci)]).cuda()
+    y = ops.conv_umma(nhwc(x).cuda().bfloat16(), wpk, None, None, Ci, Co, s, 0, pro=(vec, beta.cuda()))
     assert rel_err(nchw(y.float().cpu()), ref) < TOL
 
 

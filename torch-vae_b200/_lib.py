@@ -27,7 +27,7 @@ PROTOTYPES = {
     "vae_set_umma": [_i],
     "vae_umma_packed_elems": [_i, _i, _i, _i],
     "vae_umma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_umma_wgrad": [_i],
     "vae_umma_wgrad_supported": [_i, _i],
     "vae_conv_wgrad_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

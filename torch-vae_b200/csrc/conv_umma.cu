@@ -9,10 +9,13 @@
 //
 //   warps 0-3  A producers: one output pixel (GEMM row) per thread; per k-block
 //              the thread gathers its row's 64 input channels (8 x 16 B, one tap
-//              of the 3x3 window, zero for padding) from NHWC global memory into
-//              registers -- optionally applying the PREVIOUS layer's
-//              BatchNorm+LeakyReLU on the fly -- and stores them into the
-//              128B-swizzled K-major tile UMMA expects (conflict-free st.shared.v4).
+//              of the 3x3 window) from NHWC global memory with cp.async (zero-fill
+//              for padding) straight into the 128B-swizzled K-major tile UMMA
+//              expects.  Up to D+1 k-blocks per thread are in flight (a ring that
+//              runs across tile boundaries), so ~80 KB per SM is always
+//              outstanding.  When a k-block has landed the thread optionally
+//              applies the PREVIOUS layer's BatchNorm+LeakyReLU to its own row in
+//              place (padding stays zero), fences the async proxy and arrives.
 //              The weight tile of the k-block is a pre-swizzled contiguous image
 //              in global memory and arrives by ONE bulk-TMA copy (cp.async.bulk)
 //              signalling the same mbarrier.
@@ -34,7 +37,7 @@ namespace vae {
 
 using namespace umma;
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
@@ -50,13 +53,16 @@ struct UmmaGatherParams {
   int N;             // output channels (multiple of 16, <= 256)
   int b_stage_bytes; // N * 128 rounded up to 1024
   int tmem_cols;     // power of two >= 2 * N
+  int stages;        // smem ring depth (4..6)
+  int depth;         // k-blocks a producer thread keeps in flight beyond the oldest (D)
   const bf16* in;
   const bf16* wpk;
   const float* bias;
   bf16* out;
   double* stats;
-  const float* pro_scale;  // optional fused BatchNorm+LeakyReLU on the gathered operand
-  const float* pro_shift;
+  const float* pro_scale;  // optional fused BatchNorm+LeakyReLU on the gathered operand:
+  const float* pro_mean;   //   leaky_relu((x - mean) * scale + beta), ATen operation order
+  const float* pro_beta;
   float slope;
 };
 
@@ -102,19 +108,30 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
-__device__ __forceinline__ uint4 bn_lrelu_8(uint4 raw, const float* __restrict__ sc, const float* __restrict__ sh,
-                                            int c0, float slope) {
+__device__ __forceinline__ uint4 bn_lrelu_8(uint4 raw, const float* __restrict__ sc, const float* __restrict__ mn,
+                                            const float* __restrict__ bt, int c0, float slope) {
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float2 f = __bfloat1622float2(h[i]);
-    float u0 = fmaf(f.x, sc[c0 + 2 * i], sh[c0 + 2 * i]);
-    float u1 = fmaf(f.y, sc[c0 + 2 * i + 1], sh[c0 + 2 * i + 1]);
+    const int c = c0 + 2 * i;
+    float u0 = fmaf(f.x - mn[c], sc[c], bt[c]);
+    float u1 = fmaf(f.y - mn[c + 1], sc[c + 1], bt[c + 1]);
     u0 = u0 > 0.0f ? u0 : u0 * slope;
     u1 = u1 > 0.0f ? u1 : u1 * slope;
     h[i] = __floats2bfloat162_rn(u0, u1);
   }
   return raw;
+}
+
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -123,14 +140,15 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   // carve: [stages][A 16 KB][B b_stage_bytes] | barriers | tmem ptr | stats | prologue vectors
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = kABytes + P.b_stage_bytes;
+  const int kStages = P.stages;
   uint8_t* tail = smem + kStages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;   // [2]
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
-  float* s_pro = s_stats + 2 * 256;                         // [2][Cin] (scale, shift)
+  float* s_pro = s_stats + 2 * 256;                         // [3][Cin] (scale, mean, beta)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
@@ -140,11 +158,12 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   if (P.pro_scale != nullptr)
     for (int i = threadIdx.x; i < g.Cin; i += kThreads) {
       s_pro[i] = P.pro_scale[i];
-      s_pro[g.Cin + i] = P.pro_shift[i];
+      s_pro[g.Cin + i] = P.pro_mean[i];
+      s_pro[2 * g.Cin + i] = P.pro_beta[i];
     }
   if (warp == 8) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < kMaxStages; ++s) {
         mbar_init(&full_bar[s], 128 + 1);  // 128 producer threads + the expect_tx arrive
         mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
       }
@@ -168,62 +187,110 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     const int r = threadIdx.x;  // GEMM row owned by this thread
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t xr = (uint32_t)(r & 7);
-    int stage = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int phase = tile / P.tiles_per_phase;
-      const int mt = tile - phase * P.tiles_per_phase;
-      const TapTable& tt = g.phase[phase];
+    const bool fuse = P.pro_scale != nullptr;
+
+    // A cursor walks the CTA's flattened (tile, k-block) sequence.  "head" issues the
+    // copies, "tail" follows D k-blocks behind and publishes them to the MMA warp.
+    struct Cursor {
+      int tile, kb, nkb, phase, stage;
+      uint32_t par;
+      bool valid;
+      int bh, bw;
+      const bf16* in_b;
+    };
+    auto load_tile = [&](Cursor& c) {
+      if (c.tile >= P.total_tiles) return;
+      c.phase = c.tile / P.tiles_per_phase;
+      const int mt = c.tile - c.phase * P.tiles_per_phase;
       const long long m = (long long)mt * kTileM + r;
-      const bool valid = m < M_total;
-      int b = 0, bh = 0, bw = 0;
-      if (valid) {
+      c.valid = m < M_total;
+      int b = 0;
+      c.bh = 0; c.bw = 0;
+      if (c.valid) {
         int jw = (int)(m % g.Wj);
         long long t2 = m / g.Wj;
-        bh = (int)(t2 % g.Hj) * g.in_mul;
+        c.bh = (int)(t2 % g.Hj) * g.in_mul;
         b = (int)(t2 / g.Hj);
-        bw = jw * g.in_mul;
+        c.bw = jw * g.in_mul;
       }
-      const bf16* in_b = P.in + (long long)b * g.Hin * g.Win * g.Cin;
-      const int nkb = P.nkb[phase];
-      const int ntaps = tt.ntaps;
-      const bf16* wsrc = P.wpk + P.b_off[phase];
-
-      uint4 cur[8], nxt[8];
-      auto gather = [&](int kb, uint4* v) {
+      c.in_b = P.in + (long long)b * g.Hin * g.Win * g.Cin;
+      c.nkb = P.nkb[c.phase];
+      c.kb = 0;
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.stage == kStages) { c.stage = 0; c.par ^= 1u; }
+      if (++c.kb == c.nkb) {
+        c.tile += gridDim.x;
+        load_tile(c);
+      }
+    };
+    // source of chunk j of the cursor's k-block, or nullptr for zero padding
+    auto chunk_src = [&](const Cursor& c, int j, int& c8_out) -> const bf16* {
+      const TapTable& tt = g.phase[c.phase];
+      const int q = c.kb * 8 + j;
+      const int tap_i = q / P.cpt;
+      const int c8 = q - tap_i * P.cpt;
+      c8_out = c8;
+      if (!c.valid || tap_i >= tt.ntaps) return nullptr;
+      const int ih = c.bh + tt.dh[tap_i], iw = c.bw + tt.dw[tap_i];
+      if (ih < 0 || ih >= g.Hin || iw < 0 || iw >= g.Win) return nullptr;
+      return c.in_b + ((long long)ih * g.Win + iw) * g.Cin + c8 * 8;
+    };
+    auto issue = [&](Cursor& c) {
+      mbar_wait(&empty_bar[c.stage], c.par ^ 1u);
+      uint8_t* a_st = smem + c.stage * stage_bytes;
+      if (r == 0) {
+        mbar_arrive_expect_tx(&full_bar[c.stage], (uint32_t)(N * 128));
+        bulk_g2s(a_st + kABytes, P.wpk + P.b_off[c.phase] + (long long)c.kb * N * 64, (uint32_t)(N * 128),
+                 &full_bar[c.stage]);
+      }
+      const uint32_t a_row = smem_u32(a_st) + row_off;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int c8;
+        const bf16* src = chunk_src(c, j, c8);
+        cp_async_16_zfill(a_row + (((uint32_t)j ^ xr) << 4), src != nullptr ? src : P.in, src != nullptr ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    auto publish = [&](Cursor& c) {
+      if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this thread's own row
+        uint8_t* a_row = smem + c.stage * stage_bytes + row_off;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int q = kb * 8 + j;
-          const int tap_i = q / P.cpt;
-          const int c8 = q - tap_i * P.cpt;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
-          if (valid && tap_i < ntaps) {
-            const int ih = bh + tt.dh[tap_i], iw = bw + tt.dw[tap_i];
-            if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) {
-              val = ldg_nc_v4(in_b + ((long long)ih * g.Win + iw) * g.Cin + c8 * 8);
-              if (P.pro_scale != nullptr) val = bn_lrelu_8(val, s_pro, s_pro + g.Cin, c8 * 8, P.slope);
-            }
+          int c8;
+          if (chunk_src(c, j, c8) != nullptr) {
+            uint4* p4 = reinterpret_cast<uint4*>(a_row + (((uint32_t)j ^ xr) << 4));
+            *p4 = bn_lrelu_8(*p4, s_pro, s_pro + g.Cin, s_pro + 2 * g.Cin, c8 * 8, P.slope);
           }
-          v[j] = val;
         }
-      };
-      gather(0, cur);
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (kb + 1 < nkb) gather(kb + 1, nxt);
-        mbar_wait(&empty_bar[stage], ph ^ 1u);
-        uint8_t* a_st = smem + stage * stage_bytes;
-        if (r == 0) {
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
-          bulk_g2s(a_st + kABytes, wsrc + (long long)kb * N * 64, (uint32_t)(N * 128), &full_bar[stage]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(a_st + row_off + (((uint32_t)j ^ xr) << 4)) = cur[j];
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[stage]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-        if (++stage == kStages) { stage = 0; ph ^= 1u; }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full_bar[c.stage]);
+    };
+
+    Cursor head, tail;
+    head.tile = blockIdx.x; head.stage = 0; head.par = 0; head.kb = 0; head.nkb = 0;
+    load_tile(head);
+    tail = head;
+    int in_flight = 0;
+    const int D = P.depth;
+    for (;;) {
+      const bool head_live = head.tile < P.total_tiles;
+      if (head_live && in_flight <= D) {
+        issue(head);
+        advance(head);
+        ++in_flight;
+      } else if (in_flight > 0) {
+        if (!head_live) cp_async_wait<0>();
+        else if (D == 4) cp_async_wait<4>();
+        else if (D == 3) cp_async_wait<3>();
+        else cp_async_wait<2>();
+        publish(tail);
+        advance(tail);
+        --in_flight;
+      } else {
+        break;
       }
     }
   } else if (warp == 8) {
@@ -353,6 +420,11 @@ static void fill_params(UmmaGatherParams& P, const GatherGeom& g) {
   int cols = 32;
   while (cols < 2 * g.Nout) cols *= 2;
   P.tmem_cols = cols;
+  P.stages = (200 * 1024) / (kABytes + P.b_stage_bytes);
+  if (P.stages > kMaxStages) P.stages = kMaxStages;
+  P.depth = P.stages - 2;
+  if (P.depth > 4) P.depth = 4;
+  if (P.depth < 2) P.depth = 2;
   long long M = (long long)g.B * g.Hj * g.Wj;
   P.tiles_per_phase = (int)((M + kTileM - 1) / kTileM);
   P.total_tiles = P.tiles_per_phase * g.nphase;
@@ -376,7 +448,7 @@ static long long packed_elems(const UmmaGatherParams& P) {
 }
 
 static int launch_umma(UmmaGatherParams& P, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)kStages * (kABytes + P.b_stage_bytes) + 128 + 16 + 2 * 256 * 4 + 2 * 2048 * 4;
+  size_t smem = 1024 + (size_t)P.stages * (kABytes + P.b_stage_bytes) + 256 + 16 + 2 * 256 * 4 + 3 * 2048 * 4;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -436,13 +508,14 @@ extern "C" int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int 
 /* Conv forward (mode 0) / data gradient == ConvTranspose forward (mode 1) on the
  * tcgen05 path.  `in`, `out` NHWC bf16; wpk from vae_umma_pack_weight(same Ci, Co,
  * stride, mode).  Hi, Wi are the HIGH-resolution (conv input side) extents as in
- * vae_conv_fprop / vae_conv_dgrad.  pro_scale/pro_shift (nullable, fp32 [C_in_gemm])
- * fuse the previous layer's BatchNorm + LeakyReLU into the operand load. */
+ * vae_conv_fprop / vae_conv_dgrad.  pro_scale/pro_mean/pro_beta (nullable, fp32
+ * [C_in_gemm]) fuse the previous layer's BatchNorm + LeakyReLU into the operand load. */
 extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
-                             const float* pro_scale, const float* pro_shift, float slope, int B, int Hi,
-                             int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+                             const float* pro_scale, const float* pro_mean, const float* pro_beta, float slope,
+                             int B, int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
   VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
-                  (mode == 0 || mode == 1) && ((pro_scale == nullptr) == (pro_shift == nullptr)),
+                  (mode == 0 || mode == 1) && ((pro_scale == nullptr) == (pro_mean == nullptr)) &&
+                  ((pro_scale == nullptr) == (pro_beta == nullptr)),
               "conv_umma: bad argument");
   GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
   VAE_REQUIRE(umma_shape_ok(g.Cin, g.Nout), "conv_umma: shape (Cin=%d, N=%d) not served by the tcgen05 path", g.Cin, g.Nout);
@@ -451,7 +524,7 @@ extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias,
   UmmaGatherParams P{};
   fill_params(P, g);
   P.in = (const bf16*)in; P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
-  P.pro_scale = pro_scale; P.pro_shift = pro_shift; P.slope = slope;
+  P.pro_scale = pro_scale; P.pro_mean = pro_mean; P.pro_beta = pro_beta; P.slope = slope;
   return launch_umma(P, st);
 }
 

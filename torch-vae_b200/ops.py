@@ -61,8 +61,14 @@ class _Proxy:
     def __init__(self, lib):
         self._lib = lib
 
+    _QUERIES = frozenset({"vae_abi_version", "vae_last_error", "vae_has_umma", "vae_set_umma", "vae_set_umma_wgrad",
+                          "vae_umma_packed_elems", "vae_umma_wgrad_supported"})
+
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
+        if name in self._QUERIES:  # host-only queries: not kernel launches
+            setattr(self, name, fn)
+            return fn
 
         def call(*args):
             global LAUNCHES
@@ -396,8 +402,8 @@ def conv_umma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int, p
               slope: float = LRELU_SLOPE):
     """mode 0: inp = x [B,Hi,Wi,Ci] -> y [B,Hi/s,Wi/s,Co];
     mode 1: inp = dy [B,Hi/s,Wi/s,Co] -> dx [B,Hi,Wi,Ci].
-    pro = BatchNorm vec (scale, shift, ...) of the layer that produced ``inp``: its
-    BN+LeakyReLU is applied while the operand is gathered."""
+    pro = (vec, beta) of the BatchNorm that follows the layer which produced ``inp``:
+    its BN+LeakyReLU is applied while the operand is gathered."""
     if inp.dtype != torch.bfloat16:
         raise RuntimeError("conv_umma: bf16 activations only")
     B = inp.shape[0]
@@ -407,9 +413,10 @@ def conv_umma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int, p
     else:
         Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
         out = torch.empty((B, Hi, Wi, Ci), dtype=torch.bfloat16, device=inp.device)
-    ps = pro[0].data_ptr() if pro is not None else None
-    pf = pro[1].data_ptr() if pro is not None else None
-    rc = _L().vae_conv_umma(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), _p(stats), ps, pf, slope,
+    ps = pro[0][0].data_ptr() if pro is not None else None
+    pm = pro[0][2].data_ptr() if pro is not None else None
+    pb = _f32(pro[1], "bn bias") if pro is not None else None
+    rc = _L().vae_conv_umma(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), _p(stats), ps, pm, pb, slope,
                             B, Hi, Wi, Ci, Co, stride, mode, _stream())
     _lib.check(rc, "vae_conv_umma")
     return out
