@@ -7,11 +7,11 @@
 //
 //   D[128 pixels x N channels] (TMEM, fp32) += A[128 x 64] (smem) * B[N x 64]^T (smem)
 //
-//   warps 0-3  A producers: one output pixel (GEMM row) per thread; per k-block
-//              the thread gathers its row's 64 input channels (8 x 16 B, one tap
-//              of the 3x3 window) from NHWC global memory with cp.async (zero-fill
-//              for padding) straight into the 128B-swizzled K-major tile UMMA
-//              expects.  Up to D+1 k-blocks per thread are in flight (a ring that
+//   warps 0-7  A producers: per k-block every GEMM row (output pixel) needs 64 input
+//              channels (8 x 16 B, one tap of the 3x3 window).  Thread t copies chunk
+//              column t%8 of rows t/8 + 32*i with cp.async (zero-fill for padding)
+//              straight into the 128B-swizzled K-major tile UMMA expects; the 8
+//              lanes of a row fetch 128 contiguous bytes.  Up to D+1 k-blocks per thread are in flight (a ring that
 //              runs across tile boundaries), so ~80 KB per SM is always
 //              outstanding.  When a k-block has landed the thread optionally
 //              applies the PREVIOUS layer's BatchNorm+LeakyReLU to its own row in
@@ -19,10 +19,10 @@
 //              The weight tile of the k-block is a pre-swizzled contiguous image
 //              in global memory and arrives by ONE bulk-TMA copy (cp.async.bulk)
 //              signalling the same mbarrier.
-//   warp  8    MMA issuer: one elected thread issues 4 x tcgen05.mma (K=16 each)
+//   warp  12   MMA issuer: one elected thread issues 4 x tcgen05.mma (K=16 each)
 //              per k-block and commits to the stage's "empty" mbarrier; after the
 //              last k-block it commits to the accumulator's "full" mbarrier.
-//   warps 4-7  epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM,
+//   warps 8-11 epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM,
 //              so the epilogue of tile i overlaps the main loop of tile i+1), add
 //              bias, accumulate per-channel sum / sum-of-squares for the following
 //              train-mode BatchNorm (warp transpose-reduce -> smem -> one fp64
@@ -41,7 +41,14 @@ constexpr int kMaxStages = 6;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
-constexpr int kThreads = 288;
+constexpr int kProducers = 256;                   // 8 producer warps
+constexpr int kThreads = kProducers + 128 + 32;   // + 4 epilogue warps + 1 MMA warp
+constexpr int kRowRing = 8;  // tiles whose row geometry is kept in shared memory (> tiles in flight)
+
+struct __align__(16) RowInfo {
+  long long off;  // element offset of the row's image in the gathered tensor, -1: row beyond M
+  int bh, bw;     // in_mul * (jh, jw)
+};
 
 struct UmmaGatherParams {
   GatherGeom g;
@@ -149,22 +156,25 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
   float* s_pro = s_stats + 2 * 256;                         // [3][Cin] (scale, mean, beta)
+  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [kRowRing][128]
+  float* s_bias = reinterpret_cast<float*>(s_rows + kRowRing * kTileM);  // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
   const int N = P.N;
 
   for (int i = threadIdx.x; i < 2 * N; i += kThreads) s_stats[i] = 0.0f;
+  for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
   if (P.pro_scale != nullptr)
     for (int i = threadIdx.x; i < g.Cin; i += kThreads) {
       s_pro[i] = P.pro_scale[i];
       s_pro[g.Cin + i] = P.pro_mean[i];
       s_pro[2 * g.Cin + i] = P.pro_beta[i];
     }
-  if (warp == 8) {
+  if (warp == 12) {
     if (lane == 0) {
       for (int s = 0; s < kMaxStages; ++s) {
-        mbar_init(&full_bar[s], 128 + 1);  // 128 producer threads + the expect_tx arrive
+        mbar_init(&full_bar[s], kProducers + 1);  // producer threads + the expect_tx arrive
         mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
       }
       for (int a = 0; a < 2; ++a) {
@@ -182,86 +192,113 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   const uint32_t tmem_base = *tmem_ptr;
   const long long M_total = (long long)g.B * g.Hj * g.Wj;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =========================== A/B producers ===========================
-    const int r = threadIdx.x;  // GEMM row owned by this thread
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t xr = (uint32_t)(r & 7);
+    // Thread t copies 16-byte chunk column j = t % 8 of rows r0 + 32*i (r0 = t / 8):
+    // the 8 lanes of a row fetch 128 contiguous bytes, so one warp-wide cp.async
+    // touches 4-8 cache lines instead of 32.  Row geometry of each tile in flight
+    // lives in a small shared-memory ring written by the producers themselves.
+    const int t = threadIdx.x;
+    const int j = t & 7, r0 = t >> 3;
+    const uint32_t dst_off = (uint32_t)r0 * 128u + ((((uint32_t)j) ^ ((uint32_t)r0 & 7u)) << 4);
     const bool fuse = P.pro_scale != nullptr;
 
-    // A cursor walks the CTA's flattened (tile, k-block) sequence.  "head" issues the
-    // copies, "tail" follows D k-blocks behind and publishes them to the MMA warp.
     struct Cursor {
-      int tile, kb, nkb, phase, stage;
+      int tile, kb, nkb, phase, stage, slot;
       uint32_t par;
-      bool valid;
-      int bh, bw;
-      const bf16* in_b;
     };
-    auto load_tile = [&](Cursor& c) {
+    auto load_tile = [&](Cursor& c, bool is_head) {
       if (c.tile >= P.total_tiles) return;
       c.phase = c.tile / P.tiles_per_phase;
-      const int mt = c.tile - c.phase * P.tiles_per_phase;
-      const long long m = (long long)mt * kTileM + r;
-      c.valid = m < M_total;
-      int b = 0;
-      c.bh = 0; c.bw = 0;
-      if (c.valid) {
-        int jw = (int)(m % g.Wj);
-        long long t2 = m / g.Wj;
-        c.bh = (int)(t2 % g.Hj) * g.in_mul;
-        b = (int)(t2 / g.Hj);
-        c.bw = jw * g.in_mul;
-      }
-      c.in_b = P.in + (long long)b * g.Hin * g.Win * g.Cin;
       c.nkb = P.nkb[c.phase];
       c.kb = 0;
+      if (is_head) {  // publish this tile's row geometry: thread t < 128 owns row t
+        if (t < kTileM) {
+          const int mt = c.tile - c.phase * P.tiles_per_phase;
+          const long long m = (long long)mt * kTileM + t;
+          RowInfo ri;
+          ri.off = -1; ri.bh = 0; ri.bw = 0;
+          if (m < M_total) {
+            int jw = (int)(m % g.Wj);
+            long long t2 = m / g.Wj;
+            ri.bh = (int)(t2 % g.Hj) * g.in_mul;
+            ri.bw = jw * g.in_mul;
+            ri.off = (t2 / g.Hj) * (long long)g.Hin * g.Win * g.Cin;
+          }
+          s_rows[c.slot * kTileM + t] = ri;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
     };
-    auto advance = [&](Cursor& c) {
+    auto advance = [&](Cursor& c, bool is_head) {
       if (++c.stage == kStages) { c.stage = 0; c.par ^= 1u; }
       if (++c.kb == c.nkb) {
         c.tile += gridDim.x;
-        load_tile(c);
+        c.slot = (c.slot + 1) & (kRowRing - 1);
+        load_tile(c, is_head);
       }
     };
-    // source of chunk j of the cursor's k-block, or nullptr for zero padding
-    auto chunk_src = [&](const Cursor& c, int j, int& c8_out) -> const bf16* {
+    // geometry of this thread's chunk column in the cursor's k-block
+    struct ChunkGeom { bool tap_ok; int dh, dw, c8; };
+    auto chunk_geom = [&](const Cursor& c) {
       const TapTable& tt = g.phase[c.phase];
       const int q = c.kb * 8 + j;
       const int tap_i = q / P.cpt;
-      const int c8 = q - tap_i * P.cpt;
-      c8_out = c8;
-      if (!c.valid || tap_i >= tt.ntaps) return nullptr;
-      const int ih = c.bh + tt.dh[tap_i], iw = c.bw + tt.dw[tap_i];
+      ChunkGeom cg;
+      cg.c8 = q - tap_i * P.cpt;
+      cg.tap_ok = tap_i < tt.ntaps;
+      cg.dh = cg.tap_ok ? tt.dh[tap_i] : 0;
+      cg.dw = cg.tap_ok ? tt.dw[tap_i] : 0;
+      return cg;
+    };
+    auto row_src = [&](const RowInfo& ri, const ChunkGeom& cg) -> const bf16* {
+      if (!cg.tap_ok || ri.off < 0) return nullptr;
+      const int ih = ri.bh + cg.dh, iw = ri.bw + cg.dw;
       if (ih < 0 || ih >= g.Hin || iw < 0 || iw >= g.Win) return nullptr;
-      return c.in_b + ((long long)ih * g.Win + iw) * g.Cin + c8 * 8;
+      return P.in + ri.off + ((long long)ih * g.Win + iw) * g.Cin + cg.c8 * 8;
     };
     auto issue = [&](Cursor& c) {
       mbar_wait(&empty_bar[c.stage], c.par ^ 1u);
       uint8_t* a_st = smem + c.stage * stage_bytes;
-      if (r == 0) {
+      if (t == 0) {
         mbar_arrive_expect_tx(&full_bar[c.stage], (uint32_t)(N * 128));
         bulk_g2s(a_st + kABytes, P.wpk + P.b_off[c.phase] + (long long)c.kb * N * 64, (uint32_t)(N * 128),
                  &full_bar[c.stage]);
       }
-      const uint32_t a_row = smem_u32(a_st) + row_off;
+      const ChunkGeom cg = chunk_geom(c);
+      const uint32_t a_dst = smem_u32(a_st) + dst_off;
+      const RowInfo* rows = s_rows + c.slot * kTileM + r0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int c8;
-        const bf16* src = chunk_src(c, j, c8);
-        cp_async_16_zfill(a_row + (((uint32_t)j ^ xr) << 4), src != nullptr ? src : P.in, src != nullptr ? 16u : 0u);
+      for (int i = 0; i < 4; ++i) {
+        const bf16* src = row_src(rows[32 * i], cg);
+        cp_async_16_zfill(a_dst + (uint32_t)i * 4096u, src != nullptr ? src : P.in, src != nullptr ? 16u : 0u);
       }
       cp_async_commit();
     };
     auto publish = [&](Cursor& c) {
-      if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this thread's own row
-        uint8_t* a_row = smem + c.stage * stage_bytes + row_off;
+      if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this thread's own chunks
+        const ChunkGeom cg = chunk_geom(c);
+        uint8_t* a_dst = smem + c.stage * stage_bytes + dst_off;
+        const RowInfo* rows = s_rows + c.slot * kTileM + r0;
+        // the thread's 8 channels are the same for all of its rows: fetch their parameters once
+        float sc[8], mn[8], bt[8];
+        {
+          const float4* ps = reinterpret_cast<const float4*>(s_pro + cg.c8 * 8);
+          const float4* pm = reinterpret_cast<const float4*>(s_pro + g.Cin + cg.c8 * 8);
+          const float4* pb = reinterpret_cast<const float4*>(s_pro + 2 * g.Cin + cg.c8 * 8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int c8;
-          if (chunk_src(c, j, c8) != nullptr) {
-            uint4* p4 = reinterpret_cast<uint4*>(a_row + (((uint32_t)j ^ xr) << 4));
-            *p4 = bn_lrelu_8(*p4, s_pro, s_pro + g.Cin, s_pro + 2 * g.Cin, c8 * 8, P.slope);
+          for (int h = 0; h < 2; ++h) {
+            float4 a = ps[h], b = pm[h], d = pb[h];
+            sc[4 * h] = a.x; sc[4 * h + 1] = a.y; sc[4 * h + 2] = a.z; sc[4 * h + 3] = a.w;
+            mn[4 * h] = b.x; mn[4 * h + 1] = b.y; mn[4 * h + 2] = b.z; mn[4 * h + 3] = b.w;
+            bt[4 * h] = d.x; bt[4 * h + 1] = d.y; bt[4 * h + 2] = d.z; bt[4 * h + 3] = d.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (row_src(rows[32 * i], cg) != nullptr) {
+            uint4* p4 = reinterpret_cast<uint4*>(a_dst + i * 4096);
+            *p4 = bn_lrelu_8(*p4, sc, mn, bt, 0, P.slope);
           }
         }
       }
@@ -270,16 +307,17 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     };
 
     Cursor head, tail;
-    head.tile = blockIdx.x; head.stage = 0; head.par = 0; head.kb = 0; head.nkb = 0;
-    load_tile(head);
+    head.tile = blockIdx.x; head.stage = 0; head.par = 0; head.kb = 0; head.nkb = 0; head.slot = 0; head.phase = 0;
     tail = head;
+    load_tile(head, true);
+    load_tile(tail, false);
     int in_flight = 0;
     const int D = P.depth;
     for (;;) {
       const bool head_live = head.tile < P.total_tiles;
       if (head_live && in_flight <= D) {
         issue(head);
-        advance(head);
+        advance(head, true);
         ++in_flight;
       } else if (in_flight > 0) {
         if (!head_live) cp_async_wait<0>();
@@ -287,13 +325,13 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
         else if (D == 3) cp_async_wait<3>();
         else cp_async_wait<2>();
         publish(tail);
-        advance(tail);
+        advance(tail, false);
         --in_flight;
       } else {
         break;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ============================ MMA issuer =============================
     const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)N, 0, 0);
     int stage = 0;
@@ -328,7 +366,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     }
   } else {
     // ============================= epilogue ==============================
-    const int ew = warp - 4;             // TMEM lane group = warp % 4
+    const int ew = warp - 8;             // TMEM lane group = warp % 4
     const int r = ew * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -361,9 +399,12 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
         }
         const int ncol = min(32, N - c0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float bvl = (P.bias != nullptr && i < ncol) ? P.bias[c0 + i] : 0.0f;
-          v[i] = (valid && i < ncol) ? v[i] + bvl : 0.0f;
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
+          v[i] = (valid && i < ncol) ? v[i] + b4.x : 0.0f;
+          v[i + 1] = (valid && i + 1 < ncol) ? v[i + 1] + b4.y : 0.0f;
+          v[i + 2] = (valid && i + 2 < ncol) ? v[i + 2] + b4.z : 0.0f;
+          v[i + 3] = (valid && i + 3 < ncol) ? v[i + 3] + b4.w : 0.0f;
         }
         if (valid) {
 #pragma unroll
@@ -392,12 +433,12 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     }
     if (P.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      for (int i = threadIdx.x - 128; i < 2 * N; i += 128) atomicAdd(&P.stats[i], (double)s_stats[i]);
+      for (int i = threadIdx.x - kProducers; i < 2 * N; i += 128) atomicAdd(&P.stats[i], (double)s_stats[i]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
@@ -420,7 +461,7 @@ static void fill_params(UmmaGatherParams& P, const GatherGeom& g) {
   int cols = 32;
   while (cols < 2 * g.Nout) cols *= 2;
   P.tmem_cols = cols;
-  P.stages = (200 * 1024) / (kABytes + P.b_stage_bytes);
+  P.stages = (172 * 1024) / (kABytes + P.b_stage_bytes);
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   P.depth = P.stages - 2;
   if (P.depth > 4) P.depth = 4;
@@ -448,7 +489,8 @@ static long long packed_elems(const UmmaGatherParams& P) {
 }
 
 static int launch_umma(UmmaGatherParams& P, cudaStream_t st) {
-  size_t smem = 1024 + (size_t)P.stages * (kABytes + P.b_stage_bytes) + 256 + 16 + 2 * 256 * 4 + 3 * 2048 * 4;
+  size_t smem = 1024 + (size_t)P.stages * (kABytes + P.b_stage_bytes) + 256 + 16 + 2 * 256 * 4 + 3 * 2048 * 4 +
+                kRowRing * kTileM * sizeof(RowInfo) + 256 * 4;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
