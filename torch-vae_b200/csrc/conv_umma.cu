@@ -46,8 +46,9 @@ constexpr int kThreads = kProducers + 128 + 32;   // + 4 epilogue warps + 1 MMA 
 constexpr int kRowRing = 8;  // tiles whose row geometry is kept in shared memory (> tiles in flight)
 
 struct __align__(16) RowInfo {
-  long long off;  // element offset of the row's image in the gathered tensor, -1: row beyond M
-  int bh, bw;     // in_mul * (jh, jw)
+  const bf16* base;  // &in[b][in_mul*jh][in_mul*jw][0]: the row's window centre (taps add a constant offset)
+  uint32_t mask;     // bit t: tap t of the phase's tap list falls inside the image (0: row beyond M)
+  uint32_t pad;
 };
 
 struct UmmaGatherParams {
@@ -132,7 +133,7 @@ __device__ __forceinline__ uint4 bn_lrelu_8(uint4 raw, const float* __restrict__
 }
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -217,13 +218,17 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
           const int mt = c.tile - c.phase * P.tiles_per_phase;
           const long long m = (long long)mt * kTileM + t;
           RowInfo ri;
-          ri.off = -1; ri.bh = 0; ri.bw = 0;
+          ri.base = P.in; ri.mask = 0u; ri.pad = 0u;
           if (m < M_total) {
-            int jw = (int)(m % g.Wj);
-            long long t2 = m / g.Wj;
-            ri.bh = (int)(t2 % g.Hj) * g.in_mul;
-            ri.bw = jw * g.in_mul;
-            ri.off = (t2 / g.Hj) * (long long)g.Hin * g.Win * g.Cin;
+            const TapTable& tt = g.phase[c.phase];
+            const int jw = (int)(m % g.Wj);
+            const long long t2 = m / g.Wj;
+            const int bh = (int)(t2 % g.Hj) * g.in_mul, bw = jw * g.in_mul;
+            ri.base = P.in + (((t2 / g.Hj) * g.Hin + bh) * (long long)g.Win + bw) * g.Cin;
+            for (int ti = 0; ti < tt.ntaps; ++ti) {
+              const int ih = bh + tt.dh[ti], iw = bw + tt.dw[ti];
+              if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) ri.mask |= 1u << ti;
+            }
           }
           s_rows[c.slot * kTileM + t] = ri;
         }
@@ -239,23 +244,23 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       }
     };
     // geometry of this thread's chunk column in the cursor's k-block
-    struct ChunkGeom { bool tap_ok; int dh, dw, c8; };
+    struct ChunkGeom { uint32_t tapbit; long long delta; int c8; };
     auto chunk_geom = [&](const Cursor& c) {
       const TapTable& tt = g.phase[c.phase];
       const int q = c.kb * 8 + j;
       const int tap_i = q / P.cpt;
       ChunkGeom cg;
       cg.c8 = q - tap_i * P.cpt;
-      cg.tap_ok = tap_i < tt.ntaps;
-      cg.dh = cg.tap_ok ? tt.dh[tap_i] : 0;
-      cg.dw = cg.tap_ok ? tt.dw[tap_i] : 0;
+      cg.tapbit = 0u;
+      cg.delta = 0;
+      if (tap_i < tt.ntaps) {
+        cg.tapbit = 1u << tap_i;
+        cg.delta = ((long long)tt.dh[tap_i] * g.Win + tt.dw[tap_i]) * g.Cin + cg.c8 * 8;
+      }
       return cg;
     };
     auto row_src = [&](const RowInfo& ri, const ChunkGeom& cg) -> const bf16* {
-      if (!cg.tap_ok || ri.off < 0) return nullptr;
-      const int ih = ri.bh + cg.dh, iw = ri.bw + cg.dw;
-      if (ih < 0 || ih >= g.Hin || iw < 0 || iw >= g.Win) return nullptr;
-      return P.in + ri.off + ((long long)ih * g.Win + iw) * g.Cin + cg.c8 * 8;
+      return (ri.mask & cg.tapbit) ? ri.base + cg.delta : nullptr;
     };
     auto issue = [&](Cursor& c) {
       mbar_wait(&empty_bar[c.stage], c.par ^ 1u);
@@ -368,6 +373,9 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     // ============================= epilogue ==============================
     const int ew = warp - 8;             // TMEM lane group = warp % 4
     const int r = ew * 32 + lane;
+    float run1[32], run2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int phase = tile / P.tiles_per_phase;
@@ -419,16 +427,34 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
           }
         }
         if (P.stats != nullptr) {
-          float sq[32];
+          if (N <= 32) {
+            // narrow layers have thousands of tiles per CTA: keep the column sums of this
+            // thread's rows in registers and reduce across the warp once, after the loop
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-          warp_transpose_reduce32(v, lane);
-          warp_transpose_reduce32(sq, lane);
-          if (lane < ncol) {
-            atomicAdd(&s_stats[c0 + lane], v[0]);
-            atomicAdd(&s_stats[N + c0 + lane], sq[0]);
+            for (int i = 0; i < 32; ++i) {
+              run1[i] += v[i];
+              run2[i] = fmaf(v[i], v[i], run2[i]);
+            }
+          } else {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            warp_transpose_reduce32(v, lane);
+            warp_transpose_reduce32(sq, lane);
+            if (lane < ncol) {
+              atomicAdd(&s_stats[c0 + lane], v[0]);
+              atomicAdd(&s_stats[N + c0 + lane], sq[0]);
+            }
           }
         }
+      }
+    }
+    if (P.stats != nullptr && N <= 32) {
+      warp_transpose_reduce32(run1, lane);
+      warp_transpose_reduce32(run2, lane);
+      if (lane < N) {
+        atomicAdd(&s_stats[lane], run1[0]);
+        atomicAdd(&s_stats[N + lane], run2[0]);
       }
     }
     if (P.stats != nullptr) {
