@@ -43,12 +43,13 @@ constexpr int kBlockK = 64;                       // bf16 elements = one 128-byt
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB
 constexpr int kProducers = 256;                   // 8 producer warps
 constexpr int kThreads = kProducers + 128 + 32;   // + 4 epilogue warps + 1 MMA warp
-constexpr int kRowRing = 8;  // tiles whose row geometry is kept in shared memory (> tiles in flight)
+constexpr int kProducerWarps = kProducers / 32;
+constexpr int kWarpDepth = 1;  // k-blocks a producer warp keeps in flight beyond the oldest
+constexpr int kRowRing = 4;    // per-warp ring of tile row tables (> tiles a warp has in flight)
 
-struct __align__(16) RowInfo {
-  const bf16* base;  // &in[b][in_mul*jh][in_mul*jw][0]: the row's window centre (taps add a constant offset)
-  uint32_t mask;     // bit t: tap t of the phase's tap list falls inside the image (0: row beyond M)
-  uint32_t pad;
+struct __align__(8) RowInfo {
+  uint32_t off;   // element offset of in[b][in_mul*jh][in_mul*jw][0], the row's window centre
+  uint32_t mask;  // bit t: tap t of the phase's tap list falls inside the image (0: row beyond M)
 };
 
 struct UmmaGatherParams {
@@ -157,8 +158,8 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
   float* s_pro = s_stats + 2 * 256;                         // [3][Cin] (scale, mean, beta)
-  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [kRowRing][128]
-  float* s_bias = reinterpret_cast<float*>(s_rows + kRowRing * kTileM);  // [256]
+  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [producer warp][kRowRing][128]
+  float* s_bias = reinterpret_cast<float*>(s_rows + kProducerWarps * kRowRing * kTileM);  // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
@@ -175,7 +176,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   if (warp == 12) {
     if (lane == 0) {
       for (int s = 0; s < kMaxStages; ++s) {
-        mbar_init(&full_bar[s], kProducers + 1);  // producer threads + the expect_tx arrive
+        mbar_init(&full_bar[s], 32 + 1);  // the 32 lanes of the owning producer warp + the expect_tx arrive
         mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
       }
       for (int a = 0; a < 2; ++a) {
@@ -195,55 +196,82 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
 
   if (warp < 8) {
     // =========================== A/B producers ===========================
-    // Thread t copies 16-byte chunk column j = t % 8 of rows r0 + 32*i (r0 = t / 8):
-    // the 8 lanes of a row fetch 128 contiguous bytes, so one warp-wide cp.async
-    // touches 4-8 cache lines instead of 32.  Row geometry of each tile in flight
-    // lives in a small shared-memory ring written by the producers themselves.
-    const int t = threadIdx.x;
-    const int j = t & 7, r0 = t >> 3;
-    const uint32_t dst_off = (uint32_t)r0 * 128u + ((((uint32_t)j) ^ ((uint32_t)r0 & 7u)) << 4);
+    // Each producer WARP owns whole tiles (tile sequence index i == warp mod 8) and
+    // produces all of their k-blocks by itself, so eight independent instruction
+    // streams overlap their latencies (division, barrier waits, table look-ups)
+    // instead of all 256 threads walking every k-block in lock step.  The shared
+    // stage ring is still filled in the global k-block order the MMA warp consumes:
+    // the ring slot of a k-block is a closed-form function of (tile index, kb).
+    // Lane l copies 16-byte chunk column j = l % 8 of rows (l / 8) + 4*i, i = 0..31:
+    // the 8 lanes of a row fetch 128 contiguous bytes.
+    const int pw = warp;
+    const int j = lane & 7, rsub = lane >> 3;
     const bool fuse = P.pro_scale != nullptr;
+    RowInfo* my_rows = s_rows + pw * kRowRing * kTileM;
+    const int G = (int)gridDim.x;
+    const int n_my = (P.total_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
+    // first tile-sequence index of this CTA that lies in phase p (phases are contiguous in tile id)
+    int fi[5];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+      long long lo = (long long)p * P.tiles_per_phase - blockIdx.x;
+      int f = lo <= 0 ? 0 : (int)((lo + G - 1) / G);
+      fi[p] = (p >= g.nphase || f > n_my) ? n_my : f;
+    }
+    auto seq_of = [&](int i) {  // global k-block sequence number of tile i's first k-block
+      int sq = 0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        int a = min(i, fi[p + 1]) - fi[p];
+        if (a > 0) sq += a * P.nkb[p];
+      }
+      return sq;
+    };
+    const uint32_t M32 = (uint32_t)M_total;
 
     struct Cursor {
-      int tile, kb, nkb, phase, stage, slot;
-      uint32_t par;
+      int i, kb, nkb, phase, seq, slot;
     };
     auto load_tile = [&](Cursor& c, bool is_head) {
-      if (c.tile >= P.total_tiles) return;
-      c.phase = c.tile / P.tiles_per_phase;
+      if (c.i >= n_my) return;
+      const int tile = (int)blockIdx.x + c.i * G;
+      c.phase = tile / P.tiles_per_phase;
       c.nkb = P.nkb[c.phase];
       c.kb = 0;
-      if (is_head) {  // publish this tile's row geometry: thread t < 128 owns row t
-        if (t < kTileM) {
-          const int mt = c.tile - c.phase * P.tiles_per_phase;
-          const long long m = (long long)mt * kTileM + t;
+      c.seq = seq_of(c.i);
+      if (is_head) {  // this tile's row geometry: 4 rows per lane, warp-private table
+        const TapTable& tt = g.phase[c.phase];
+        const int mt = tile - c.phase * P.tiles_per_phase;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = lane + 32 * k;
+          const uint32_t m = (uint32_t)mt * kTileM + row;
           RowInfo ri;
-          ri.base = P.in; ri.mask = 0u; ri.pad = 0u;
-          if (m < M_total) {
-            const TapTable& tt = g.phase[c.phase];
-            const int jw = (int)(m % g.Wj);
-            const long long t2 = m / g.Wj;
-            const int bh = (int)(t2 % g.Hj) * g.in_mul, bw = jw * g.in_mul;
-            ri.base = P.in + (((t2 / g.Hj) * g.Hin + bh) * (long long)g.Win + bw) * g.Cin;
+          ri.off = 0u; ri.mask = 0u;
+          if (m < M32) {
+            const uint32_t jw = m % (uint32_t)g.Wj, t2 = m / (uint32_t)g.Wj;
+            const uint32_t jh = t2 % (uint32_t)g.Hj, b = t2 / (uint32_t)g.Hj;
+            const int bh = (int)jh * g.in_mul, bw = (int)jw * g.in_mul;
+            ri.off = ((b * (uint32_t)g.Hin + (uint32_t)bh) * (uint32_t)g.Win + (uint32_t)bw) * (uint32_t)g.Cin;
             for (int ti = 0; ti < tt.ntaps; ++ti) {
               const int ih = bh + tt.dh[ti], iw = bw + tt.dw[ti];
               if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) ri.mask |= 1u << ti;
             }
           }
-          s_rows[c.slot * kTileM + t] = ri;
+          my_rows[c.slot * kTileM + row] = ri;
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        __syncwarp();
       }
     };
     auto advance = [&](Cursor& c, bool is_head) {
-      if (++c.stage == kStages) { c.stage = 0; c.par ^= 1u; }
+      ++c.seq;
       if (++c.kb == c.nkb) {
-        c.tile += gridDim.x;
+        c.i += kProducerWarps;
         c.slot = (c.slot + 1) & (kRowRing - 1);
         load_tile(c, is_head);
       }
     };
-    // geometry of this thread's chunk column in the cursor's k-block
+    // geometry of this lane's chunk column in the cursor's k-block
     struct ChunkGeom { uint32_t tapbit; long long delta; int c8; };
     auto chunk_geom = [&](const Cursor& c) {
       const TapTable& tt = g.phase[c.phase];
@@ -259,34 +287,40 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       }
       return cg;
     };
-    auto row_src = [&](const RowInfo& ri, const ChunkGeom& cg) -> const bf16* {
-      return (ri.mask & cg.tapbit) ? ri.base + cg.delta : nullptr;
+    // byte offset of (row rsub + 4*i, chunk j) inside a swizzled A stage
+    auto dst_of = [&](int i) -> uint32_t {
+      const uint32_t row = (uint32_t)(rsub + 4 * i);
+      return row * 128u + ((((uint32_t)j) ^ (row & 7u)) << 4);
     };
     auto issue = [&](Cursor& c) {
-      mbar_wait(&empty_bar[c.stage], c.par ^ 1u);
-      uint8_t* a_st = smem + c.stage * stage_bytes;
-      if (t == 0) {
-        mbar_arrive_expect_tx(&full_bar[c.stage], (uint32_t)(N * 128));
+      const int stage = c.seq % kStages;
+      const uint32_t par = (uint32_t)(c.seq / kStages) & 1u;
+      mbar_wait(&empty_bar[stage], par ^ 1u);
+      uint8_t* a_st = smem + stage * stage_bytes;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
         bulk_g2s(a_st + kABytes, P.wpk + P.b_off[c.phase] + (long long)c.kb * N * 64, (uint32_t)(N * 128),
-                 &full_bar[c.stage]);
+                 &full_bar[stage]);
       }
       const ChunkGeom cg = chunk_geom(c);
-      const uint32_t a_dst = smem_u32(a_st) + dst_off;
-      const RowInfo* rows = s_rows + c.slot * kTileM + r0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const bf16* src = row_src(rows[32 * i], cg);
-        cp_async_16_zfill(a_dst + (uint32_t)i * 4096u, src != nullptr ? src : P.in, src != nullptr ? 16u : 0u);
+      const uint32_t a_dst = smem_u32(a_st);
+      const RowInfo* rows = my_rows + c.slot * kTileM + rsub;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const RowInfo ri = rows[4 * i];
+        const bool ok = (ri.mask & cg.tapbit) != 0u;
+        const bf16* src = ok ? P.in + ((long long)ri.off + cg.delta) : P.in;
+        cp_async_16_zfill(a_dst + dst_of(i), src, ok ? 16u : 0u);
       }
       cp_async_commit();
     };
     auto publish = [&](Cursor& c) {
-      if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this thread's own chunks
+      const int stage = c.seq % kStages;
+      if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this lane's own chunks
         const ChunkGeom cg = chunk_geom(c);
-        uint8_t* a_dst = smem + c.stage * stage_bytes + dst_off;
-        const RowInfo* rows = s_rows + c.slot * kTileM + r0;
-        // the thread's 8 channels are the same for all of its rows: fetch their parameters once
-        float sc[8], mn[8], bt[8];
+        uint8_t* a_st = smem + stage * stage_bytes;
+        const RowInfo* rows = my_rows + c.slot * kTileM + rsub;
+        float sc[8], mn[8], bt[8];  // the lane's 8 channels are the same for all of its rows
         {
           const float4* ps = reinterpret_cast<const float4*>(s_pro + cg.c8 * 8);
           const float4* pm = reinterpret_cast<const float4*>(s_pro + g.Cin + cg.c8 * 8);
@@ -299,36 +333,33 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
             bt[4 * h] = d.x; bt[4 * h + 1] = d.y; bt[4 * h + 2] = d.z; bt[4 * h + 3] = d.w;
           }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (row_src(rows[32 * i], cg) != nullptr) {
-            uint4* p4 = reinterpret_cast<uint4*>(a_dst + i * 4096);
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          if (rows[4 * i].mask & cg.tapbit) {
+            uint4* p4 = reinterpret_cast<uint4*>(a_st + dst_of(i));
             *p4 = bn_lrelu_8(*p4, sc, mn, bt, 0, P.slope);
           }
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(&full_bar[c.stage]);
+      mbar_arrive(&full_bar[stage]);
     };
 
-    Cursor head, tail;
-    head.tile = blockIdx.x; head.stage = 0; head.par = 0; head.kb = 0; head.nkb = 0; head.slot = 0; head.phase = 0;
-    tail = head;
+    Cursor head;
+    head.i = pw; head.kb = 0; head.nkb = 0; head.phase = 0; head.seq = 0; head.slot = 0;
+    Cursor tail = head;
     load_tile(head, true);
     load_tile(tail, false);
     int in_flight = 0;
-    const int D = P.depth;
     for (;;) {
-      const bool head_live = head.tile < P.total_tiles;
-      if (head_live && in_flight <= D) {
+      const bool head_live = head.i < n_my;
+      if (head_live && in_flight <= kWarpDepth) {
         issue(head);
         advance(head, true);
         ++in_flight;
       } else if (in_flight > 0) {
         if (!head_live) cp_async_wait<0>();
-        else if (D == 4) cp_async_wait<4>();
-        else if (D == 3) cp_async_wait<3>();
-        else cp_async_wait<2>();
+        else cp_async_wait<kWarpDepth>();
         publish(tail);
         advance(tail, false);
         --in_flight;
@@ -487,7 +518,7 @@ static void fill_params(UmmaGatherParams& P, const GatherGeom& g) {
   int cols = 32;
   while (cols < 2 * g.Nout) cols *= 2;
   P.tmem_cols = cols;
-  P.stages = (172 * 1024) / (kABytes + P.b_stage_bytes);
+  P.stages = (150 * 1024) / (kABytes + P.b_stage_bytes);
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   P.depth = P.stages - 2;
   if (P.depth > 4) P.depth = 4;
@@ -516,7 +547,7 @@ static long long packed_elems(const UmmaGatherParams& P) {
 
 static int launch_umma(UmmaGatherParams& P, cudaStream_t st) {
   size_t smem = 1024 + (size_t)P.stages * (kABytes + P.b_stage_bytes) + 256 + 16 + 2 * 256 * 4 + 3 * 2048 * 4 +
-                kRowRing * kTileM * sizeof(RowInfo) + 256 * 4;
+                kProducerWarps * kRowRing * kTileM * sizeof(RowInfo) + 256 * 4;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -587,6 +618,8 @@ extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias,
               "conv_umma: bad argument");
   GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
   VAE_REQUIRE(umma_shape_ok(g.Cin, g.Nout), "conv_umma: shape (Cin=%d, N=%d) not served by the tcgen05 path", g.Cin, g.Nout);
+  VAE_REQUIRE((long long)g.B * g.Hin * g.Win * g.Cin < (1LL << 32) && (long long)g.B * g.Hj * g.Wj < (1LL << 31),
+              "conv_umma: tensor too large for 32-bit row offsets");
   cudaStream_t st = as_stream(stream);
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
   UmmaGatherParams P{};
