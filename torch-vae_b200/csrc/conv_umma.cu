@@ -137,6 +137,14 @@ __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void*
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -156,6 +164,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* s_consumed = tmem_ptr + 1;  // k-blocks whose MMAs have completed (written by the MMA warp)
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
   float* s_pro = s_stats + 2 * 256;                         // [3][Cin] (scale, mean, beta)
   RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [producer warp][kRowRing][128]
@@ -175,6 +184,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     }
   if (warp == 12) {
     if (lane == 0) {
+      tmem_ptr[1] = 0u;
       for (int s = 0; s < kMaxStages; ++s) {
         mbar_init(&full_bar[s], 32 + 1);  // the 32 lanes of the owning producer warp + the expect_tx arrive
         mbar_init(&empty_bar[s], 1);       // one tcgen05.commit
@@ -294,8 +304,13 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     };
     auto issue = [&](Cursor& c) {
       const int stage = c.seq % kStages;
-      const uint32_t par = (uint32_t)(c.seq / kStages) & 1u;
-      mbar_wait(&empty_bar[stage], par ^ 1u);
+      // the slot is free once k-block (seq - stages) has been consumed.  Producer warps
+      // run out of order with respect to each other, so a 1-bit mbarrier parity could
+      // alias; the MMA warp publishes an exact completed-k-block count instead.
+      if (c.seq >= kStages) {
+        const uint32_t need = (uint32_t)(c.seq - kStages + 1);
+        while (ld_acquire_shared(const_cast<const uint32_t*>(s_consumed)) < need) {}
+      }
       uint8_t* a_st = smem + stage * stage_bytes;
       if (lane == 0) {
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
@@ -372,6 +387,8 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     const uint32_t idesc = make_idesc_bf16(kTileM, (uint32_t)N, 0, 0);
     int stage = 0;
     uint32_t ph = 0;
+    int prev_stage = -1;
+    uint32_t prev_ph = 0, seq = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int phase = tile / P.tiles_per_phase;
@@ -393,12 +410,24 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
             const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
             mma_bf16_ss(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          mma_commit(&empty_bar[stage]);              // smem stage reusable once these MMAs finish
+          mma_commit(&empty_bar[stage]);              // completes when these MMAs have read the stage
           if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
+        // retire the PREVIOUS k-block (its MMAs overlap the ones just issued) and publish the
+        // exact count of consumed k-blocks to the producer warps
+        if (prev_stage >= 0) {
+          mbar_wait(&empty_bar[prev_stage], prev_ph);
+          if (lane == 0) st_release_shared(const_cast<uint32_t*>(s_consumed), seq);
+        }
+        prev_stage = stage; prev_ph = ph;
+        ++seq;
         if (++stage == kStages) { stage = 0; ph ^= 1u; }
       }
+    }
+    if (prev_stage >= 0) {
+      mbar_wait(&empty_bar[prev_stage], prev_ph);
+      if (lane == 0) st_release_shared(const_cast<uint32_t*>(s_consumed), seq);
     }
   } else {
     // ============================= epilogue ==============================
