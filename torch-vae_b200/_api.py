@@ -1,6 +1,6 @@
 """Public surface of the B200-native VanillaVAE training path."""
 
-from . import engine, ops  # noqa: F401
+from . import config, data_transformations, engine, ops, parallel  # noqa: F401
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .models import VanillaVAE
 from .types_helpers import EncoderOutput, LossOutput, ModelOutput
@@ -12,6 +12,9 @@ __all__ = [
     "LossOutput",
     "ops",
     "engine",
+    "parallel",
+    "config",
+    "data_transformations",
     "load_library",
     "LIB_PATH",
 ]

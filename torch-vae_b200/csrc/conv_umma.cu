@@ -302,15 +302,15 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       const uint32_t row = (uint32_t)(rsub + 4 * i);
       return row * 128u + ((((uint32_t)j) ^ (row & 7u)) << 4);
     };
+    auto slot_free = [&](const Cursor& c) -> bool {
+      return c.seq < kStages ||
+             ld_acquire_shared(const_cast<const uint32_t*>(s_consumed)) >= (uint32_t)(c.seq - kStages + 1);
+    };
     auto issue = [&](Cursor& c) {
       const int stage = c.seq % kStages;
       // the slot is free once k-block (seq - stages) has been consumed.  Producer warps
       // run out of order with respect to each other, so a 1-bit mbarrier parity could
       // alias; the MMA warp publishes an exact completed-k-block count instead.
-      if (c.seq >= kStages) {
-        const uint32_t need = (uint32_t)(c.seq - kStages + 1);
-        while (ld_acquire_shared(const_cast<const uint32_t*>(s_consumed)) < need) {}
-      }
       uint8_t* a_st = smem + stage * stage_bytes;
       if (lane == 0) {
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
@@ -368,17 +368,19 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     int in_flight = 0;
     for (;;) {
       const bool head_live = head.i < n_my;
-      if (head_live && in_flight <= kWarpDepth) {
+      // never block on a ring slot while holding unpublished k-blocks: the slot may only
+      // free up after the MMA warp has consumed what this warp still has in flight
+      if (head_live && in_flight <= kWarpDepth && slot_free(head)) {
         issue(head);
         advance(head, true);
         ++in_flight;
       } else if (in_flight > 0) {
-        if (!head_live) cp_async_wait<0>();
-        else cp_async_wait<kWarpDepth>();
+        if (in_flight == kWarpDepth + 1) cp_async_wait<kWarpDepth>();
+        else cp_async_wait<0>();
         publish(tail);
         advance(tail, false);
         --in_flight;
-      } else {
+      } else if (!head_live) {
         break;
       }
     }
