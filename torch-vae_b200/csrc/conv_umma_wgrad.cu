@@ -17,8 +17,9 @@
 //
 // grid.x splits the pixel range (split-K); every CTA reduces its pixels into TMEM
 // and adds its partial into the fp32 OIHW gradient with red.global.add.f32.
-//   warps 0-3: cp.async producers, then the epilogue (one TMEM lane = one co each)
-//   warp  4  : TMEM allocation + single-thread tcgen05.mma issue
+//   warps 0-7: cp.async producers (pixel row = t % 64, every 4th 16-byte chunk each);
+//              warps 0-3 then run the epilogue (one TMEM lane = one co each)
+//   warp  8  : TMEM allocation + single-thread tcgen05.mma issue
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -50,7 +51,8 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kWgThreads = 160;
+constexpr int kWgProducers = 256;            // 8 producer warps
+constexpr int kWgThreads = kWgProducers + 32;  // + the MMA warp
 constexpr int kAStage = 2 * 8192;  // two 64-channel groups x 64 pixel rows x 128 B
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -82,10 +84,10 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
     for (int i = threadIdx.x; i < n16; i += kWgThreads) reinterpret_cast<uint4*>(smem)[i] = z;
     fence_proxy_async_smem();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       for (int s = 0; s < P.stages; ++s) {
-        mbar_init(&full_bar[s], 128);
+        mbar_init(&full_bar[s], kWgProducers);
         mbar_init(&empty_bar[s], 1);
       }
       mbar_init(done_bar, 1);
@@ -99,9 +101,9 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ============================ producers ============================
-    const int p = threadIdx.x & 63, half = threadIdx.x >> 6;
+    const int p = threadIdx.x & 63, part = threadIdx.x >> 6;  // pixel row, chunk residue mod 4
     const uint32_t row_off = (uint32_t)p * 128u;
     const uint32_t xr = (uint32_t)(p & 7);
     int stage = 0;
@@ -110,18 +112,19 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
       const long long j = j_begin + (long long)kb * 64 + p;
       const bool valid = j < j_end;
       int b = 0, ho = 0, wo = 0;
-      if (valid) {
-        wo = (int)(j % P.Wo);
-        long long t2 = j / P.Wo;
-        ho = (int)(t2 % P.Ho);
-        b = (int)(t2 / P.Ho);
+      if (valid) {  // J < 2^31 (checked on the host): 32-bit divisions
+        const uint32_t ju = (uint32_t)j;
+        wo = (int)(ju % (uint32_t)P.Wo);
+        const uint32_t t2 = ju / (uint32_t)P.Wo;
+        ho = (int)(t2 % (uint32_t)P.Ho);
+        b = (int)(t2 / (uint32_t)P.Ho);
       }
       mbar_wait(&empty_bar[stage], ph ^ 1u);
       const uint32_t a_base = smem_u32(smem + stage * P.stage_bytes);
       const uint32_t b_base = a_base + kAStage;
       // A: Y[j][co_base + 8*ca ...]
       const bf16* ysrc = P.Y + (valid ? j : 0) * P.Co + co_base;
-      for (int ca = half; ca < CA; ca += 2)
+      for (int ca = part; ca < CA; ca += 4)
         cp_async_16(a_base + (uint32_t)(ca >> 3) * 8192u + row_off + ((((uint32_t)ca & 7u) ^ xr) << 4),
                     ysrc + ca * 8, valid ? 16u : 0u);
       // B: X[pix(j, tap)][8*c8 ...] for the TG taps of this CTA
@@ -132,7 +135,7 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
         const bool inb = valid && ih >= 0 && ih < P.Hi && iw >= 0 && iw < P.Wi;
         const bf16* xsrc = inb ? P.X + (((long long)b * P.Hi + ih) * P.Wi + iw) * P.Ci : P.X;
         const uint32_t nbytes = inb ? 16u : 0u;
-        for (int c8 = half; c8 < P.cpt; c8 += 2) {
+        for (int c8 = part; c8 < P.cpt; c8 += 4) {
           const uint32_t cb = (uint32_t)(tl * P.cpt + c8);
           cp_async_16(b_base + (cb >> 3) * 8192u + row_off + (((cb & 7u) ^ xr) << 4), xsrc + c8 * 8, nbytes);
         }
@@ -141,12 +144,14 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
       if (++stage == P.stages) { stage = 0; ph ^= 1u; }
     }
     // ============================= epilogue =============================
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;  // co within the tile == TMEM lane
+    const int row = warp * 32 + lane;  // co within the tile == TMEM lane (warps 0-3 only)
     const int co = co_base + row;
-    const int ncols = P.TG * P.Ci;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int ncols = warp < 4 ? P.TG * P.Ci : 0;
+    if (warp < 4) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       float v[32];
       tmem_ld_32x32(t_row + (uint32_t)c0, v);
@@ -194,7 +199,7 @@ umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
   }
@@ -249,6 +254,7 @@ extern "C" int vae_conv_wgrad_umma(const void* x, const void* dy, float* dw, int
   P.Ho = Hi / stride; P.Wo = Wi / stride;
   P.J = (long long)B * P.Ho * P.Wo;
   VAE_REQUIRE(wgrad_plan(P), "conv_wgrad_umma: shape (Ci=%d, Co=%d) not served by the tcgen05 path", Ci, Co);
+  VAE_REQUIRE(P.J < (1LL << 31), "conv_wgrad_umma: too many pixels for 32-bit indexing");
   cudaStream_t st = as_stream(stream);
   VAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
   const int m_tiles = (Co + 127) / 128;
