@@ -45,7 +45,7 @@ constexpr int kProducers = 256;                   // 8 producer warps
 constexpr int kThreads = kProducers + 128 + 32;   // + 4 epilogue warps + 1 MMA warp
 constexpr int kProducerWarps = kProducers / 32;
 constexpr int kWarpDepth = 1;  // k-blocks a producer warp keeps in flight beyond the oldest
-constexpr int kRowRing = 4;    // per-warp ring of tile row tables (> tiles a warp has in flight)
+constexpr int kRowRing = 8;    // shared ring of tile row tables (> ring stages: tiles that can be in flight)
 
 struct __align__(8) RowInfo {
   uint32_t off;   // element offset of in[b][in_mul*jh][in_mul*jw][0], the row's window centre
@@ -167,8 +167,9 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   volatile uint32_t* s_consumed = tmem_ptr + 1;  // k-blocks whose MMAs have completed (written by the MMA warp)
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][N]
   float* s_pro = s_stats + 2 * 256;                         // [3][Cin] (scale, mean, beta)
-  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [producer warp][kRowRing][128]
-  float* s_bias = reinterpret_cast<float*>(s_rows + kProducerWarps * kRowRing * kTileM);  // [256]
+  RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_pro + 3 * 2048);  // [kRowRing][128]
+  float* s_bias = reinterpret_cast<float*>(s_rows + kRowRing * kTileM);  // [256]
+  uint32_t* s_ready = reinterpret_cast<uint32_t*>(s_bias + 256);       // [kRowRing]: tile index + 1 whose table is valid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
@@ -176,6 +177,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
 
   for (int i = threadIdx.x; i < 2 * N; i += kThreads) s_stats[i] = 0.0f;
   for (int i = threadIdx.x; i < 256; i += kThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
+  if (threadIdx.x < kRowRing) s_ready[threadIdx.x] = 0u;
   if (P.pro_scale != nullptr)
     for (int i = threadIdx.x; i < g.Cin; i += kThreads) {
       s_pro[i] = P.pro_scale[i];
@@ -206,80 +208,64 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
 
   if (warp < 8) {
     // =========================== A/B producers ===========================
-    // Each producer WARP owns whole tiles (tile sequence index i == warp mod 8) and
-    // produces all of their k-blocks by itself, so eight independent instruction
-    // streams overlap their latencies (division, barrier waits, table look-ups)
-    // instead of all 256 threads walking every k-block in lock step.  The shared
-    // stage ring is still filled in the global k-block order the MMA warp consumes:
-    // the ring slot of a k-block is a closed-form function of (tile index, kb).
-    // Lane l copies 16-byte chunk column j = l % 8 of rows (l / 8) + 4*i, i = 0..31:
-    // the 8 lanes of a row fetch 128 contiguous bytes.
+    // The CTA's k-blocks form one global sequence (the order the MMA warp consumes
+    // them).  Producer warp w owns k-blocks seq == w (mod 8) and produces each of them
+    // completely by itself: eight independent instruction streams, and the window of
+    // ring slots that is open at any moment always maps to distinct warps, so ~6
+    // k-blocks (96 KB) are in flight per SM.  Lane l copies 16-byte chunk column
+    // j = l % 8 of rows (l / 8) + 4*i, i = 0..31: the 8 lanes of a row fetch 128
+    // contiguous bytes.  Row geometry of a tile is computed once, by the warp that owns
+    // the tile's first k-block, into a shared ring; the others wait for its ready flag.
     const int pw = warp;
     const int j = lane & 7, rsub = lane >> 3;
     const bool fuse = P.pro_scale != nullptr;
-    RowInfo* my_rows = s_rows + pw * kRowRing * kTileM;
     const int G = (int)gridDim.x;
     const int n_my = (P.total_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
-    // first tile-sequence index of this CTA that lies in phase p (phases are contiguous in tile id)
-    int fi[5];
-#pragma unroll
-    for (int p = 0; p < 5; ++p) {
-      long long lo = (long long)p * P.tiles_per_phase - blockIdx.x;
-      int f = lo <= 0 ? 0 : (int)((lo + G - 1) / G);
-      fi[p] = (p >= g.nphase || f > n_my) ? n_my : f;
-    }
-    auto seq_of = [&](int i) {  // global k-block sequence number of tile i's first k-block
-      int sq = 0;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        int a = min(i, fi[p + 1]) - fi[p];
-        if (a > 0) sq += a * P.nkb[p];
-      }
-      return sq;
-    };
     const uint32_t M32 = (uint32_t)M_total;
 
     struct Cursor {
-      int i, kb, nkb, phase, seq, slot;
+      int seq, i, kb, nkb, phase;
     };
-    auto load_tile = [&](Cursor& c, bool is_head) {
+    auto tile_info = [&](Cursor& c) {
       if (c.i >= n_my) return;
       const int tile = (int)blockIdx.x + c.i * G;
       c.phase = tile / P.tiles_per_phase;
       c.nkb = P.nkb[c.phase];
-      c.kb = 0;
-      c.seq = seq_of(c.i);
-      if (is_head) {  // this tile's row geometry: 4 rows per lane, warp-private table
-        const TapTable& tt = g.phase[c.phase];
-        const int mt = tile - c.phase * P.tiles_per_phase;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = lane + 32 * k;
-          const uint32_t m = (uint32_t)mt * kTileM + row;
-          RowInfo ri;
-          ri.off = 0u; ri.mask = 0u;
-          if (m < M32) {
-            const uint32_t jw = m % (uint32_t)g.Wj, t2 = m / (uint32_t)g.Wj;
-            const uint32_t jh = t2 % (uint32_t)g.Hj, b = t2 / (uint32_t)g.Hj;
-            const int bh = (int)jh * g.in_mul, bw = (int)jw * g.in_mul;
-            ri.off = ((b * (uint32_t)g.Hin + (uint32_t)bh) * (uint32_t)g.Win + (uint32_t)bw) * (uint32_t)g.Cin;
-            for (int ti = 0; ti < tt.ntaps; ++ti) {
-              const int ih = bh + tt.dh[ti], iw = bw + tt.dw[ti];
-              if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) ri.mask |= 1u << ti;
-            }
-          }
-          my_rows[c.slot * kTileM + row] = ri;
-        }
-        __syncwarp();
+    };
+    auto advance = [&](Cursor& c) {
+      c.seq += kProducerWarps;
+      c.kb += kProducerWarps;
+      while (c.i < n_my && c.kb >= c.nkb) {
+        c.kb -= c.nkb;
+        ++c.i;
+        tile_info(c);
       }
     };
-    auto advance = [&](Cursor& c, bool is_head) {
-      ++c.seq;
-      if (++c.kb == c.nkb) {
-        c.i += kProducerWarps;
-        c.slot = (c.slot + 1) & (kRowRing - 1);
-        load_tile(c, is_head);
+    auto build_rows = [&](const Cursor& c) {  // 4 rows per lane
+      const TapTable& tt = g.phase[c.phase];
+      const int tile = (int)blockIdx.x + c.i * G;
+      const int mt = tile - c.phase * P.tiles_per_phase;
+      RowInfo* tab = s_rows + (c.i & (kRowRing - 1)) * kTileM;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = lane + 32 * k;
+        const uint32_t m = (uint32_t)mt * kTileM + row;
+        RowInfo ri;
+        ri.off = 0u; ri.mask = 0u;
+        if (m < M32) {
+          const uint32_t jw = m % (uint32_t)g.Wj, t2 = m / (uint32_t)g.Wj;
+          const uint32_t jh = t2 % (uint32_t)g.Hj, b = t2 / (uint32_t)g.Hj;
+          const int bh = (int)jh * g.in_mul, bw = (int)jw * g.in_mul;
+          ri.off = ((b * (uint32_t)g.Hin + (uint32_t)bh) * (uint32_t)g.Win + (uint32_t)bw) * (uint32_t)g.Cin;
+          for (int ti = 0; ti < tt.ntaps; ++ti) {
+            const int ih = bh + tt.dh[ti], iw = bw + tt.dw[ti];
+            if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) ri.mask |= 1u << ti;
+          }
+        }
+        tab[row] = ri;
       }
+      __syncwarp();
+      if (lane == 0) st_release_shared(&s_ready[c.i & (kRowRing - 1)], (uint32_t)(c.i + 1));
     };
     // geometry of this lane's chunk column in the cursor's k-block
     struct ChunkGeom { uint32_t tapbit; long long delta; int c8; };
@@ -302,15 +288,20 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       const uint32_t row = (uint32_t)(rsub + 4 * i);
       return row * 128u + ((((uint32_t)j) ^ (row & 7u)) << 4);
     };
-    auto slot_free = [&](const Cursor& c) -> bool {
-      return c.seq < kStages ||
-             ld_acquire_shared(const_cast<const uint32_t*>(s_consumed)) >= (uint32_t)(c.seq - kStages + 1);
+    // a k-block may be issued when (a) its ring slot has been consumed -- producer warps
+    // run out of order with respect to each other, so a 1-bit mbarrier parity could
+    // alias; the MMA warp publishes an exact completed-k-block count instead -- and
+    // (b) its tile's row table exists.  Never BLOCK here: the slot may only free up
+    // after the MMA warp has consumed what this warp still holds unpublished.
+    auto can_issue = [&](const Cursor& c) -> bool {
+      if (c.seq >= kStages &&
+          ld_acquire_shared(const_cast<const uint32_t*>(s_consumed)) < (uint32_t)(c.seq - kStages + 1))
+        return false;
+      return c.kb == 0 || ld_acquire_shared(&s_ready[c.i & (kRowRing - 1)]) == (uint32_t)(c.i + 1);
     };
     auto issue = [&](Cursor& c) {
+      if (c.kb == 0) build_rows(c);
       const int stage = c.seq % kStages;
-      // the slot is free once k-block (seq - stages) has been consumed.  Producer warps
-      // run out of order with respect to each other, so a 1-bit mbarrier parity could
-      // alias; the MMA warp publishes an exact completed-k-block count instead.
       uint8_t* a_st = smem + stage * stage_bytes;
       if (lane == 0) {
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(N * 128));
@@ -319,7 +310,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       }
       const ChunkGeom cg = chunk_geom(c);
       const uint32_t a_dst = smem_u32(a_st);
-      const RowInfo* rows = my_rows + c.slot * kTileM + rsub;
+      const RowInfo* rows = s_rows + (c.i & (kRowRing - 1)) * kTileM + rsub;
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
         const RowInfo ri = rows[4 * i];
@@ -334,7 +325,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       if (fuse) {  // previous layer's BatchNorm + LeakyReLU, in place on this lane's own chunks
         const ChunkGeom cg = chunk_geom(c);
         uint8_t* a_st = smem + stage * stage_bytes;
-        const RowInfo* rows = my_rows + c.slot * kTileM + rsub;
+        const RowInfo* rows = s_rows + (c.i & (kRowRing - 1)) * kTileM + rsub;
         float sc[8], mn[8], bt[8];  // the lane's 8 channels are the same for all of its rows
         {
           const float4* ps = reinterpret_cast<const float4*>(s_pro + cg.c8 * 8);
@@ -361,24 +352,26 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
     };
 
     Cursor head;
-    head.i = pw; head.kb = 0; head.nkb = 0; head.phase = 0; head.seq = 0; head.slot = 0;
+    head.seq = pw; head.i = 0; head.kb = pw; head.nkb = 0; head.phase = 0;
+    tile_info(head);
+    while (head.i < n_my && head.kb >= head.nkb) {  // position on k-block number pw
+      head.kb -= head.nkb;
+      ++head.i;
+      tile_info(head);
+    }
     Cursor tail = head;
-    load_tile(head, true);
-    load_tile(tail, false);
     int in_flight = 0;
     for (;;) {
       const bool head_live = head.i < n_my;
-      // never block on a ring slot while holding unpublished k-blocks: the slot may only
-      // free up after the MMA warp has consumed what this warp still has in flight
-      if (head_live && in_flight <= kWarpDepth && slot_free(head)) {
+      if (head_live && in_flight <= kWarpDepth && can_issue(head)) {
         issue(head);
-        advance(head, true);
+        advance(head);
         ++in_flight;
       } else if (in_flight > 0) {
         if (in_flight == kWarpDepth + 1) cp_async_wait<kWarpDepth>();
         else cp_async_wait<0>();
         publish(tail);
-        advance(tail, false);
+        advance(tail);
         --in_flight;
       } else if (!head_live) {
         break;
@@ -549,7 +542,7 @@ static void fill_params(UmmaGatherParams& P, const GatherGeom& g) {
   int cols = 32;
   while (cols < 2 * g.Nout) cols *= 2;
   P.tmem_cols = cols;
-  P.stages = (150 * 1024) / (kABytes + P.b_stage_bytes);
+  P.stages = (170 * 1024) / (kABytes + P.b_stage_bytes);
   if (P.stages > kMaxStages) P.stages = kMaxStages;
   P.depth = P.stages - 2;
   if (P.depth > 4) P.depth = 4;
@@ -578,7 +571,7 @@ static long long packed_elems(const UmmaGatherParams& P) {
 
 static int launch_umma(UmmaGatherParams& P, cudaStream_t st) {
   size_t smem = 1024 + (size_t)P.stages * (kABytes + P.b_stage_bytes) + 256 + 16 + 2 * 256 * 4 + 3 * 2048 * 4 +
-                kProducerWarps * kRowRing * kTileM * sizeof(RowInfo) + 256 * 4;
+                kRowRing * kTileM * sizeof(RowInfo) + 256 * 4 + kRowRing * 4;
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(umma_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
