@@ -89,6 +89,7 @@ int vae_conv_wgrad(const void* x, const void* dy, float* dw, int B, int Hi, int 
  * Weights are pre-packed once per optimizer step into the exact 128B-swizzled
  * shared-memory images the kernel's bulk-TMA copies fetch. */
 int vae_set_umma(int enable); /* returns the previous setting; tests use it to cross-check */
+int vae_umma_set_trace(void* buf); /* tuning aid: 6*512 int64 clock64 samples from CTA 0; NULL = off */
 long long vae_umma_packed_elems(int Ci, int Co, int stride, int mode); /* 0: shape not served */
 int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
                          vae_stream_t stream);
@@ -100,6 +101,19 @@ int vae_umma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int str
 int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
                   const float* pro_scale, const float* pro_mean, const float* pro_beta, float slope,
                   int B, int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream);
+
+/* TMA-fed variant of vae_conv_umma: the A operand of every 128-pixel tile is staged by
+ * cp.async.bulk.tensor (one strided box of the NHWC tensor per filter tap, zero-filled
+ * outside the image) instead of cp.async threads.  Serves layers whose extents decompose
+ * into whole output rows per tile and Cin == 32 or Cin % 64 == 0; no fused prologue. */
+int vae_set_umma_tma(int enable);
+int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode);
+long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode);
+int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
+                             vae_stream_t stream);
+int vae_conv_umma_tma(const void* in, const void* wpk, const float* bias, void* out, double* stats,
+                      int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
+                      vae_stream_t stream);
 
 /* Weight gradient on the tcgen05 path (both operands MN-major, split over pixels,
  * fp32 red.global.add into dw).  x, dy NHWC bf16; dw [Co][Ci][3][3] fp32, overwritten.

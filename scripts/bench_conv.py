@@ -28,7 +28,10 @@ for name, H, W, Ci, Co in LAYERS:
     st_o = torch.empty(2 * Co, dtype=torch.float64, device="cuda"); st_i = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
     xb, yb = x.numel() * 2, y.numel() * 2
     vec = torch.stack([torch.ones(Ci), torch.zeros(Ci), torch.zeros(Ci), torch.ones(Ci)]).cuda(); beta = torch.zeros(Ci, device="cuda")
+    t0, t1 = ops.umma_tma_pack_weight(w, 2, 0), ops.umma_tma_pack_weight(w, 2, 1)
     cases = {
+        "tma_fprop": (lambda: ops.conv_umma_tma(x, t0, bias_o, st_o, Ci, Co, 2, 0), xb + yb),
+        "tma_dgrad": (lambda: ops.conv_umma_tma(y, t1, bias_i, st_i, Ci, Co, 2, 1), xb + yb),
         "fprop": (lambda: ops.conv_umma(x, w0, bias_o, st_o, Ci, Co, 2, 0), xb + yb),
         "fprop_fused": (lambda: ops.conv_umma(x, w0, bias_o, st_o, Ci, Co, 2, 0, pro=(vec, beta)), xb + yb),
         "dgrad": (lambda: ops.conv_umma(y, w1, bias_i, st_i, Ci, Co, 2, 1), xb + yb),

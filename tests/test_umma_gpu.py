@@ -148,3 +148,43 @@ def test_umma_wgrad(ops, case):
     finally:
         ops._L().vae_set_umma_wgrad(1)
     assert rel_err(dw, dw2) < 1e-4
+
+
+TMA_CASES = [
+    # B, H, W, Ci, Co, stride: extents that decompose into whole output rows per 128-pixel tile
+    (2, 128, 128, 32, 32, 2),   # Wj = 64: two rows per tile
+    (3, 64, 64, 32, 64, 2),     # Wj = 32
+    (5, 32, 32, 64, 128, 2),    # Wj = 16, 128B swizzle
+    (6, 16, 16, 128, 256, 2),   # tile spans two images; two channel chunks per tap
+    (2, 16, 512, 64, 32, 2),    # wide rolls: Wj = 256, tiles of 128 pixels inside a row
+    (3, 16, 16, 32, 32, 1),     # stride 1
+    (64, 64, 64, 32, 64, 2),    # many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("case", TMA_CASES)
+def test_umma_tma_fprop_and_dgrad(ops, case):
+    B, H, W, Ci, Co, s = case
+    x = rnd(B, Ci, H, W, seed=1)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))
+    b = rnd(Co, seed=3, scale=0.1)
+    if ops.umma_tma_eligible(B, H, W, Ci, Co, s, 0):
+        ref = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), b.double(), stride=s, padding=1)
+        stats = torch.empty(2 * Co, dtype=torch.float64, device="cuda")
+        y = ops.conv_umma_tma(nhwc(x).cuda().bfloat16(), ops.umma_tma_pack_weight(w.cuda(), s, 0), b.cuda(), stats, Ci, Co, s, 0)
+        torch.cuda.synchronize()
+        assert rel_err(nchw(y.float().cpu()), ref) < TOL
+        assert rel_err(stats.cpu()[:Co], ref.sum(dim=(0, 2, 3))) < 2e-3
+        assert rel_err(stats.cpu()[Co:], (ref**2).sum(dim=(0, 2, 3))) < 2e-3
+    else:
+        assert Ci != 32 and Ci % 64 != 0
+    dy = rnd(B, Co, H // s, W // s, seed=4)
+    bi = rnd(Ci, seed=5, scale=0.1)
+    if ops.umma_tma_eligible(B, H, W, Ci, Co, s, 1):
+        ref = F.conv_transpose2d(dy.bfloat16().double(), w.bfloat16().double(), bi.double(), stride=s, padding=1,
+                                 output_padding=s - 1)
+        stats = torch.empty(2 * Ci, dtype=torch.float64, device="cuda")
+        dx = ops.conv_umma_tma(nhwc(dy).cuda().bfloat16(), ops.umma_tma_pack_weight(w.cuda(), s, 1), bi.cuda(), stats, Ci, Co, s, 1)
+        torch.cuda.synchronize()
+        assert rel_err(nchw(dx.float().cpu()), ref) < TOL
+        assert rel_err(stats.cpu()[:Ci], ref.sum(dim=(0, 2, 3))) < 2e-3

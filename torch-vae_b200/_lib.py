@@ -25,9 +25,15 @@ PROTOTYPES = {
     "vae_conv_dgrad": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_conv_wgrad": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_umma": [_i],
+    "vae_umma_set_trace": [_vp],
     "vae_umma_packed_elems": [_i, _i, _i, _i],
     "vae_umma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
     "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_set_umma_tma": [_i],
+    "vae_umma_tma_eligible": [_i, _i, _i, _i, _i, _i, _i],
+    "vae_umma_tma_packed_elems": [_i, _i, _i, _i],
+    "vae_umma_tma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "vae_conv_umma_tma": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_umma_wgrad": [_i],
     "vae_umma_wgrad_supported": [_i, _i],
     "vae_conv_wgrad_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -48,7 +54,7 @@ PROTOTYPES = {
     "vae_sigmoid_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "vae_roll_transform": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _ull, _ull, _vp],
 }
-_RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong}
+_RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong, "vae_umma_tma_packed_elems": C.c_longlong}
 
 _lib = None
 

@@ -73,6 +73,7 @@ struct UmmaGatherParams {
   const float* pro_mean;   //   leaky_relu((x - mean) * scale + beta), ATen operation order
   const float* pro_beta;
   float slope;
+  long long* trace;  // optional [6][512] clock64 samples of CTA 0 (debug / tuning aid)
 };
 
 // --------------------------------------------------------------------------
@@ -150,6 +151,12 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+#define VAE_TRACE(role, idx)                                                              \
+  do {                                                                                   \
+    if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && (idx) < 512)                \
+      P.trace[(role) * 512 + (idx)] = clock64();                                          \
+  } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
@@ -300,6 +307,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       return c.kb == 0 || ld_acquire_shared(&s_ready[c.i & (kRowRing - 1)]) == (uint32_t)(c.i + 1);
     };
     auto issue = [&](Cursor& c) {
+      VAE_TRACE(0, c.seq);
       if (c.kb == 0) build_rows(c);
       const int stage = c.seq % kStages;
       uint8_t* a_st = smem + stage * stage_bytes;
@@ -318,7 +326,14 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
         const bf16* src = ok ? P.in + ((long long)ri.off + cg.delta) : P.in;
         cp_async_16_zfill(a_dst + dst_of(i), src, ok ? 16u : 0u);
       }
-      cp_async_commit();
+      if (fuse) {
+        cp_async_commit();
+      } else {
+        // no transform needed: let the copies themselves arrive on the barrier when they
+        // land (no wait, no fence in this warp; the MMA warp fences the proxy once)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+      }
+      VAE_TRACE(1, c.seq);
     };
     auto publish = [&](Cursor& c) {
       const int stage = c.seq % kStages;
@@ -366,7 +381,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       if (head_live && in_flight <= kWarpDepth && can_issue(head)) {
         issue(head);
         advance(head);
-        ++in_flight;
+        if (fuse) ++in_flight;
       } else if (in_flight > 0) {
         if (in_flight == kWarpDepth + 1) cp_async_wait<kWarpDepth>();
         else cp_async_wait<0>();
@@ -395,6 +410,8 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], ph);
+        VAE_TRACE(2, seq);
+        fence_proxy_async_smem();  // cp.async (generic proxy) writes -> visible to the tensor core
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -409,6 +426,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
           if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
+        VAE_TRACE(3, seq);
         // retire the PREVIOUS k-block (its MMAs overlap the ones just issued) and publish the
         // exact count of consumed k-blocks to the producer warps
         if (prev_stage >= 0) {
@@ -450,6 +468,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
         dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * g.Nout;
       }
       mbar_wait(&tfull_bar[acc], acc_ph);
+      if (ew == 0) VAE_TRACE(4, it);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
       for (int c0 = 0; c0 < N; c0 += 32) {
@@ -459,6 +478,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
         if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
+          if (ew == 0) VAE_TRACE(5, it);
         }
         const int ncol = min(32, N - c0);
 #pragma unroll
@@ -529,6 +549,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
 // host side
 // ============================================================================
 static bool g_umma_enabled = true;
+static long long* g_trace = nullptr;
 
 static bool umma_shape_ok(int Cin_gemm, int Nout) {
   return g_umma_enabled && Cin_gemm % 32 == 0 && Nout % 16 == 0 && Nout >= 16 && Nout <= 256 && Cin_gemm <= 2048;
@@ -598,6 +619,13 @@ using namespace vae;
 
 extern "C" int vae_has_umma(void) { return 1; }
 
+/* tuning aid: device buffer of 6*512 int64 that CTA 0 of vae_conv_umma fills with clock64()
+ * samples per k-block / tile (NULL switches it off) */
+extern "C" int vae_umma_set_trace(void* buf) {
+  g_trace = (long long*)buf;
+  return VAE_OK;
+}
+
 extern "C" int vae_set_umma(int enable) {
   int old = g_umma_enabled ? 1 : 0;
   g_umma_enabled = enable != 0;
@@ -650,6 +678,7 @@ extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias,
   fill_params(P, g);
   P.in = (const bf16*)in; P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
   P.pro_scale = pro_scale; P.pro_mean = pro_mean; P.pro_beta = pro_beta; P.slope = slope;
+  P.trace = g_trace;
   return launch_umma(P, st);
 }
 

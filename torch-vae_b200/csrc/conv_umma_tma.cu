@@ -1,0 +1,491 @@
+// TMA-fed tcgen05 / TMEM implicit-GEMM convolution (bf16 x bf16 -> fp32), sm_100a.
+//
+// Same GEMM as conv_umma.cu (D[128 pixels x N] += A[128 x K] * B[N x K]^T, geometry
+// in conv_geom.cuh) but the A operand is staged by the TMA engine instead of by
+// cp.async threads.  The trick that makes a plain TILED tensor map do the im2col
+// gather: a 128-pixel GEMM tile is made of whole output rows (128 = n x h x w with
+// w = min(Wj,128)), so for one filter tap its input pixels form a strided BOX of
+// the NHWC tensor  {C: 64 channels, W: w pixels step in_mul, H: h rows step in_mul,
+// N: n images}  starting at (in_mul*jw0 + dw, in_mul*jh0 + dh).  One
+// cp.async.bulk.tensor.4d per tap moves it into the 128B/64B-swizzled K-major
+// sub-tile UMMA reads; coordinates outside the image (the 3x3 padding, or the far
+// edge of a transposed conv) are zero-filled by the TMA unit.  A single thread
+// issues everything: no address arithmetic, no LSU instructions, no registers.
+//
+//   warp 0     producer: per stage wait(empty) -> expect_tx -> 1-2 tensor TMA loads
+//              (A sub-tiles) + 1 bulk copy (pre-swizzled weight image)
+//   warp 1     MMA issuer (one elected thread), TMEM accumulator double-buffered
+//   warps 2-5  epilogue: tcgen05.ld, bias, BatchNorm statistics, bf16 NHWC store
+//
+// Grid = #SMs, persistent static tile schedule.  Layers whose extents do not
+// decompose into whole rows fall back to the cp.async gather kernel.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_geom.cuh"
+#include "umma.cuh"
+
+namespace vae {
+
+using namespace umma;
+
+constexpr int kTStagesMax = 6;
+constexpr int kTTileM = 128;
+constexpr int kTThreads = 192;  // producer warp, MMA warp, 4 epilogue warps
+
+struct TmaConvParams {
+  CUtensorMap tmap;
+  GatherGeom g;
+  int nkb[4];          // stages per phase
+  int b_off[4];        // element offset of the phase's first weight image
+  int tiles_per_phase, total_tiles;
+  int N;               // output channels
+  int kc;              // channels per sub-tile: 32 (64-byte swizzle) or 64 (128-byte swizzle)
+  int cin_chunks;      // sub-tiles per tap = Cin / kc
+  int sps;             // sub-tiles per stage (2 when kc == 32, else 1)
+  int sub_a_bytes;     // 128 * kc * 2
+  int sub_b_elems;     // N * kc
+  int a_stage_bytes, b_stage_bytes;
+  int stages, tmem_cols;
+  int rows_w, rows_h, rows_n;  // 128 = rows_n * rows_h * rows_w (whole output rows)
+  const bf16* wpk;
+  const float* bias;
+  bf16* out;
+  double* stats;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// shared-memory matrix descriptor with a selectable swizzle (2 = 128B, 4 = 64B)
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// weight images for this kernel: per phase, per stage: [sub][N rows][kc] bf16, rows
+// swizzled like the A sub-tiles (64B: chunk ^= (n>>1)&3, 128B: chunk ^= n&7).
+// sub-k-block q = stage*sps + sub -> tap = q / cin_chunks, channel chunk = q % cin_chunks.
+__global__ void pack_tma_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out,
+                                       const __grid_constant__ TmaConvParams P, int Co, int Ci, int mode) {
+  const int phase = blockIdx.y;
+  const TapTable& tt = P.g.phase[phase];
+  const int stage_elems = P.sps * P.sub_b_elems;
+  const long long n_elem = (long long)P.nkb[phase] * stage_elems;
+  bf16* dst = out + P.b_off[phase];
+  const int cpr = P.kc / 8;  // 16-byte chunks per row
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elem;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % P.kc);
+    const int n = (int)((i / P.kc) % P.N);
+    const int sub = (int)((i / P.sub_b_elems) % P.sps);
+    const int st = (int)(i / stage_elems);
+    const int q = st * P.sps + sub;
+    const int tap_i = q / P.cin_chunks;
+    float v = 0.0f;
+    if (tap_i < tt.ntaps) {
+      const int c = (q - tap_i * P.cin_chunks) * P.kc + e;
+      const int t = tt.wt[tap_i];
+      const int co = mode == 0 ? n : c, ci = mode == 0 ? c : n;
+      v = w[((long long)co * Ci + ci) * 9 + t];
+    }
+    const int chunk = e >> 3;
+    const int sw = cpr == 4 ? (chunk ^ ((n >> 1) & 3)) : (chunk ^ (n & 7));
+    dst[(long long)st * stage_elems + (long long)sub * P.sub_b_elems + (long long)n * P.kc + sw * 8 + (e & 7)] =
+        __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(kTThreads, 1)
+umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = P.a_stage_bytes + P.b_stage_bytes;
+  uint8_t* tail = smem + P.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kTStagesMax;
+  uint64_t* tfull_bar = empty_bar + kTStagesMax;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][256]
+  float* s_bias = s_stats + 512;                            // [256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GatherGeom& g = P.g;
+  const int N = P.N;
+  const int kStages = P.stages;
+
+  for (int i = threadIdx.x; i < 512; i += kTThreads) s_stats[i] = 0.0f;
+  for (int i = threadIdx.x; i < 256; i += kTThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kTStagesMax; ++s) {
+        mbar_init(&full_bar[s], 1);   // the producer's expect_tx arrive; TMA completes the bytes
+        mbar_init(&empty_bar[s], 1);  // one tcgen05.commit
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, (uint32_t)P.tmem_cols);
+  }
+  if (warp == 0 && lane == 0)
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const long long M_total = (long long)g.B * g.Hj * g.Wj;
+
+  if (warp == 0) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      const uint32_t b_bytes = (uint32_t)P.b_stage_bytes;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int phase = tile / P.tiles_per_phase;
+        const int mt = tile - phase * P.tiles_per_phase;
+        const TapTable& tt = g.phase[phase];
+        const uint32_t m0 = (uint32_t)mt * kTTileM;
+        const uint32_t jw0 = m0 % (uint32_t)g.Wj, t2 = m0 / (uint32_t)g.Wj;
+        const uint32_t jh0 = t2 % (uint32_t)g.Hj, b0 = t2 / (uint32_t)g.Hj;
+        const int nsub_total = tt.ntaps * P.cin_chunks;
+        const bf16* wsrc = P.wpk + P.b_off[phase];
+        const int nkb = P.nkb[phase];
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          uint8_t* a_st = smem + stage * stage_bytes;
+          const int q0 = kb * P.sps;
+          const int nsub = min(P.sps, nsub_total - q0);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nsub * P.sub_a_bytes) + b_bytes);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int q = q0 + sub;
+            const int tap_i = q / P.cin_chunks;
+            const int cc = q - tap_i * P.cin_chunks;
+            tma_load_4d(a_st + sub * P.sub_a_bytes, &P.tmap, &full_bar[stage], cc * P.kc,
+                        (int)jw0 * g.in_mul + tt.dw[tap_i], (int)jh0 * g.in_mul + tt.dh[tap_i], (int)b0);
+          }
+          bulk_g2s(a_st + P.a_stage_bytes, wsrc + (long long)kb * P.sps * P.sub_b_elems, b_bytes, &full_bar[stage]);
+          if (++stage == kStages) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================= MMA issuer =============================
+    const uint32_t idesc = make_idesc_bf16(kTTileM, (uint32_t)N, 0, 0);
+    const uint32_t layout = P.kc == 32 ? 4u : 2u;        // SWIZZLE_64B : SWIZZLE_128B
+    const uint32_t sbo = P.kc == 32 ? 512u : 1024u;      // 8 rows of 64 / 128 bytes
+    const int ksteps = P.kc / 16;
+    int stage = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int phase = tile / P.tiles_per_phase;
+      const int nkb = P.nkb[phase];
+      const int nsub_total = g.phase[phase].ntaps * P.cin_chunks;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + (uint32_t)P.a_stage_bytes;
+          const int nsub = min(P.sps, nsub_total - kb * P.sps);
+          for (int sub = 0; sub < nsub; ++sub) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_desc_sw(a_addr + sub * P.sub_a_bytes + k * 32, sbo, layout);
+              const uint64_t bd = make_desc_sw(b_addr + sub * P.sub_b_elems * 2 + k * 32, sbo, layout);
+              mma_bf16_ss(d_tmem, ad, bd, idesc, (kb > 0 || sub > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          mma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int ew = warp & 3;  // TMEM lane group = warp % 4 (warps 2,3,4,5 -> 2,3,0,1)
+    const int r = ew * 32 + lane;
+    float run1[32], run2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int phase = tile / P.tiles_per_phase;
+      const int mt = tile - phase * P.tiles_per_phase;
+      const TapTable& tt = g.phase[phase];
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const long long m = (long long)mt * kTTileM + r;
+      const bool valid = m < M_total;
+      bf16* dst = nullptr;
+      if (valid) {
+        const uint32_t mu = (uint32_t)m;
+        const uint32_t jw = mu % (uint32_t)g.Wj, t2 = mu / (uint32_t)g.Wj;
+        const uint32_t jh = t2 % (uint32_t)g.Hj, b = t2 / (uint32_t)g.Hj;
+        const int oh = (int)jh * g.out_mul + tt.ph, ow = (int)jw * g.out_mul + tt.pw;
+        dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * g.Nout;
+      }
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        const int ncol = min(32, N - c0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
+          v[i] = (valid && i < ncol) ? v[i] + b4.x : 0.0f;
+          v[i + 1] = (valid && i + 1 < ncol) ? v[i + 1] + b4.y : 0.0f;
+          v[i + 2] = (valid && i + 2 < ncol) ? v[i + 2] + b4.z : 0.0f;
+          v[i + 3] = (valid && i + 3 < ncol) ? v[i + 3] + b4.w : 0.0f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            if (i < ncol) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+              *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+            }
+          }
+        }
+        if (P.stats != nullptr) {
+          if (N <= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              run1[i] += v[i];
+              run2[i] = fmaf(v[i], v[i], run2[i]);
+            }
+          } else {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            warp_transpose_reduce32(v, lane);
+            warp_transpose_reduce32(sq, lane);
+            if (lane < ncol) {
+              atomicAdd(&s_stats[c0 + lane], v[0]);
+              atomicAdd(&s_stats[256 + c0 + lane], sq[0]);
+            }
+          }
+        }
+      }
+    }
+    if (P.stats != nullptr && N <= 32) {
+      warp_transpose_reduce32(run1, lane);
+      warp_transpose_reduce32(run2, lane);
+      if (lane < N) {
+        atomicAdd(&s_stats[lane], run1[0]);
+        atomicAdd(&s_stats[256 + lane], run2[0]);
+      }
+    }
+    if (P.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      for (int i = threadIdx.x - 64; i < N; i += 128) {
+        atomicAdd(&P.stats[i], (double)s_stats[i]);
+        atomicAdd(&P.stats[N + i], (double)s_stats[256 + i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static bool g_tma_enabled = true;
+
+// tile decomposition 128 = rows_n * rows_h * rows_w made of whole output rows
+static bool tile_rows(const GatherGeom& g, int* rw, int* rh, int* rn) {
+  if (g.Wj >= 128) {
+    if (g.Wj % 128) return false;
+    *rw = 128; *rh = 1; *rn = 1;
+    return true;
+  }
+  if (128 % g.Wj) return false;
+  int rows = 128 / g.Wj;
+  if (rows <= g.Hj) {
+    if (g.Hj % rows) return false;
+    *rw = g.Wj; *rh = rows; *rn = 1;
+    return true;
+  }
+  if (rows % g.Hj) return false;
+  *rw = g.Wj; *rh = g.Hj; *rn = rows / g.Hj;
+  return true;
+}
+
+static bool tma_plan(TmaConvParams& P, const GatherGeom& g) {
+  if (!g_tma_enabled) return false;
+  if (!(g.Cin == 32 || g.Cin % 64 == 0) || g.Cin > 2048) return false;
+  if (g.Nout % 16 || g.Nout < 16 || g.Nout > 256) return false;
+  if (!tile_rows(g, &P.rows_w, &P.rows_h, &P.rows_n)) return false;
+  if (P.rows_w * g.in_mul > 256 || P.rows_h * g.in_mul > 256 || P.rows_n > 256) return false;
+  P.g = g;
+  P.N = g.Nout;
+  P.kc = g.Cin == 32 ? 32 : 64;
+  P.cin_chunks = g.Cin / P.kc;
+  P.sps = P.kc == 32 ? 2 : 1;
+  P.sub_a_bytes = kTTileM * P.kc * 2;
+  P.sub_b_elems = g.Nout * P.kc;
+  P.a_stage_bytes = P.sps * P.sub_a_bytes;                                     // 16 KB
+  P.b_stage_bytes = (P.sps * P.sub_b_elems * 2 + 1023) / 1024 * 1024;
+  P.stages = (190 * 1024) / (P.a_stage_bytes + P.b_stage_bytes);
+  if (P.stages > kTStagesMax) P.stages = kTStagesMax;
+  if (P.stages < 2) return false;
+  int cols = 32;
+  while (cols < 2 * g.Nout) cols *= 2;
+  P.tmem_cols = cols;
+  long long M = (long long)g.B * g.Hj * g.Wj;
+  if (M >= (1LL << 31)) return false;
+  P.tiles_per_phase = (int)((M + kTTileM - 1) / kTTileM);
+  P.total_tiles = P.tiles_per_phase * g.nphase;
+  int off = 0;
+  for (int p = 0; p < 4; ++p) {
+    P.b_off[p] = off;
+    if (p < g.nphase) {
+      P.nkb[p] = (g.phase[p].ntaps * P.cin_chunks + P.sps - 1) / P.sps;
+      off += P.nkb[p] * (P.b_stage_bytes / 2);
+    } else {
+      P.nkb[p] = 0;
+    }
+  }
+  return true;
+}
+
+static long long tma_packed_elems(const TmaConvParams& P) {
+  long long n = 0;
+  for (int p = 0; p < P.g.nphase; ++p) n += (long long)P.nkb[p] * (P.b_stage_bytes / 2);
+  return n;
+}
+
+}  // namespace vae
+
+using namespace vae;
+
+extern "C" int vae_set_umma_tma(int enable) {
+  int old = g_tma_enabled ? 1 : 0;
+  g_tma_enabled = enable != 0;
+  return old;
+}
+
+/* 1 when vae_conv_umma_tma serves this layer: channel counts fit the swizzled sub-tiles and
+ * the spatial extents decompose into whole output rows per 128-pixel tile. */
+extern "C" int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode) {
+  if (B <= 0 || Hi <= 0 || Wi <= 0 || (stride != 1 && stride != 2) || Hi % stride || Wi % stride) return 0;
+  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
+  TmaConvParams P{};
+  return tma_plan(P, g) ? 1 : 0;
+}
+
+extern "C" long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode) {
+  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, Co, stride)
+                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, Co, stride);
+  TmaConvParams P{};
+  if (!tma_plan(P, g)) return 0;
+  return tma_packed_elems(P);
+}
+
+extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
+                                        vae_stream_t stream) {
+  VAE_REQUIRE(w_oihw && out && (mode == 0 || mode == 1) && (stride == 1 || stride == 2),
+              "umma_tma_pack_weight: bad argument");
+  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, Co, stride)
+                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, Co, stride);
+  TmaConvParams P{};
+  VAE_REQUIRE(tma_plan(P, g), "umma_tma_pack_weight: shape not served by the TMA path");
+  dim3 grid(64, g.nphase);
+  pack_tma_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (bf16*)out, P, Co, Ci, mode);
+  return check_launch("pack_tma_weight");
+}
+
+/* Conv forward (mode 0) / data gradient == ConvTranspose forward (mode 1) with the A
+ * operand staged by tiled TMA loads.  Same contract as vae_conv_umma (no prologue);
+ * wpk from vae_umma_tma_pack_weight. */
+extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
+                                 int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
+                  (mode == 0 || mode == 1),
+              "conv_umma_tma: bad argument");
+  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
+  TmaConvParams P{};
+  VAE_REQUIRE(tma_plan(P, g), "conv_umma_tma: shape not served by the TMA path");
+  EncodeTiledFn encode = get_encode_fn();
+  VAE_REQUIRE(encode != nullptr, "conv_umma_tma: cuTensorMapEncodeTiled is not available in this driver");
+  // NHWC tensor, innermost dimension first
+  cuuint64_t gdim[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Win, (cuuint64_t)g.Hin, (cuuint64_t)g.B};
+  cuuint64_t gstr[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Win * g.Cin * 2, (cuuint64_t)g.Hin * g.Win * g.Cin * 2};
+  // with a traversal stride s the unit loads ceil(box / s) elements: box = count * s
+  cuuint32_t box[4] = {(cuuint32_t)P.kc, (cuuint32_t)(P.rows_w * g.in_mul), (cuuint32_t)(P.rows_h * g.in_mul),
+                       (cuuint32_t)P.rows_n};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.in_mul, (cuuint32_t)g.in_mul, 1};
+  CUresult cr = encode(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       P.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VAE_REQUIRE(cr == CUDA_SUCCESS, "conv_umma_tma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  cudaStream_t st = as_stream(stream);
+  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
+  P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VAE_CUDA(cudaFuncSetAttribute(umma_tma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > P.total_tiles) grid = P.total_tiles;
+  umma_tma_conv_kernel<<<grid, kTThreads, smem, st>>>(P);
+  return check_launch("umma_tma_conv");
+}

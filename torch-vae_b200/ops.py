@@ -62,7 +62,8 @@ class _Proxy:
         self._lib = lib
 
     _QUERIES = frozenset({"vae_abi_version", "vae_last_error", "vae_has_umma", "vae_set_umma", "vae_set_umma_wgrad",
-                          "vae_umma_packed_elems", "vae_umma_wgrad_supported"})
+                          "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
+                          "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -422,6 +423,38 @@ def conv_umma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int, p
     return out
 
 
+def umma_tma_eligible(B: int, Hi: int, Wi: int, Ci: int, Co: int, stride: int, mode: int) -> bool:
+    return bool(_L().vae_umma_tma_eligible(B, Hi, Wi, Ci, Co, stride, mode))
+
+
+def umma_tma_pack_weight(w: torch.Tensor, stride: int, mode: int) -> Optional[torch.Tensor]:
+    Co, Ci = w.shape[0], w.shape[1]
+    n = int(_L().vae_umma_tma_packed_elems(Ci, Co, stride, mode))
+    if n == 0:
+        return None
+    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    rc = _L().vae_umma_tma_pack_weight(_f32(w, "conv weight"), _p(out), Ci, Co, stride, mode, _stream())
+    _lib.check(rc, "vae_umma_tma_pack_weight")
+    return out
+
+
+def conv_umma_tma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int):
+    """TMA-fed tcgen05 conv: same contract as conv_umma without the fused prologue."""
+    if inp.dtype != torch.bfloat16:
+        raise RuntimeError("conv_umma_tma: bf16 activations only")
+    B = inp.shape[0]
+    if mode == 0:
+        Hi, Wi = inp.shape[1], inp.shape[2]
+        out = torch.empty((B, Hi // stride, Wi // stride, Co), dtype=torch.bfloat16, device=inp.device)
+    else:
+        Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
+        out = torch.empty((B, Hi, Wi, Ci), dtype=torch.bfloat16, device=inp.device)
+    rc = _L().vae_conv_umma_tma(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), _p(stats), B, Hi, Wi, Ci, Co,
+                                stride, mode, _stream())
+    _lib.check(rc, "vae_conv_umma_tma")
+    return out
+
+
 class ConvWeights:
     """Per-step operand layouts of one 3x3 conv weight (fp32 OIHW master copy).
 
@@ -442,17 +475,21 @@ class ConvWeights:
             self._simt = pack_conv_weight(self.w, self.dtype)
         return self._simt
 
-    def umma(self, mode: int):
+    def umma(self, mode: int, tma: bool = False):
         if self.dtype != torch.bfloat16 or not umma_available():
             return None
-        if mode not in self._umma:
-            self._umma[mode] = umma_pack_weight(self.w, self.stride, mode)
-        return self._umma[mode]
+        key = (mode, tma)
+        if key not in self._umma:
+            pack = umma_tma_pack_weight if tma else umma_pack_weight
+            self._umma[key] = pack(self.w, self.stride, mode)
+        return self._umma[key]
 
 
 def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None):
     """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies."""
     if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == cw.Ci:
+        if pro is None and umma_tma_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+            return conv_umma_tma(x, cw.umma(0, tma=True), bias, stats, cw.Ci, cw.Co, cw.stride, 0)
         wpk = cw.umma(0)
         if wpk is not None:
             return conv_umma(x, wpk, bias, stats, cw.Ci, cw.Co, cw.stride, 0, pro=pro)
@@ -464,6 +501,9 @@ def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None,
 def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
     """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward."""
     if dy.dtype == torch.bfloat16:
+        s_ = cw.stride
+        if pro is None and umma_tma_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+            return conv_umma_tma(dy, cw.umma(1, tma=True), bias, stats, cw.Ci, cw.Co, s_, 1)
         wpk = cw.umma(1)
         if wpk is not None:
             return conv_umma(dy, wpk, bias, stats, cw.Ci, cw.Co, cw.stride, 1, pro=pro)
