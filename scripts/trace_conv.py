@@ -8,12 +8,14 @@ mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 x = torch.randn(B, H, W, Ci, device="cuda").bfloat16()
 y = torch.randn(B, H // 2, W // 2, Co, device="cuda").bfloat16()
 w = torch.randn(Co, Ci, 3, 3, device="cuda") / math.sqrt(9 * Ci)
-wpk = ops.umma_pack_weight(w, 2, mode)
+tma = len(sys.argv) > 2 and sys.argv[2] == 'tma'
+wpk = ops.umma_tma_pack_weight(w, 2, mode) if tma else ops.umma_pack_weight(w, 2, mode)
+run = (lambda: ops.conv_umma_tma(inp, wpk, None, None, Ci, Co, 2, mode)) if tma else (lambda: ops.conv_umma(inp, wpk, None, None, Ci, Co, 2, mode))
 inp = x if mode == 0 else y
-ops.conv_umma(inp, wpk, None, None, Ci, Co, 2, mode); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 buf = torch.zeros(6 * 512, dtype=torch.int64, device="cuda")
 ops._L().vae_umma_set_trace(buf.data_ptr())
-ops.conv_umma(inp, wpk, None, None, Ci, Co, 2, mode); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()
 ops._L().vae_umma_set_trace(None)
 t = buf.view(6, 512).cpu()
 t0 = int(t[0][t[0] > 0].min())

@@ -550,6 +550,7 @@ umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
 // ============================================================================
 static bool g_umma_enabled = true;
 static long long* g_trace = nullptr;
+long long* umma_trace_ptr() { return g_trace; }
 
 static bool umma_shape_ok(int Cin_gemm, int Nout) {
   return g_umma_enabled && Cin_gemm % 32 == 0 && Nout % 16 == 0 && Nout >= 16 && Nout <= 256 && Cin_gemm <= 2048;

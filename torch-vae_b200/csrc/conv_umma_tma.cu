@@ -15,7 +15,8 @@
 //   warp 0     producer: per stage wait(empty) -> expect_tx -> 1-2 tensor TMA loads
 //              (A sub-tiles) + 1 bulk copy (pre-swizzled weight image)
 //   warp 1     MMA issuer (one elected thread), TMEM accumulator double-buffered
-//   warps 2-5  epilogue: tcgen05.ld, bias, BatchNorm statistics, bf16 NHWC store
+//   warps 2-9  epilogue: two sets of four warps, one per TMEM accumulator buffer (even /
+//              odd tiles): tcgen05.ld, bias, BatchNorm statistics, bf16 NHWC store
 //
 // Grid = #SMs, persistent static tile schedule.  Layers whose extents do not
 // decompose into whole rows fall back to the cp.async gather kernel.
@@ -29,9 +30,11 @@ namespace vae {
 
 using namespace umma;
 
-constexpr int kTStagesMax = 6;
+constexpr int kTStagesMax = 10;
 constexpr int kTTileM = 128;
-constexpr int kTThreads = 192;  // producer warp, MMA warp, 4 epilogue warps
+constexpr int kTThreads = 320;  // producer warp, MMA warp, 2 x 4 epilogue warps (one set per TMEM accumulator)
+
+long long* umma_trace_ptr();
 
 struct TmaConvParams {
   CUtensorMap tmap;
@@ -52,6 +55,7 @@ struct TmaConvParams {
   const float* bias;
   bf16* out;
   double* stats;
+  long long* trace;  // optional [6][512] clock64 samples of CTA 0 (tuning aid)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
@@ -106,6 +110,12 @@ __global__ void pack_tma_weight_kernel(const float* __restrict__ w, bf16* __rest
   }
 }
 
+#define VAE_TTRACE(role, idx)                                                             \
+  do {                                                                                   \
+    if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && (idx) < 512)                \
+      P.trace[(role) * 512 + (idx)] = clock64();                                          \
+  } while (0)
+
 __global__ void __launch_bounds__(kTThreads, 1)
 umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -153,7 +163,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   if (warp == 0) {
     // ============================== producer ==============================
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, seq = 0;
       uint32_t ph = 0;
       const uint32_t b_bytes = (uint32_t)P.b_stage_bytes;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -167,6 +177,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
         const bf16* wsrc = P.wpk + P.b_off[phase];
         const int nkb = P.nkb[phase];
         for (int kb = 0; kb < nkb; ++kb) {
+          VAE_TTRACE(0, seq);
           mbar_wait(&empty_bar[stage], ph ^ 1u);
           uint8_t* a_st = smem + stage * stage_bytes;
           const int q0 = kb * P.sps;
@@ -180,6 +191,8 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
                         (int)jw0 * g.in_mul + tt.dw[tap_i], (int)jh0 * g.in_mul + tt.dh[tap_i], (int)b0);
           }
           bulk_g2s(a_st + P.a_stage_bytes, wsrc + (long long)kb * P.sps * P.sub_b_elems, b_bytes, &full_bar[stage]);
+          VAE_TTRACE(1, seq);
+          ++seq;
           if (++stage == kStages) { stage = 0; ph ^= 1u; }
         }
       }
@@ -190,7 +203,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const uint32_t layout = P.kc == 32 ? 4u : 2u;        // SWIZZLE_64B : SWIZZLE_128B
     const uint32_t sbo = P.kc == 32 ? 512u : 1024u;      // 8 rows of 64 / 128 bytes
     const int ksteps = P.kc / 16;
-    int stage = 0;
+    int stage = 0, seq = 0;
     uint32_t ph = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -204,6 +217,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], ph);
+        VAE_TTRACE(2, seq);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -220,18 +234,20 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
           if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
+        VAE_TTRACE(3, seq);
+        ++seq;
         if (++stage == kStages) { stage = 0; ph ^= 1u; }
       }
     }
   } else {
     // ============================== epilogue ==============================
-    const int ew = warp & 3;  // TMEM lane group = warp % 4 (warps 2,3,4,5 -> 2,3,0,1)
+    const int ew = warp & 3;           // TMEM lane group = warp % 4
+    const int eset = (warp - 2) >> 2;  // warps 2-5 serve accumulator 0 (even tiles), 6-9 accumulator 1
     const int r = ew * 32 + lane;
     float run1[32], run2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+    for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int phase = tile / P.tiles_per_phase;
       const int mt = tile - phase * P.tiles_per_phase;
       const TapTable& tt = g.phase[phase];
@@ -248,6 +264,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
         dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * g.Nout;
       }
       mbar_wait(&tfull_bar[acc], acc_ph);
+      if (ew == 0) VAE_TTRACE(4, it);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
       for (int c0 = 0; c0 < N; c0 += 32) {
@@ -257,6 +274,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
         if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
+          if (ew == 0) VAE_TTRACE(5, it);
         }
         const int ncol = min(32, N - c0);
 #pragma unroll
@@ -309,8 +327,8 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
       }
     }
     if (P.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      for (int i = threadIdx.x - 64; i < N; i += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      for (int i = threadIdx.x - 64; i < N; i += 256) {
         atomicAdd(&P.stats[i], (double)s_stats[i]);
         atomicAdd(&P.stats[N + i], (double)s_stats[256 + i]);
       }
@@ -478,6 +496,7 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
   cudaStream_t st = as_stream(stream);
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
   P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  P.trace = umma_trace_ptr();
   size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4;
   static bool attr_set = false;
   if (!attr_set) {
