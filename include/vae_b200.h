@@ -163,6 +163,48 @@ int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
                            int training, int dtype, vae_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Fused output block of the decoder (models.py:76-82, run at :171):
+ *   y = ConvT(..) [B,H,W,C] -> BatchNorm2d -> LeakyReLU -> Conv2d(C->1,k3,s1,p1) -> Sigmoid.
+ * y is the largest tensor of the network; these three entry points read it once
+ * each and never store the normalised activation or its gradient.
+ * mean/scale/beta/rstd are the BatchNorm vectors of vae_bn_finalize
+ * (u = (y-mean)*scale+beta); w_last is the fp32 OIHW weight [1,C,3,3] as torch
+ * holds it (no repacking); C in {8,16,32,64}, W % 4 == 0.
+ * ---------------------------------------------------------------------- */
+
+/* 1 when the three entry points below serve this shape. */
+int vae_final_block_supported(int B, int H, int W, int C);
+
+/* logits[B,H,W] (dtype) = conv(lrelu(bn(y)), w_last) + b_last; probs[B,H,W] (fp32,
+ * may be NULL) = sigmoid(logits).
+ * replaces: aten::native_batch_norm (apply) + leaky_relu + convolution + sigmoid at
+ * models.py:78-81 */
+int vae_final_conv_fwd(const void* y, const float* mean, const float* scale, const float* beta,
+                       const float* w_last, const float* b_last, void* logits, float* probs, int B,
+                       int H, int W, int C, float slope, int dtype, vae_stream_t stream);
+
+/* Backward pass 1.  With da = conv_data_grad(dlogits, w_last) and du = da*lrelu'(u):
+ *   dstats[0:C] = sum du, dstats[C:2C] = sum du*xhat, dstats[2C] = sum dlogits
+ *   (double[2C+1], zeroed by this call);  dw_last[C*9] = weight gradient of the final
+ *   conv (fp32 OIHW, zeroed by this call).
+ * replaces: convolution_backward (models.py:80) + leaky_relu_backward + the reductions
+ * of native_batch_norm_backward (models.py:78) inside train.py:650 */
+int vae_final_bwd_reduce(const void* dlogits, const void* y, const float* mean, const float* scale,
+                         const float* beta, const float* rstd, const float* w_last, double* dstats,
+                         float* dw_last, int B, int H, int W, int C, float slope, int dtype,
+                         vae_stream_t stream);
+
+/* Backward pass 2: dy[B,H,W,C] = gamma*rstd*(du - dstats[c]/M - xhat*dstats[C+c]/M)
+ * (training) or du*gamma*rstd (eval); also writes dgamma[C], dbeta[C], dbias[C] = sum dy
+ * (bias of the ConvT feeding the BatchNorm) and db_last[1] (bias of the final conv).
+ * replaces: native_batch_norm_backward (models.py:78) inside train.py:650 */
+int vae_final_bwd_apply(const void* dlogits, const void* y, const float* mean, const float* scale,
+                        const float* beta, const float* rstd, const float* gamma, const float* w_last,
+                        const double* dstats, void* dy, float* dgamma, float* dbeta, float* dbias,
+                        float* db_last, int B, int H, int W, int C, float slope, int training,
+                        int dtype, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Layout glue between the NHWC conv stack and the reference's C-major
  * flatten / view (models.py:133 and :166).
  * ---------------------------------------------------------------------- */

@@ -273,3 +273,72 @@ def test_roll_transform_matches_midi_stack(tv):
     o3 = ops.roll_transform(dev(rolls), 128, 128, 0, 6, 0.5, 0.0, 1.0, 11, 0).cpu()
     assert set(o3.unique().tolist()) <= {0.0, 1.0}
     assert float(o3.sum()) <= float((rolls[:, :, 16:144] > 127).sum()) + 1e-3
+
+
+# ---------------------------------------------------------------------------
+# fused output block (models.py:76-82): BN apply + LeakyReLU + Conv2d(C->1) + Sigmoid
+# forward, and its two-pass backward, against autograd on the same fp64 graph
+# ---------------------------------------------------------------------------
+FINAL_CASES = [
+    # B, H, W, C
+    (3, 16, 32, 32),
+    (2, 32, 16, 8),
+    (2, 8, 64, 16),
+    (1, 24, 36, 64),  # partial tiles in both directions
+    (2, 128, 128, 32),
+]
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", FINAL_CASES)
+def test_final_block_forward_backward(tv, case, dtype, training):
+    B, H, W, C = case
+    ops = tv.ops
+    assert ops.final_block_supported(B, H, W, C)
+    y = rnd(B, C, H, W, seed=11) * 1.5 + 0.3
+    gamma = rnd(C, seed=12, scale=0.3) + 1.0
+    beta = rnd(C, seed=13, scale=0.2)
+    w_last = rnd(1, C, 3, 3, seed=14, scale=1.0 / math.sqrt(9 * C))
+    b_last = rnd(1, seed=15, scale=0.1)
+    dlog = rnd(B, 1, H, W, seed=16, scale=1.0 / (B * H * W))
+    run_mean, run_var = rnd(C, seed=17, scale=0.1) + 0.3, torch.rand(C, generator=torch.Generator().manual_seed(18)) + 1.5
+
+    yq = q(y, dtype).requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    w64, bl64 = w_last.double().requires_grad_(True), b_last.double().requires_grad_(True)
+    u = F.batch_norm(yq, run_mean.double().clone(), run_var.double().clone(), g64, b64, training=training, eps=1e-5)
+    logits_ref = F.conv2d(F.leaky_relu(u, 0.01), w64, bl64, padding=1)
+    dlq = q(dlog, dtype)
+    logits_ref.backward(dlq)
+
+    y_d = dev(nhwc(y).to(dtype))
+    n = B * H * W
+    if training:
+        yy = y_d.double()
+        stats = torch.cat([yy.sum((0, 1, 2)), (yy * yy).sum((0, 1, 2))])
+    else:
+        stats = None
+    rm, rv = dev(run_mean.clone()), dev(run_var.clone())
+    vec = ops.bn_finalize(stats, dev(gamma), dev(beta), rm, rv, n, training)
+    logits, probs = ops.final_conv_fwd(y_d, vec, dev(beta), dev(w_last), dev(b_last))
+    tol = TOL[dtype]
+    assert logits.shape == (B, 1, H, W) and probs.dtype == torch.float32
+    assert rel_err(logits.float(), logits_ref.detach()) <= tol
+    assert rel_err(probs, torch.sigmoid(logits.double())) <= 1e-6
+
+    dy, dgamma, dbeta, dbias, dw, db = ops.final_block_backward(
+        dev(dlog.to(dtype)), y_d, vec, dev(gamma), dev(beta), dev(w_last), training)
+    # gradients: fp32 arithmetic on (for bf16) rounded operands, one output rounding for dy
+    assert rel_err(nchw(dy.float()), yq.grad) <= tol
+    gtol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert rel_err(dgamma, g64.grad) <= gtol
+    assert rel_err(dbeta, b64.grad) <= gtol
+    assert rel_err(dw, w64.grad) <= gtol
+    assert rel_err(db, bl64.grad) <= gtol
+    # bias of the conv feeding a train-mode BatchNorm: exactly zero in exact arithmetic
+    scale_ref = float(yq.grad.abs().sum())
+    if training:
+        assert float(dbias.abs().max()) <= 1e-3 * scale_ref
+    else:
+        assert rel_err(dbias, yq.grad.sum((0, 2, 3))) <= max(gtol, 1e-4)

@@ -496,6 +496,11 @@ int umma_conv_dgrad(const void*, const void*, const float*, void*, double*, int,
                     int, cudaStream_t, bool*);
 int umma_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t,
                     bool*);
+// conv_edge.cu: strip-mined edge-layer kernels; return 1 when the shape is not served
+int edge_cin1(const GatherGeom& g, bool is_dgrad, const void* in, const void* wq, const float* bias, void* out,
+              double* stats, int dt_in, int dt_out, cudaStream_t st);
+int edge_c1_wgrad(const void* mc, const void* s1, float* dw, int B, int Hm, int Wm, int N, int Hs, int Ws, int mul,
+                  int flip, int dt_m, int dt_s, cudaStream_t st);
 }  // namespace vae
 
 extern "C" int vae_conv_fprop(const void* x, const void* wp, const float* bias, void* y,
@@ -509,6 +514,8 @@ extern "C" int vae_conv_fprop(const void* x, const void* wp, const float* bias, 
   GatherGeom g = geom_fprop(B, Hi, Wi, Ci, Co, stride);
   const bool bf = dt_out == VAE_BF16;
   if (Ci == 1 && edge_ok(Co)) {
+    const int rc = edge_cin1(g, false, x, wp, bias, y, stats, dt_in, dt_out, st);
+    if (rc != 1) return rc;
     if (dt_in == VAE_F32 && !bf) return launch_cin1<float, float, float>(g, x, wp, bias, y, stats, st);
     if (dt_in == VAE_F32 && bf) return launch_cin1<float, bf16, bf16>(g, x, wp, bias, y, stats, st);
     if (dt_in == VAE_BF16 && bf) return launch_cin1<bf16, bf16, bf16>(g, x, wp, bias, y, stats, st);
@@ -567,6 +574,8 @@ extern "C" int vae_conv_wgrad(const void* x, const void* dy, float* dw, int B, i
   VAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
   const int Ho = Hi / stride, Wo = Wi / stride;
   if (Ci == 1 && edge_ok(Co) && Co <= 64) {  // enc.conv0: Mc = dY, S1 = x
+    const int rc = edge_c1_wgrad(dy, x, dw, B, Ho, Wo, Co, Hi, Wi, stride, 0, dt_dy, dt_x, st);
+    if (rc != 1) return rc;
     if (dt_x == VAE_F32 && dt_dy == VAE_F32)
       return launch_c1_wgrad<float, float>(dy, x, dw, B, Ho, Wo, Co, Hi, Wi, stride, 0, st);
     if (dt_x == VAE_F32 && dt_dy == VAE_BF16)

@@ -37,6 +37,19 @@ class ConvBlockSpec:
         self.bn = bn  # nn.BatchNorm2d holding running stats (buffers are not autograd inputs)
 
 
+def _bn_vectors(y, stats, gamma, beta, bn, training: bool):
+    """BatchNorm statistics -> (scale, shift, mean, rstd) + running-stat update; no apply pass."""
+    count = y.numel() // y.shape[-1]
+    use_batch = training or bn.running_mean is None
+    vec = ops.bn_finalize(
+        stats if use_batch else None, gamma, beta, bn.running_mean, bn.running_var, count, use_batch,
+        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps,
+    )
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return vec
+
+
 def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     count = y.numel() // y.shape[-1]
     use_batch = training or bn.running_mean is None
@@ -164,20 +177,31 @@ class DecodeFn(torch.autograd.Function):
         d = ops.linear_fwd(z, w_in, b_in, dtype)  # [B, C*h*w], C-major
         h = ops.nchw_to_nhwc(d, C, h0, w0)
         saved = []
+        fused_last = False
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
             cw = ops.ConvWeights(w, dtype, 2)
             stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
             y = ops.conv_data_grad(h, cw, b, stats)  # ConvTranspose2d forward
+            if i == len(specs) - 1 and ops.final_block_supported(B, y.shape[1], y.shape[2], sp.ci):
+                # output block: BatchNorm apply + LeakyReLU ride in the final conv's operand load
+                vec = _bn_vectors(y, stats, gamma, beta, sp.bn, training)
+                saved.append((h, y, vec, cw))
+                fused_last = True
+                break
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
             saved.append((h, y, vec, cw))
             h = act
-        cw3 = ops.ConvWeights(w_last, dtype, 1)
-        logits = ops.conv_forward(h, cw3, b_last)  # [B,H,W,1]
-        H, W = logits.shape[1], logits.shape[2]
-        probs = ops.sigmoid(logits).view(B, 1, H, W)
-        logits = logits.view(B, 1, H, W)
-        ctx.specs, ctx.training, ctx.saved, ctx.last = specs, training, saved, (h, cw3)
+        if fused_last:
+            logits, probs = ops.final_conv_fwd(y, vec, beta, w_last, b_last)
+            cw3 = None
+        else:
+            cw3 = ops.ConvWeights(w_last, dtype, 1)
+            logits = ops.conv_forward(h, cw3, b_last)  # [B,H,W,1]
+            H, W = logits.shape[1], logits.shape[2]
+            probs = ops.sigmoid(logits).view(B, 1, H, W)
+            logits = logits.view(B, 1, H, W)
+        ctx.specs, ctx.training, ctx.saved, ctx.last = specs, training, saved, (None if fused_last else h, cw3)
         ctx.save_for_backward(z, w_in, probs, b_in, w_last, b_last, *conv_params)
         ctx.z_needs_grad = z.requires_grad
         return probs, logits
@@ -189,7 +213,8 @@ class DecodeFn(torch.autograd.Function):
         specs, saved, sink = ctx.specs, ctx.saved, ctx.sink
         act_last, cw3 = ctx.last
         B, _, H, W = probs.shape
-        dtype = act_last.dtype
+        fused_last = cw3 is None
+        dtype = saved[-1][1].dtype
         if dlogits is not None:
             dlog = dlogits.contiguous()
             if dprobs is not None:
@@ -199,22 +224,34 @@ class DecodeFn(torch.autograd.Function):
         else:
             dlog = torch.zeros((B, 1, H, W), dtype=dtype, device=probs.device)
         dlog = dlog.view(B, H, W, 1)
-        c_last = act_last.shape[-1]
-        # final Conv2d(C -> 1): bias grad is a plain sum, done as two column sums
-        n = dlog.numel()
-        cols = 256 if n % 256 == 0 else 1
-        g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1))
-        g_w_last = ops.conv_weight_grad(act_last, dlog, 1, c_last, 1, H, W)
+        conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
+        n_blk = len(specs)
+        if fused_last:
+            # Conv2d(C->1) backward + LeakyReLU + BatchNorm backward in two passes over y
+            _, y, vec, _ = saved[-1]
+            gamma, beta = conv_params[4 * (n_blk - 1) + 2], conv_params[4 * (n_blk - 1) + 3]
+            fused = ops.final_block_backward(dlog, y, vec, gamma, beta, w_last, ctx.training)
+            g_w_last, g_b_last = fused[4], fused[5]
+            d_act = None
+        else:
+            c_last = act_last.shape[-1]
+            # final Conv2d(C -> 1): bias grad is a plain sum, done as two column sums
+            n = dlog.numel()
+            cols = 256 if n % 256 == 0 else 1
+            g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1))
+            g_w_last = ops.conv_weight_grad(act_last, dlog, 1, c_last, 1, H, W)
+            d_act = ops.conv_data_grad(dlog, cw3)
         if sink is not None:
             sink.push(w_last, g_w_last)
             sink.push(b_last, g_b_last)
-        d_act = ops.conv_data_grad(dlog, cw3)
-        conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
-        for i in range(len(specs) - 1, -1, -1):
+        for i in range(n_blk - 1, -1, -1):
             sp = specs[i]
             h_in, y, vec, cw = saved[i]
             gamma, beta = conv_params[4 * i + 2], conv_params[4 * i + 3]
-            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
+            if fused_last and i == n_blk - 1:
+                dy, dgamma, dbeta, dbias = fused[:4]
+            else:
+                dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
             Hi, Wi = y.shape[1], y.shape[2]
             # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
             conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)

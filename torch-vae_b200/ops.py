@@ -63,7 +63,8 @@ class _Proxy:
 
     _QUERIES = frozenset({"vae_abi_version", "vae_last_error", "vae_has_umma", "vae_set_umma", "vae_set_umma_wgrad",
                           "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
-                          "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems"})
+                          "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
+                          "vae_final_block_supported"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -215,6 +216,50 @@ def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = 
     )
     _lib.check(rc, "vae_bn_lrelu_bwd_apply")
     return dy, small[0], small[1], small[2]
+
+
+# ------------------------------------------------- fused output block (models.py:76-82)
+def final_block_supported(B: int, H: int, W: int, C: int) -> bool:
+    return bool(_L().vae_final_block_supported(B, H, W, C))
+
+
+def final_conv_fwd(y, vec, beta, w_last, b_last, slope: float = LRELU_SLOPE):
+    """y [B,H,W,C] raw ConvT output -> (logits [B,1,H,W] in y.dtype, probs [B,1,H,W] fp32):
+    BatchNorm apply + LeakyReLU + Conv2d(C->1) + Sigmoid in one pass over y."""
+    B, H, W, C = y.shape
+    logits = torch.empty((B, 1, H, W), dtype=y.dtype, device=y.device)
+    probs = torch.empty((B, 1, H, W), dtype=torch.float32, device=y.device)
+    rc = _L().vae_final_conv_fwd(
+        _p(y), vec[2].data_ptr(), vec[0].data_ptr(), _f32(beta, "bn bias"), _f32(w_last, "final conv weight"),
+        _f32(b_last, "final conv bias"), _p(logits), _p(probs), B, H, W, C, slope, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_final_conv_fwd")
+    return logits, probs
+
+
+def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, slope: float = LRELU_SLOPE):
+    """-> (dy, dgamma, dbeta, dbias, dw_last, db_last): backward of Conv2d(C->1) + LeakyReLU +
+    BatchNorm in two passes over y (reduce, apply)."""
+    B, H, W, C = y.shape
+    lib = _L()
+    dstats = torch.empty(2 * C + 1, dtype=torch.float64, device=y.device)
+    dw_last = torch.empty((1, C, 3, 3), dtype=torch.float32, device=y.device)
+    mean, scale, rstd = vec[2].data_ptr(), vec[0].data_ptr(), vec[3].data_ptr()
+    rc = lib.vae_final_bwd_reduce(
+        _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(w_last, "final conv weight"), _p(dstats),
+        _p(dw_last), B, H, W, C, slope, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_final_bwd_reduce")
+    dy = torch.empty_like(y)
+    small = torch.empty((3, C), dtype=torch.float32, device=y.device)
+    db_last = torch.empty(1, dtype=torch.float32, device=y.device)
+    rc = lib.vae_final_bwd_apply(
+        _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
+        _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
+        small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_final_bwd_apply")
+    return dy, small[0], small[1], small[2], dw_last, db_last
 
 
 # ---------------------------------------------------------------- layout glue
