@@ -29,7 +29,11 @@ for name, H, W, Ci, Co in LAYERS:
     xb, yb = x.numel() * 2, y.numel() * 2
     vec = torch.stack([torch.ones(Ci), torch.zeros(Ci), torch.zeros(Ci), torch.ones(Ci)]).cuda(); beta = torch.zeros(Ci, device="cuda")
     t0, t1 = ops.umma_tma_pack_weight(w, 2, 0), ops.umma_tma_pack_weight(w, 2, 1)
+    r0 = ops.umma_rw_pack_weight(w, 0) if ops.umma_rw_eligible(B, H, W, Ci, Co, 2, 0) else None
+    r1 = ops.umma_rw_pack_weight(w, 1) if ops.umma_rw_eligible(B, H, W, Ci, Co, 2, 1) else None
     cases = {
+        "rw_fprop": (lambda: ops.conv_umma_rw(x, r0, bias_o, st_o, Ci, Co, 2, 0), xb + yb) if r0 is not None else None,
+        "rw_dgrad": (lambda: ops.conv_umma_rw(y, r1, bias_i, st_i, Ci, Co, 2, 1), xb + yb) if r1 is not None else None,
         "tma_fprop": (lambda: ops.conv_umma_tma(x, t0, bias_o, st_o, Ci, Co, 2, 0), xb + yb),
         "tma_dgrad": (lambda: ops.conv_umma_tma(y, t1, bias_i, st_i, Ci, Co, 2, 1), xb + yb),
         "fprop": (lambda: ops.conv_umma(x, w0, bias_o, st_o, Ci, Co, 2, 0), xb + yb),
@@ -37,7 +41,10 @@ for name, H, W, Ci, Co in LAYERS:
         "dgrad": (lambda: ops.conv_umma(y, w1, bias_i, st_i, Ci, Co, 2, 1), xb + yb),
         "wgrad": (lambda: ops.conv_weight_grad(x, y, 2, Ci, Co, H, W), xb + yb),
     }
-    for cname, (fn, nbytes) in cases.items():
+    for cname, case in cases.items():
+        if case is None:
+            continue
+        fn, nbytes = case
         full = f"{name}.{cname}"
         if flt and flt not in full:
             continue

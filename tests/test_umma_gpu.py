@@ -188,3 +188,50 @@ def test_umma_tma_fprop_and_dgrad(ops, case):
         torch.cuda.synchronize()
         assert rel_err(nchw(dx.float().cpu()), ref) < TOL
         assert rel_err(stats.cpu()[:Ci], ref.sum(dim=(0, 2, 3))) < 2e-3
+
+
+# ---------------------------------------------------------------------------
+# resident-weight TMA kernel for the narrow layers (conv_umma_rw.cu)
+# ---------------------------------------------------------------------------
+RW_CASES = [
+    # B, H, W (high-res side), Ci, Co, stride, mode
+    (2, 32, 32, 32, 32, 2, 0),
+    (3, 16, 64, 32, 64, 2, 0),
+    (2, 256, 256, 32, 32, 2, 0),   # Wj = 128: one output row per tile
+    (5, 16, 16, 32, 64, 2, 0),     # several images per tile, B not a multiple of them
+    (1, 16, 8, 32, 32, 1, 0),
+    (2, 32, 32, 32, 32, 2, 1),
+    (3, 16, 64, 32, 64, 2, 1),     # ConvT 64 -> 32 (128-byte swizzle)
+    (5, 16, 16, 32, 32, 2, 1),
+    (40, 128, 128, 32, 32, 2, 1),  # persistent loop, TMEM double buffering
+    (40, 128, 128, 32, 64, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", RW_CASES)
+def test_umma_rw_conv(ops, case):
+    B, H, W, Ci, Co, s, mode = case
+    assert ops.umma_rw_eligible(B, H, W, Ci, Co, s, mode)
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * (Ci if mode == 0 else Co)))
+    wq = w.bfloat16().double()
+    if mode == 0:
+        x = rnd(B, Ci, H, W, seed=1)
+        b = rnd(Co, seed=3, scale=0.1)
+        ref = F.conv2d(x.bfloat16().double(), wq, b.double(), stride=s, padding=1)
+        inp, n_out = nhwc(x), Co
+    else:
+        dy = rnd(B, Co, H // s, W // s, seed=4)
+        b = rnd(Ci, seed=5, scale=0.1)
+        ref = F.conv_transpose2d(dy.bfloat16().double(), wq, b.double(), stride=s, padding=1, output_padding=s - 1)
+        inp, n_out = nhwc(dy), Ci
+    wpk = ops.umma_rw_pack_weight(w.cuda(), mode)
+    stats = torch.empty(2 * n_out, dtype=torch.float64, device="cuda")
+    out = ops.conv_umma_rw(inp.cuda().bfloat16(), wpk, b.cuda(), stats, Ci, Co, s, mode)
+    torch.cuda.synchronize()
+    assert out.shape == (B, ref.shape[2], ref.shape[3], n_out)
+    assert rel_err(nchw(out.float().cpu()), ref) < TOL
+    assert rel_err(stats.cpu()[:n_out], ref.sum(dim=(0, 2, 3))) < 2e-3
+    assert rel_err(stats.cpu()[n_out:], (ref**2).sum(dim=(0, 2, 3))) < 2e-3
+    out2 = ops.conv_umma_rw(inp.cuda().bfloat16(), wpk, None, None, Ci, Co, s, mode)  # no bias / stats
+    ref2 = ref - b.double().view(1, -1, 1, 1)
+    assert rel_err(nchw(out2.float().cpu()), ref2) < TOL

@@ -34,6 +34,11 @@ PROTOTYPES = {
     "vae_umma_tma_packed_elems": [_i, _i, _i, _i],
     "vae_umma_tma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
     "vae_conv_umma_tma": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_set_umma_rw": [_i],
+    "vae_umma_rw_eligible": [_i, _i, _i, _i, _i, _i, _i],
+    "vae_umma_rw_packed_elems": [_i, _i],
+    "vae_umma_rw_pack_weight": [_vp, _vp, _i, _i, _i, _vp],
+    "vae_conv_umma_rw": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_umma_wgrad": [_i],
     "vae_umma_wgrad_supported": [_i, _i],
     "vae_conv_wgrad_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
@@ -59,7 +64,8 @@ PROTOTYPES = {
     "vae_sigmoid_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "vae_roll_transform": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _ull, _ull, _vp],
 }
-_RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong, "vae_umma_tma_packed_elems": C.c_longlong}
+_RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong, "vae_umma_tma_packed_elems": C.c_longlong,
+             "vae_umma_rw_packed_elems": C.c_longlong}
 
 _lib = None
 

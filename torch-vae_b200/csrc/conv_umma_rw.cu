@@ -1,0 +1,417 @@
+// Resident-weight TMA / tcgen05 convolution for the NARROW, HBM-bound layers (32 / 64 channels
+// at 64x64 .. 128x128: 80 % of the activation bytes of the network).
+//
+// Same GEMM and the same strided-box TMA gather as conv_umma_tma.cu, re-cut for layers whose
+// K loop is so short (K = 32 .. 288) that per-stage issue latency, not bandwidth, was the limit:
+//
+//  * all nine 3x3 weight images (<= 36 KB) are loaded ONCE per CTA and stay in shared memory;
+//    pipeline stages carry activations only, 24-32 KB each (3-4 filter taps per stage);
+//  * producer and MMA issuer are straight-line template code: no divisions, no table look-ups,
+//    descriptors are constant + immediate;
+//  * MODE 1 (ConvTranspose2d k3 s2 p1 op1 == data gradient of the stride-2 conv) computes all
+//    FOUR output-parity phases of a tile from the same four gathered taps (offsets {0,1}^2 of the
+//    low-resolution input): 4 TMA boxes instead of 9, four TMEM accumulators, and every thread
+//    stores 2 x 128 contiguous bytes (the 2x2 output pixels of its input pixel) instead of four
+//    64-byte pieces at 128-byte stride written by four different tiles.
+//
+//   warp 0     producer (one thread): resident weights, then per stage wait(empty) -> expect_tx -> TMA boxes
+//   warp 1     MMA issuer (one thread), TMEM accumulators double-buffered across tiles
+//   warps 2-9  epilogue: two sets of four warps (even / odd tiles): tcgen05.ld, bias, BatchNorm
+//              statistics, bf16 NHWC stores
+#include "tma_util.cuh"
+
+namespace vae {
+
+constexpr int kRwThreads = 320;
+constexpr int kRwMaxStages = 8;
+
+struct RwParams {
+  CUtensorMap tmap;
+  int B, Hj, Wj;          // iteration grid (output pixels for MODE 0, input pixels for MODE 1)
+  int in_mul;             // MODE 0: conv stride; MODE 1: 1
+  int Hout, Wout;         // produced tensor
+  int total_tiles, stages;
+  const bf16* wpk;        // 9 swizzled [N][KC] images, tap-major
+  const float* bias;
+  bf16* out;
+  double* stats;
+};
+
+template <int MODE, int KC, int N>
+struct RwCfg {
+  static constexpr int SUB = 128 * KC * 2;                        // one tap's 128-pixel sub-tile
+  static constexpr int T = MODE == 0 ? 9 : 4;                     // sub-tiles per tile
+  static constexpr int S = MODE == 0 ? 3 : (KC == 32 ? 4 : 2);    // sub-tiles per stage
+  static constexpr int SPT = T / S;                               // stages per tile
+  static constexpr int STAGE = S * SUB;
+  static constexpr int IMG = N * KC * 2;
+  static constexpr int WBYTES = 9 * IMG;
+  static constexpr int ACC_COLS = MODE == 0 ? N : 4 * N;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
+  static constexpr uint32_t LAYOUT = KC == 32 ? 4u : 2u;          // SWIZZLE_64B : SWIZZLE_128B
+  static constexpr uint32_t SBO = KC == 32 ? 512u : 1024u;
+  static constexpr int KS = KC / 16;
+  static constexpr int TAIL = 8 * 24 + 16 + 4 * (2 * 64 + 64);
+  static size_t smem_bytes(int stages) { return 1024 + (size_t)stages * STAGE + WBYTES + TAIL; }
+};
+
+// weight images: tap t = kh*3+kw; image[n][c] (K-major rows of KC elements, swizzled like the A tiles)
+//   MODE 0: B[n][c] = w[co = n][ci = c][t]       MODE 1: B[n][c] = w[co = c][ci = n][t]
+__global__ void pack_rw_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Ci, int mode,
+                                      int N, int KC) {
+  const int total = 9 * N * KC;
+  const int cpr = KC / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % KC, n = (i / KC) % N, t = i / (KC * N);
+    const int co = mode == 0 ? n : e, ci = mode == 0 ? e : n;
+    const float v = w[((long long)co * Ci + ci) * 9 + t];
+    const int chunk = e >> 3;
+    const int sw = cpr == 4 ? (chunk ^ ((n >> 1) & 3)) : (chunk ^ (n & 7));
+    out[(long long)t * N * KC + n * KC + sw * 8 + (e & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int MODE, int KC, int N>
+__global__ void __launch_bounds__(kRwThreads, 1)
+umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
+  using Cfg = RwCfg<MODE, KC, N>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kStages = P.stages;
+  uint8_t* wsm = smem + kStages * Cfg::STAGE;
+  uint8_t* tail = wsm + Cfg::WBYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + kRwMaxStages;
+  uint64_t* tfull_bar = empty_bar + kRwMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 24);  // barrier block padded to 192 B
+  float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][64]
+  float* s_bias = s_stats + 128;                            // [64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 128; i += kRwThreads) s_stats[i] = 0.0f;
+  for (int i = threadIdx.x; i < 64; i += kRwThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kRwMaxStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], 128);
+      }
+      mbar_init(w_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, (uint32_t)Cfg::TMEM_COLS);
+  }
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t Wj = (uint32_t)P.Wj, Hj = (uint32_t)P.Hj;
+  const long long M_total = (long long)P.B * P.Hj * P.Wj;
+
+  if (warp == 0) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, (uint32_t)Cfg::WBYTES);
+      bulk_g2s(wsm, P.wpk, (uint32_t)Cfg::WBYTES, w_bar);
+      int stage = 0;
+      uint32_t ph = 0;
+      const int im = P.in_mul;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const uint32_t m0 = (uint32_t)tile * 128u;
+        const uint32_t jw0 = m0 % Wj, t2 = m0 / Wj;
+        const int jh0 = (int)(t2 % Hj), b0 = (int)(t2 / Hj);
+        const int cw = (int)jw0 * im, ch = jh0 * im;
+#pragma unroll
+        for (int st = 0; st < Cfg::SPT; ++st) {
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          uint8_t* a_st = smem + stage * Cfg::STAGE;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)Cfg::STAGE);
+#pragma unroll
+          for (int i = 0; i < Cfg::S; ++i) {
+            const int o = st * Cfg::S + i;
+            // MODE 0: tap (kh, kw) = (o / 3, o % 3) reads input pixel s*j + (kh-1, kw-1)
+            // MODE 1: offset (dh, dw) = (o >> 1, o & 1) reads input pixel j + (dh, dw)
+            const int dw = MODE == 0 ? (o % 3) - 1 : (o & 1);
+            const int dh = MODE == 0 ? (o / 3) - 1 : (o >> 1);
+            tma_load_4d(a_st + i * Cfg::SUB, &P.tmap, &full_bar[stage], 0, cw + dw, ch + dh, b0);
+          }
+          if (++stage == kStages) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================= MMA issuer =============================
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)N, 0, 0);
+    const uint32_t a_base = smem_u32(smem), w_base = smem_u32(wsm);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+#pragma unroll
+      for (int st = 0; st < Cfg::SPT; ++st) {
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = a_base + (uint32_t)(stage * Cfg::STAGE);
+#pragma unroll
+          for (int i = 0; i < Cfg::S; ++i) {
+            const int o = st * Cfg::S + i;
+            if constexpr (MODE == 0) {
+#pragma unroll
+              for (int k = 0; k < Cfg::KS; ++k) {
+                const uint64_t ad = make_desc_sw(a_addr + i * Cfg::SUB + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                const uint64_t bd = make_desc_sw(w_base + o * Cfg::IMG + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                mma_bf16_ss(d_tmem, ad, bd, idesc, (o > 0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+              const int dh = o >> 1, dw = o & 1;
+#pragma unroll
+              for (int php = dh; php < 2; ++php)
+#pragma unroll
+                for (int pwp = dw; pwp < 2; ++pwp) {
+                  const int kh = php + 1 - 2 * dh, kw = pwp + 1 - 2 * dw;
+#pragma unroll
+                  for (int k = 0; k < Cfg::KS; ++k) {
+                    const uint64_t ad = make_desc_sw(a_addr + i * Cfg::SUB + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                    const uint64_t bd = make_desc_sw(w_base + (kh * 3 + kw) * Cfg::IMG + k * 32, Cfg::SBO, Cfg::LAYOUT);
+                    mma_bf16_ss(d_tmem + (uint32_t)((php * 2 + pwp) * N), ad, bd, idesc, (o > 0 || k > 0) ? 1u : 0u);
+                  }
+                }
+            }
+          }
+          mma_commit(&empty_bar[stage]);
+          if (st == Cfg::SPT - 1) mma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int ew = warp & 3;           // TMEM lane group = warp % 4
+    const int eset = (warp - 2) >> 2;  // warps 2-5: even tiles, 6-9: odd tiles
+    const int r = ew * 32 + lane;
+    float run1[32], run2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
+    for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const long long m = (long long)tile * 128 + r;
+      const bool valid = m < M_total;
+      bf16* dst = nullptr;
+      if (valid) {
+        const uint32_t mu = (uint32_t)m;
+        const uint32_t jw = mu % Wj, t2 = mu / Wj;
+        const uint32_t jh = t2 % Hj, b = t2 / Hj;
+        if constexpr (MODE == 0)
+          dst = P.out + (((long long)b * P.Hout + jh) * P.Wout + jw) * N;
+        else
+          dst = P.out + (((long long)b * P.Hout + 2 * jh) * P.Wout + 2 * jw) * N;
+      }
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+      constexpr int NCHUNK = Cfg::ACC_COLS / 32;
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK; ++ci) {
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+        tmem_ld_wait();
+        if (ci == NCHUNK - 1) {  // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        // channel base of this chunk / destination offset in elements
+        const int cbase = MODE == 0 ? ci * 32 : 0;
+        const long long doff = MODE == 0 ? ci * 32 : ((long long)(ci >> 1) * P.Wout * N + (ci & 1) * N);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
+          v[i] = valid ? v[i] + b4.x : 0.0f;
+          v[i + 1] = valid ? v[i + 1] + b4.y : 0.0f;
+          v[i + 2] = valid ? v[i + 2] + b4.z : 0.0f;
+          v[i + 3] = valid ? v[i + 3] + b4.w : 0.0f;
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+            *reinterpret_cast<uint4*>(dst + doff + i) = pk;
+          }
+        }
+        if (P.stats != nullptr) {
+          if (N <= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              run1[i] += v[i];
+              run2[i] = fmaf(v[i], v[i], run2[i]);
+            }
+          } else {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            warp_transpose_reduce32(v, lane);
+            warp_transpose_reduce32(sq, lane);
+            atomicAdd(&s_stats[cbase + lane], v[0]);
+            atomicAdd(&s_stats[64 + cbase + lane], sq[0]);
+          }
+        }
+      }
+    }
+    if (P.stats != nullptr) {
+      if (N <= 32) {
+        warp_transpose_reduce32(run1, lane);
+        warp_transpose_reduce32(run2, lane);
+        if (lane < N) {
+          atomicAdd(&s_stats[lane], run1[0]);
+          atomicAdd(&s_stats[64 + lane], run2[0]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      for (int i = threadIdx.x - 64; i < N; i += 256) {
+        atomicAdd(&P.stats[i], (double)s_stats[i]);
+        atomicAdd(&P.stats[N + i], (double)s_stats[64 + i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
+  }
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+static bool g_rw_enabled = true;
+
+struct RwPlan {
+  int mode, kc, n;
+  int rows_w, rows_h, rows_n;
+  int Hj, Wj, in_mul, Hout, Wout, Hin, Win;
+};
+
+// mode 0: X[B,Hi,Wi,Ci] -> Y[B,Hi/s,Wi/s,Co]; mode 1: dY[B,Hi/2,Wi/2,Co] -> dX[B,Hi,Wi,Ci]
+static bool rw_plan(RwPlan& p, int B, int Hi, int Wi, int Ci, int Co, int stride, int mode) {
+  if (!g_rw_enabled || B <= 0 || Hi <= 0 || Wi <= 0 || Hi % stride || Wi % stride) return false;
+  GatherGeom g{};
+  if (mode == 0) {
+    if (Ci != 32 || !(Co == 32 || Co == 64) || !(stride == 1 || stride == 2)) return false;
+    p.kc = 32; p.n = Co;
+    p.Hj = Hi / stride; p.Wj = Wi / stride; p.in_mul = stride;
+    p.Hout = p.Hj; p.Wout = p.Wj; p.Hin = Hi; p.Win = Wi;
+  } else {
+    if (stride != 2 || Ci != 32 || !(Co == 32 || Co == 64)) return false;
+    p.kc = Co; p.n = Ci;
+    p.Hj = Hi / 2; p.Wj = Wi / 2; p.in_mul = 1;
+    p.Hout = Hi; p.Wout = Wi; p.Hin = p.Hj; p.Win = p.Wj;
+  }
+  p.mode = mode;
+  g.Hj = p.Hj; g.Wj = p.Wj;
+  if (!tile_rows(g, &p.rows_w, &p.rows_h, &p.rows_n)) return false;
+  if (p.rows_w * p.in_mul > 256 || p.rows_h * p.in_mul > 256 || p.rows_n > 256) return false;
+  if ((long long)B * p.Hj * p.Wj >= (1LL << 31)) return false;
+  return get_encode_fn() != nullptr;
+}
+
+template <int MODE, int KC, int N>
+static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const float* bias, void* out, double* stats,
+                     int B, cudaStream_t st) {
+  using Cfg = RwCfg<MODE, KC, N>;
+  RwParams P{};
+  cuuint64_t gdim[4] = {(cuuint64_t)KC, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)KC * 2, (cuuint64_t)pl.Win * KC * 2, (cuuint64_t)pl.Hin * pl.Win * KC * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(pl.rows_w * pl.in_mul), (cuuint32_t)(pl.rows_h * pl.in_mul),
+                       (cuuint32_t)pl.rows_n};
+  cuuint32_t estr[4] = {1, (cuuint32_t)pl.in_mul, (cuuint32_t)pl.in_mul, 1};
+  CUresult cr = get_encode_fn()(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), gdim, gstr, box,
+                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VAE_REQUIRE(cr == CUDA_SUCCESS, "conv_umma_rw: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  P.B = B; P.Hj = pl.Hj; P.Wj = pl.Wj; P.in_mul = pl.in_mul; P.Hout = pl.Hout; P.Wout = pl.Wout;
+  const long long M = (long long)B * pl.Hj * pl.Wj;
+  P.total_tiles = (int)((M + 127) / 128);
+  int stages = (int)((220 * 1024 - 1024 - Cfg::WBYTES - Cfg::TAIL) / Cfg::STAGE);
+  if (stages > kRwMaxStages) stages = kRwMaxStages;
+  VAE_REQUIRE(stages >= 2, "conv_umma_rw: shared memory budget");
+  P.stages = stages;
+  P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  auto kern = umma_rw_conv_kernel<MODE, KC, N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > P.total_tiles) grid = P.total_tiles;
+  kern<<<grid, kRwThreads, Cfg::smem_bytes(stages), st>>>(P);
+  return check_launch("umma_rw_conv");
+}
+
+}  // namespace vae
+
+using namespace vae;
+
+extern "C" int vae_set_umma_rw(int enable) {
+  int old = g_rw_enabled ? 1 : 0;
+  g_rw_enabled = enable != 0;
+  return old;
+}
+
+/* 1 when vae_conv_umma_rw serves this layer (narrow layers: 32-channel conv inputs for
+ * mode 0; 32-channel ConvTranspose outputs fed by 32 / 64 channels for mode 1). */
+extern "C" int vae_umma_rw_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode) {
+  RwPlan p{};
+  return rw_plan(p, B, Hi, Wi, Ci, Co, stride, mode) ? 1 : 0;
+}
+
+extern "C" long long vae_umma_rw_packed_elems(int Ci, int Co) { return 9LL * Ci * Co; }
+
+extern "C" int vae_umma_rw_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(w_oihw && out && (mode == 0 || mode == 1), "umma_rw_pack_weight: bad argument");
+  const int N = mode == 0 ? Co : Ci, KC = mode == 0 ? Ci : Co;
+  VAE_REQUIRE((KC == 32 || KC == 64) && N % 16 == 0 && N <= 64, "umma_rw_pack_weight: shape not served");
+  pack_rw_weight_kernel<<<(9 * N * KC + 255) / 256, 256, 0, as_stream(stream)>>>(w_oihw, (bf16*)out, Co, Ci, mode, N, KC);
+  return check_launch("pack_rw_weight");
+}
+
+/* Conv forward (mode 0) / fused-phase ConvTranspose forward == data gradient (mode 1) with the
+ * weights resident in shared memory; same contract as vae_conv_umma_tma, wpk from
+ * vae_umma_rw_pack_weight.
+ * replaces: aten::convolution (models.py:45, 66-68, 77) and the data-gradient half of
+ * aten::convolution_backward (train.py:650) on the narrow layers */
+extern "C" int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
+                                int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(in && wpk && out && (mode == 0 || mode == 1), "conv_umma_rw: bad argument");
+  RwPlan pl{};
+  VAE_REQUIRE(rw_plan(pl, B, Hi, Wi, Ci, Co, stride, mode), "conv_umma_rw: shape not served by this kernel");
+  cudaStream_t st = as_stream(stream);
+  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * pl.n, st));
+  if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st);
+  if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st);
+  if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st);
+  if (mode == 1 && pl.kc == 64) return rw_launch<1, 64, 32>(pl, in, wpk, bias, out, stats, B, st);
+  set_error("conv_umma_rw: no instantiation");
+  return VAE_ERR_UNSUPPORTED;
+}

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "conv_geom.cuh"
 #include "umma.cuh"
+#include "tma_util.cuh"
 
 namespace vae {
 
@@ -57,25 +58,6 @@ struct TmaConvParams {
   double* stats;
   long long* trace;  // optional [6][512] clock64 samples of CTA 0 (tuning aid)
 };
-
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-// shared-memory matrix descriptor with a selectable swizzle (2 = 128B, 4 = 64B)
-__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 // weight images for this kernel: per phase, per stage: [sub][N rows][kc] bf16, rows
 // swizzled like the A sub-tiles (64B: chunk ^= (n>>1)&3, 128B: chunk ^= n&7).
@@ -345,44 +327,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
 // ============================================================================
 // host side
 // ============================================================================
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 static bool g_tma_enabled = true;
-
-// tile decomposition 128 = rows_n * rows_h * rows_w made of whole output rows
-static bool tile_rows(const GatherGeom& g, int* rw, int* rh, int* rn) {
-  if (g.Wj >= 128) {
-    if (g.Wj % 128) return false;
-    *rw = 128; *rh = 1; *rn = 1;
-    return true;
-  }
-  if (128 % g.Wj) return false;
-  int rows = 128 / g.Wj;
-  if (rows <= g.Hj) {
-    if (g.Hj % rows) return false;
-    *rw = g.Wj; *rh = rows; *rn = 1;
-    return true;
-  }
-  if (rows % g.Hj) return false;
-  *rw = g.Wj; *rh = g.Hj; *rn = rows / g.Hj;
-  return true;
-}
 
 static bool tma_plan(TmaConvParams& P, const GatherGeom& g) {
   if (!g_tma_enabled) return false;

@@ -64,7 +64,8 @@ class _Proxy:
     _QUERIES = frozenset({"vae_abi_version", "vae_last_error", "vae_has_umma", "vae_set_umma", "vae_set_umma_wgrad",
                           "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
-                          "vae_final_block_supported"})
+                          "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
+                          "vae_umma_rw_packed_elems"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -500,6 +501,40 @@ def conv_umma_tma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: in
     return out
 
 
+def umma_rw_eligible(B: int, Hi: int, Wi: int, Ci: int, Co: int, stride: int, mode: int) -> bool:
+    return bool(_L().vae_umma_rw_eligible(B, Hi, Wi, Ci, Co, stride, mode))
+
+
+def set_umma_rw(enable: bool) -> bool:
+    return bool(_L().vae_set_umma_rw(1 if enable else 0))
+
+
+def umma_rw_pack_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
+    Co, Ci = w.shape[0], w.shape[1]
+    out = torch.empty(9 * Ci * Co, dtype=torch.bfloat16, device=w.device)
+    rc = _L().vae_umma_rw_pack_weight(_f32(w, "conv weight"), _p(out), Ci, Co, mode, _stream())
+    _lib.check(rc, "vae_umma_rw_pack_weight")
+    return out
+
+
+def conv_umma_rw(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int):
+    """Resident-weight TMA/tcgen05 conv for the narrow layers (same contract as conv_umma_tma);
+    mode 1 computes the four output-parity phases of the transposed conv per tile."""
+    if inp.dtype != torch.bfloat16:
+        raise RuntimeError("conv_umma_rw: bf16 activations only")
+    B = inp.shape[0]
+    if mode == 0:
+        Hi, Wi = inp.shape[1], inp.shape[2]
+        out = torch.empty((B, Hi // stride, Wi // stride, Co), dtype=torch.bfloat16, device=inp.device)
+    else:
+        Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
+        out = torch.empty((B, Hi, Wi, Ci), dtype=torch.bfloat16, device=inp.device)
+    rc = _L().vae_conv_umma_rw(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), _p(stats), B, Hi, Wi, Ci, Co,
+                               stride, mode, _stream())
+    _lib.check(rc, "vae_conv_umma_rw")
+    return out
+
+
 class ConvWeights:
     """Per-step operand layouts of one 3x3 conv weight (fp32 OIHW master copy).
 
@@ -507,18 +542,24 @@ class ConvWeights:
     images; everything else gets the CUDA-core K-major packs.  Layouts are built
     lazily, once per forward (the optimizer changes the master copy every step)."""
 
-    __slots__ = ("w", "dtype", "stride", "Co", "Ci", "_simt", "_umma")
+    __slots__ = ("w", "dtype", "stride", "Co", "Ci", "_simt", "_umma", "_rw")
 
     def __init__(self, w: torch.Tensor, dtype: torch.dtype, stride: int):
         self.w, self.dtype, self.stride = w, dtype, stride
         self.Co, self.Ci = w.shape[0], w.shape[1]
         self._simt = None
         self._umma = {}
+        self._rw = {}
 
     def simt(self):
         if self._simt is None:
             self._simt = pack_conv_weight(self.w, self.dtype)
         return self._simt
+
+    def rw(self, mode: int):
+        if mode not in self._rw:
+            self._rw[mode] = umma_rw_pack_weight(self.w, mode)
+        return self._rw[mode]
 
     def umma(self, mode: int, tma: bool = False):
         if self.dtype != torch.bfloat16 or not umma_available():
@@ -533,6 +574,8 @@ class ConvWeights:
 def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None):
     """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies."""
     if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == cw.Ci:
+        if pro is None and umma_available() and umma_rw_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+            return conv_umma_rw(x, cw.rw(0), bias, stats, cw.Ci, cw.Co, cw.stride, 0)
         if pro is None and umma_tma_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
             return conv_umma_tma(x, cw.umma(0, tma=True), bias, stats, cw.Ci, cw.Co, cw.stride, 0)
         wpk = cw.umma(0)
@@ -547,6 +590,8 @@ def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
     """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward."""
     if dy.dtype == torch.bfloat16:
         s_ = cw.stride
+        if pro is None and umma_available() and umma_rw_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+            return conv_umma_rw(dy, cw.rw(1), bias, stats, cw.Ci, cw.Co, s_, 1)
         if pro is None and umma_tma_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
             return conv_umma_tma(dy, cw.umma(1, tma=True), bias, stats, cw.Ci, cw.Co, s_, 1)
         wpk = cw.umma(1)
