@@ -150,6 +150,41 @@ def test_umma_wgrad(ops, case):
     assert rel_err(dw, dw2) < 1e-4
 
 
+WG_TMA_CASES = [
+    # B, H, W, Ci, Co, stride : layer shapes of the default and the wide model
+    (2, 128, 128, 32, 32, 2),
+    (3, 64, 64, 32, 64, 2),
+    (5, 32, 32, 64, 128, 2),
+    (6, 16, 16, 128, 256, 2),
+    (3, 16, 16, 256, 512, 2),
+    (2, 16, 512, 64, 32, 2),
+    (3, 16, 16, 32, 32, 1),
+    (40, 64, 64, 32, 64, 2),    # many k-blocks per CTA: ring wrap-around
+    (130, 16, 16, 128, 128, 2),
+]
+
+
+@pytest.mark.parametrize("case", WG_TMA_CASES)
+def test_wgrad_tma(ops, case):
+    B, H, W, Ci, Co, s = case
+    assert ops._L().vae_wgrad_tma_eligible(B, H, W, Ci, Co, s)
+    x = rnd(B, Ci, H, W, seed=1)
+    dy = rnd(B, Co, H // s, W // s, seed=4)
+    wr = torch.zeros(Co, Ci, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.bfloat16().double(), wr, None, stride=s, padding=1).backward(dy.bfloat16().double())
+    xd, yd = nhwc(x).cuda().bfloat16(), nhwc(dy).cuda().bfloat16()
+    dw = ops.conv_weight_grad(xd, yd, s, Ci, Co, H, W)
+    torch.cuda.synchronize()
+    assert dw.shape == (Co, Ci, 3, 3) and dw.dtype == torch.float32
+    assert rel_err(dw.cpu(), wr.grad) < 1e-4
+    old = ops._L().vae_set_wgrad_tma(0)  # the cp.async kernel of the same library agrees
+    try:
+        dw2 = ops.conv_weight_grad(xd, yd, s, Ci, Co, H, W)
+    finally:
+        ops._L().vae_set_wgrad_tma(old)
+    assert rel_err(dw, dw2) < 1e-4
+
+
 TMA_CASES = [
     # B, H, W, Ci, Co, stride: extents that decompose into whole output rows per 128-pixel tile
     (2, 128, 128, 32, 32, 2),   # Wj = 64: two rows per tile

@@ -65,7 +65,7 @@ class _Proxy:
                           "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
-                          "vae_umma_rw_packed_elems"})
+                          "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -605,6 +605,14 @@ def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
 def conv_weight_grad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int):
     """dW [Co,Ci,3,3] fp32: tcgen05 kernel for bf16 tensor-core shaped layers, the
     CUDA-core kernels otherwise (fp32 path, single-channel edge layers)."""
+    if x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and umma_available() and \
+            _L().vae_wgrad_tma_eligible(dy.shape[0], Hi, Wi, Ci, Co, stride):
+        B = dy.shape[0]
+        dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+        ws = torch.empty(9 * Co * Ci, dtype=torch.float32, device=dy.device)
+        rc = _L().vae_conv_wgrad_tma(_p(x), _p(dy), _p(dw), _p(ws), B, Hi, Wi, Ci, Co, stride, _stream())
+        _lib.check(rc, "vae_conv_wgrad_tma")
+        return dw
     if x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and _L().vae_umma_wgrad_supported(Ci, Co):
         B = dy.shape[0]
         dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
