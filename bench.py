@@ -129,6 +129,23 @@ def algorithmic_cost(name, tag):
         B, Hi, Wi, Ci, Co, s, dx, dy = t[:8]
         Ho, Wo = Hi // s, Wi // s
         return (B * Hi * Wi * Ci * _sz(dx) + B * Ho * Wo * Co * _sz(dy) + 9 * Ci * Co * 4, 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name in ("vae_conv_umma", "vae_conv_umma_tma", "vae_conv_umma_rw"):
+        B, Hi, Wi, Ci, Co, s = t[:6]
+        Ho, Wo = Hi // s, Wi // s
+        return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co + 9 * Ci * Co), 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name in ("vae_conv_wgrad_umma", "vae_conv_wgrad_tma"):
+        B, Hi, Wi, Ci, Co, s = t[:6]
+        Ho, Wo = Hi // s, Wi // s
+        return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co) + 4 * 9 * Ci * Co, 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name == "vae_final_conv_fwd":  # reads y, writes logits (+ fp32 probabilities)
+        B, H, W, C, d = t[:5]
+        return (B * H * W * (C * _sz(d) + _sz(d) + 4), 2 * B * H * W * 9 * C)
+    if name == "vae_final_bwd_reduce":  # reads y and dlogits
+        B, H, W, C, d = t[:5]
+        return (B * H * W * (C + 1) * _sz(d), 4 * B * H * W * 9 * C)
+    if name == "vae_final_bwd_apply":  # reads y and dlogits, writes dy
+        B, H, W, C, _, d = t[:6]
+        return (B * H * W * (2 * C + 1) * _sz(d), 2 * B * H * W * 9 * C)
     if name == "vae_bn_apply_lrelu":
         n, C, d = t[:3]
         return (2 * n * C * _sz(d), 3 * n * C)
