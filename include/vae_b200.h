@@ -123,6 +123,30 @@ int vae_umma_wgrad_supported(int Ci, int Co);
 int vae_conv_wgrad_umma(const void* x, const void* dy, float* dw, int B, int Hi, int Wi, int Ci,
                         int Co, int stride, vae_stream_t stream);
 
+/* Resident-weight TMA/tcgen05 conv for the narrow layers (conv_umma_rw.cu): all nine weight
+ * images stay in shared memory, stages carry activations only; mode 1 computes the four
+ * output-parity phases of ConvTranspose2d(k3,s2,p1,op1) per tile from the same four boxes.
+ * Serves mode 0: Ci == 32, Co in {32,64}; mode 1: Ci == 32 (outputs), Co in {32,64}, stride 2.
+ * Same contract as vae_conv_umma_tma; wpk (9*Ci*Co bf16) from vae_umma_rw_pack_weight.
+ * replaces: aten::convolution (models.py:45,66-68,77) and the data-gradient half of
+ * aten::convolution_backward (train.py:650) on those layers */
+int vae_set_umma_rw(int enable);
+int vae_umma_rw_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode);
+long long vae_umma_rw_packed_elems(int Ci, int Co);
+int vae_umma_rw_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int mode,
+                            vae_stream_t stream);
+int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* out, double* stats,
+                     int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
+                     vae_stream_t stream);
+
+/* TMA-fed weight gradient (conv_wgrad_tma.cu): operands staged MN-major straight from NHWC
+ * boxes; ws is a caller-provided fp32 workspace of 9*Co*Ci elements; dw overwritten.
+ * replaces: the weight-gradient half of aten::convolution_backward (train.py:650) */
+int vae_set_wgrad_tma(int enable);
+int vae_wgrad_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride);
+int vae_conv_wgrad_tma(const void* x, const void* dy, float* dw, float* ws, int B, int Hi, int Wi,
+                       int Ci, int Co, int stride, vae_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * BatchNorm2d (train and eval) + LeakyReLU.   models.py:46-47,69-70,78-79
  * ---------------------------------------------------------------------- */
@@ -203,6 +227,31 @@ int vae_final_bwd_apply(const void* dlogits, const void* y, const float* mean, c
                         const double* dstats, void* dy, float* dgamma, float* dbeta, float* dbias,
                         float* db_last, int B, int H, int W, int C, float slope, int training,
                         int dtype, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Skinny GEMMs of the latent heads for L <= 16 (models.py:55-59,137,141,162 and their
+ * gradients inside train.py:650).  fp32 master weights are used in place:
+ * W(n, k) = W[n*wsn + k*wsk] covers both [L,F] (fc_mu / fc_var) and [F,L]
+ * (decoder_input) layouts.  K (= F) must be a multiple of 8.
+ * ---------------------------------------------------------------------- */
+int vae_heads_supported(int F, int L);
+
+/* out[M][N] fp32 = A[M][K] (dtype dtA) . W + bias.
+ * replaces: aten::addmm at models.py:137,141 and dL/dz of decoder_input */
+int vae_skinny_reduce(const void* A, const float* W, const float* bias, float* out, int M, int N,
+                      int K, long long wsn, long long wsk, int dtA, vae_stream_t stream);
+
+/* G[n*gsn + k*gsk] += sum_m D[m][n]*A[m][k]; colsum[k] += sum_m A[m][k] (may be NULL).
+ * G and colsum must be zeroed by the caller.
+ * replaces: weight / bias gradients of the three Linear layers */
+int vae_skinny_wgrad(const float* D, const void* A, float* G, float* colsum, int M, int N, int K,
+                     long long gsn, long long gsk, int dtA, vae_stream_t stream);
+
+/* out[M][K] (dtype dtO) = bias[k] + D0.W0 (+ D1.W1), D [M][N] fp32.
+ * replaces: aten::addmm at models.py:162 and the input gradient of fc_mu + fc_var */
+int vae_skinny_expand(const float* D0, const float* W0, const float* D1, const float* W1,
+                      const float* bias, void* out, int M, int N, int K, long long wsn,
+                      long long wsk, int dtO, vae_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Layout glue between the NHWC conv stack and the reference's C-major

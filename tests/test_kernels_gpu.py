@@ -342,3 +342,37 @@ def test_final_block_forward_backward(tv, case, dtype, training):
         assert float(dbias.abs().max()) <= 1e-3 * scale_ref
     else:
         assert rel_err(dbias, yq.grad.sum((0, 2, 3))) <= max(gtol, 1e-4)
+
+
+# ---------------------------------------------------------------------------
+# skinny GEMMs of the latent heads (heads.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(7, 1024, 10), (64, 16384, 10), (5, 4096, 6), (33, 2048, 16), (3, 264, 1)])
+def test_skinny_head_gemms(tv, shape, dtype):
+    ops = tv.ops
+    M, Fd, L = shape
+    assert ops.heads_supported(Fd, L)
+    a = rnd(M, Fd, seed=21)
+    w_lf = rnd(L, Fd, seed=22, scale=1.0 / math.sqrt(Fd))   # fc_mu / fc_var layout
+    w_fl = rnd(Fd, L, seed=23, scale=1.0 / math.sqrt(L))    # decoder_input layout
+    b_l, b_f = rnd(L, seed=24, scale=0.1), rnd(Fd, seed=25, scale=0.1)
+    d0, d1 = rnd(M, L, seed=26), rnd(M, L, seed=27)
+    aq = q(a, dtype)
+    tol = TOL[dtype]
+    # reduce: [L,F] layout (forward heads) and [F,L] layout (dz)
+    out = ops.skinny_reduce(dev(a.to(dtype)), dev(w_lf), dev(b_l), Fd, 1, L)
+    assert rel_err(out, aq @ w_lf.double().t() + b_l.double()) <= 1e-5
+    out = ops.skinny_reduce(dev(a.to(dtype)), dev(w_fl), None, 1, L, L)
+    assert rel_err(out, aq @ w_fl.double()) <= 1e-5
+    # weight gradients in both layouts, with the column sums
+    g, cs = ops.skinny_wgrad(dev(d0), dev(a.to(dtype)), (L, Fd), Fd, 1, False)
+    assert cs is None and rel_err(g, d0.double().t() @ aq) <= 1e-5
+    g, cs = ops.skinny_wgrad(dev(d0), dev(a.to(dtype)), (Fd, L), 1, L, True)
+    assert rel_err(g, aq.t() @ d0.double()) <= 1e-5
+    assert rel_err(cs, aq.sum(0)) <= 1e-5
+    # expand: decoder_input forward and the summed input gradient of the two heads
+    out = ops.skinny_expand(dev(d0), dev(w_fl), None, None, dev(b_f), 1, L, Fd, dtype)
+    assert rel_err(out.float(), d0.double() @ w_fl.double().t() + b_f.double()) <= tol
+    out = ops.skinny_expand(dev(d0), dev(w_lf), dev(d1), dev(w_lf * 0.5), None, Fd, 1, Fd, dtype)
+    assert rel_err(out.float(), (d0.double() + 0.5 * d1.double()) @ w_lf.double()) <= tol

@@ -54,6 +54,10 @@ PROTOTYPES = {
     "vae_final_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
     "vae_final_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f,
                             _i, _i, _vp],
+    "vae_heads_supported": [_i, _i],
+    "vae_skinny_reduce": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
+    "vae_skinny_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
+    "vae_skinny_expand": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vae_nchw_to_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "vae_gemm": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _vp],

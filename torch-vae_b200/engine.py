@@ -87,8 +87,13 @@ class EncodeFn(torch.autograd.Function):
             h = act
             Hi, Wi = Hi // 2, Wi // 2
         pre = ops.nhwc_to_nchw(h)  # [B, C*h*w], C-major like x.flatten(1) (models.py:133)
-        mu = ops.linear_fwd(pre, w_mu, b_mu, torch.float32)
-        log_var = ops.linear_fwd(pre, w_var, b_var, torch.float32)
+        F_, L_ = pre.shape[1], w_mu.shape[0]
+        if ops.heads_supported(F_, L_):
+            mu = ops.skinny_reduce(pre, w_mu, b_mu, F_, 1, L_)
+            log_var = ops.skinny_reduce(pre, w_var, b_var, F_, 1, L_)
+        else:
+            mu = ops.linear_fwd(pre, w_mu, b_mu, torch.float32)
+            log_var = ops.linear_fwd(pre, w_var, b_var, torch.float32)
         ctx.specs, ctx.training, ctx.saved, ctx.feat = specs, training, saved, (specs[-1].co, Hi, Wi)
         ctx.save_for_backward(pre, w_mu, w_var, b_mu, b_var, *conv_params)
         ctx.x_needs_grad = x.requires_grad
@@ -106,12 +111,18 @@ class EncodeFn(torch.autograd.Function):
         if dlv is None:
             dlv = torch.zeros((B, L), dtype=torch.float32, device=dev)
         dmu, dlv = dmu.contiguous(), dlv.contiguous()
-        d_pre = ops.linear_bwd_input(dmu, w_mu, out_dtype=pre.dtype)
-        ops.linear_bwd_input(dlv, w_var, out=d_pre, accumulate=True)
+        F_ = pre.shape[1]
+        if ops.heads_supported(F_, L):
+            d_pre = ops.skinny_expand(dmu, w_mu, dlv, w_var, None, F_, 1, F_, pre.dtype)
+            g_w_mu, _ = ops.skinny_wgrad(dmu, pre, (L, F_), F_, 1, False)
+            g_w_var, _ = ops.skinny_wgrad(dlv, pre, (L, F_), F_, 1, False)
+        else:
+            d_pre = ops.linear_bwd_input(dmu, w_mu, out_dtype=pre.dtype)
+            ops.linear_bwd_input(dlv, w_var, out=d_pre, accumulate=True)
+            g_w_mu, g_w_var = ops.linear_bwd_weight(dmu, pre), ops.linear_bwd_weight(dlv, pre)
         if dpre is not None:
             d_pre = d_pre + dpre.to(d_pre.dtype)
-        g_w_mu, g_b_mu = ops.linear_bwd_weight(dmu, pre), ops.colsum(dmu)
-        g_w_var, g_b_var = ops.linear_bwd_weight(dlv, pre), ops.colsum(dlv)
+        g_b_mu, g_b_var = ops.colsum(dmu), ops.colsum(dlv)
         if sink is not None:
             for p_, g_ in ((w_mu, g_w_mu), (b_mu, g_b_mu), (w_var, g_w_var), (b_var, g_b_var)):
                 sink.push(p_, g_)
@@ -174,7 +185,11 @@ class DecodeFn(torch.autograd.Function):
             z = z.float()
         B = z.shape[0]
         C, h0, w0 = feat
-        d = ops.linear_fwd(z, w_in, b_in, dtype)  # [B, C*h*w], C-major
+        L_, F_ = z.shape[1], w_in.shape[0]
+        if ops.heads_supported(F_, L_):
+            d = ops.skinny_expand(z, w_in, None, None, b_in, 1, L_, F_, dtype)  # [B, C*h*w], C-major
+        else:
+            d = ops.linear_fwd(z, w_in, b_in, dtype)
         h = ops.nchw_to_nhwc(d, C, h0, w0)
         saved = []
         fused_last = False
@@ -263,12 +278,22 @@ class DecodeFn(torch.autograd.Function):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
             d_act = ops.conv_forward(dy, cw, None)  # gradient w.r.t. the ConvT input
         d_d = ops.nhwc_to_nchw(d_act)  # [B, F] C-major, matching decoder_input's output
-        g_w_in = ops.linear_bwd_weight(d_d, z)
-        g_b_in = ops.colsum(d_d)
+        L_, F_ = z.shape[1], w_in.shape[0]
+        skinny = ops.heads_supported(F_, L_)
+        if skinny:
+            g_w_in, g_b_in = ops.skinny_wgrad(z, d_d, (F_, L_), 1, L_, True)
+        else:
+            g_w_in = ops.linear_bwd_weight(d_d, z)
+            g_b_in = ops.colsum(d_d)
         if sink is not None:
             sink.push(w_in, g_w_in)
             sink.push(b_in, g_b_in)
-        dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32) if ctx.z_needs_grad else None
+        if not ctx.z_needs_grad:
+            dz = None
+        elif skinny:
+            dz = ops.skinny_reduce(d_d, w_in, None, 1, L_, L_)
+        else:
+            dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32)
         ctx.saved = None
         ctx.last = None
         return (None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)

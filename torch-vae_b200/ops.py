@@ -65,7 +65,7 @@ class _Proxy:
                           "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
-                          "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible"})
+                          "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -292,6 +292,43 @@ def gemm(A, Bm, out, M, N, K, sa, sb, sc, bias=None, accumulate=False):
         code(A), code(Bm), code(out), 1 if accumulate else 0, _stream(),
     )
     _lib.check(rc, "vae_gemm")
+    return out
+
+
+def heads_supported(F: int, L: int) -> bool:
+    return bool(_L().vae_heads_supported(F, L))
+
+
+def skinny_reduce(A, W, bias, wsn: int, wsk: int, N: int):
+    """out[M,N] fp32 = A[M,K] . W(n,k) + bias, W(n,k) = W.flat[n*wsn + k*wsk]."""
+    M, K = A.shape
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    rc = _L().vae_skinny_reduce(_p(A), _f32(W, "weight"), _f32(bias, "bias"), _p(out), M, N, K, wsn, wsk, code(A),
+                                _stream())
+    _lib.check(rc, "vae_skinny_reduce")
+    return out
+
+
+def skinny_wgrad(D, A, g_shape, gsn: int, gsk: int, want_colsum: bool):
+    """G(n,k) = sum_m D[m,n] A[m,k] laid out as G.flat[n*gsn + k*gsk]; colsum[k] = sum_m A[m,k]."""
+    M, K = A.shape
+    N = D.shape[1]
+    buf = torch.zeros(N * K + (K if want_colsum else 0), dtype=torch.float32, device=A.device)
+    G = buf[: N * K].view(g_shape)
+    cs = buf[N * K:] if want_colsum else None
+    rc = _L().vae_skinny_wgrad(_f32(D, "latent gradient"), _p(A), G.data_ptr(), cs.data_ptr() if want_colsum else None,
+                               M, N, K, gsn, gsk, code(A), _stream())
+    _lib.check(rc, "vae_skinny_wgrad")
+    return G, cs
+
+
+def skinny_expand(D0, W0, D1, W1, bias, wsn: int, wsk: int, K: int, out_dtype):
+    """out[M,K] = bias + D0 . W0 (+ D1 . W1)."""
+    M, N = D0.shape
+    out = torch.empty((M, K), dtype=out_dtype, device=D0.device)
+    rc = _L().vae_skinny_expand(_f32(D0, "latent"), _f32(W0, "weight"), _f32(D1, "latent"), _f32(W1, "weight"),
+                                _f32(bias, "bias"), _p(out), M, N, K, wsn, wsk, code(out_dtype), _stream())
+    _lib.check(rc, "vae_skinny_expand")
     return out
 
 
