@@ -228,6 +228,25 @@ int vae_final_bwd_apply(const void* dlogits, const void* y, const float* mean, c
                         float* db_last, int B, int H, int W, int C, float slope, int training,
                         int dtype, vae_stream_t stream);
 
+/* tcgen05 / TMEM versions of the three output-block kernels (final_block_tc.cu) for bf16,
+ * C == 32, W == 128: per pixel the C->1 conv is P[p][tap] = act[p][:] . w[tap][:] (a GEMM with
+ * M = pixels, N = 9, K = C) followed by a 9-point shifted sum; its data gradient is a GEMM with
+ * K = 9.  Same contracts as the entry points above. */
+int vae_set_final_tc(int enable);
+int vae_final_tc_supported(int B, int H, int W, int C, int dtype);
+int vae_final_conv_fwd_tc(const void* y, const float* mean, const float* scale, const float* beta,
+                          const float* w_last, const float* b_last, void* logits, float* probs,
+                          int B, int H, int W, int C, float slope, vae_stream_t stream);
+int vae_final_bwd_reduce_tc(const void* dlogits, const void* y, const float* mean, const float* scale,
+                            const float* beta, const float* rstd, const float* w_last, double* dstats,
+                            float* dw_last, int B, int H, int W, int C, float slope,
+                            vae_stream_t stream);
+int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const float* mean, const float* scale,
+                           const float* beta, const float* rstd, const float* gamma, const float* w_last,
+                           const double* dstats, void* dy, float* dgamma, float* dbeta, float* dbias,
+                           float* db_last, int B, int H, int W, int C, float slope, int training,
+                           vae_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Skinny GEMMs of the latent heads for L <= 16 (models.py:55-59,137,141,162 and their
  * gradients inside train.py:650).  fp32 master weights are used in place:

@@ -286,6 +286,8 @@ FINAL_CASES = [
     (2, 8, 64, 16),
     (1, 24, 36, 64),  # partial tiles in both directions
     (2, 128, 128, 32),
+    (3, 64, 128, 32),   # tcgen05 path (bf16): two 32-row bands per image
+    (5, 48, 128, 32),   # tcgen05 path: 16-row bands
 ]
 
 
@@ -299,7 +301,9 @@ def test_final_block_forward_backward(tv, case, dtype, training):
     y = rnd(B, C, H, W, seed=11) * 1.5 + 0.3
     gamma = rnd(C, seed=12, scale=0.3) + 1.0
     beta = rnd(C, seed=13, scale=0.2)
-    w_last = rnd(1, C, 3, 3, seed=14, scale=1.0 / math.sqrt(9 * C))
+    # bf16-representable weights: the tcgen05 kernels feed the tensor cores bf16 weight images, the
+    # CUDA-core kernels read the fp32 master; with representable values both see the same numbers
+    w_last = rnd(1, C, 3, 3, seed=14, scale=1.0 / math.sqrt(9 * C)).bfloat16().float()
     b_last = rnd(1, seed=15, scale=0.1)
     dlog = rnd(B, 1, H, W, seed=16, scale=1.0 / (B * H * W))
     run_mean, run_var = rnd(C, seed=17, scale=0.1) + 0.3, torch.rand(C, generator=torch.Generator().manual_seed(18)) + 1.5
@@ -326,15 +330,32 @@ def test_final_block_forward_backward(tv, case, dtype, training):
     assert logits.shape == (B, 1, H, W) and probs.dtype == torch.float32
     assert rel_err(logits.float(), logits_ref.detach()) <= tol
     assert rel_err(probs, torch.sigmoid(logits.double())) <= 1e-6
+    if ops.final_tc_supported(y_d):  # the CUDA-core kernels of the same library agree
+        old = ops.set_final_tc(False)
+        try:
+            logits2, _ = ops.final_conv_fwd(y_d, vec, dev(beta), dev(w_last), dev(b_last))
+        finally:
+            ops.set_final_tc(old)
+        assert rel_err(logits.float(), logits2.float()) <= tol
 
     dy, dgamma, dbeta, dbias, dw, db = ops.final_block_backward(
         dev(dlog.to(dtype)), y_d, vec, dev(gamma), dev(beta), dev(w_last), training)
+    if ops.final_tc_supported(y_d):  # the CUDA-core kernels of the same library agree
+        old = ops.set_final_tc(False)
+        try:
+            ref2 = ops.final_block_backward(dev(dlog.to(dtype)), y_d, vec, dev(gamma), dev(beta), dev(w_last), training)
+        finally:
+            ops.set_final_tc(old)
+        assert rel_err(dy.float(), ref2[0].float()) <= tol
+        # dw: the tensor-core path rounds the normalised activation to bf16 before the pixel sum
+        for got, want, lim in zip((dgamma, dbeta, dw, db), (ref2[1], ref2[2], ref2[4], ref2[5]), (2e-3, 2e-3, 6e-3, 2e-3)):
+            assert rel_err(got, want) <= lim
     # gradients: fp32 arithmetic on (for bf16) rounded operands, one output rounding for dy
     assert rel_err(nchw(dy.float()), yq.grad) <= tol
     gtol = 1e-5 if dtype == torch.float32 else 2e-3
     assert rel_err(dgamma, g64.grad) <= gtol
     assert rel_err(dbeta, b64.grad) <= gtol
-    assert rel_err(dw, w64.grad) <= gtol
+    assert rel_err(dw, w64.grad) <= (6e-3 if ops.final_tc_supported(y_d) else gtol)
     assert rel_err(db, bl64.grad) <= gtol
     # bias of the conv feeding a train-mode BatchNorm: exactly zero in exact arithmetic
     scale_ref = float(yq.grad.abs().sum())

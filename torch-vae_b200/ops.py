@@ -65,7 +65,8 @@ class _Proxy:
                           "vae_umma_packed_elems", "vae_umma_wgrad_supported", "vae_umma_set_trace",
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
-                          "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported"})
+                          "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported", "vae_set_final_tc",
+                          "vae_final_tc_supported"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -224,12 +225,28 @@ def final_block_supported(B: int, H: int, W: int, C: int) -> bool:
     return bool(_L().vae_final_block_supported(B, H, W, C))
 
 
+def final_tc_supported(y) -> bool:
+    B, H, W, C = y.shape
+    return y.dtype == torch.bfloat16 and umma_available() and bool(_L().vae_final_tc_supported(B, H, W, C, code(y)))
+
+
+def set_final_tc(enable: bool) -> bool:
+    return bool(_L().vae_set_final_tc(1 if enable else 0))
+
+
 def final_conv_fwd(y, vec, beta, w_last, b_last, slope: float = LRELU_SLOPE):
     """y [B,H,W,C] raw ConvT output -> (logits [B,1,H,W] in y.dtype, probs [B,1,H,W] fp32):
     BatchNorm apply + LeakyReLU + Conv2d(C->1) + Sigmoid in one pass over y."""
     B, H, W, C = y.shape
     logits = torch.empty((B, 1, H, W), dtype=y.dtype, device=y.device)
     probs = torch.empty((B, 1, H, W), dtype=torch.float32, device=y.device)
+    if final_tc_supported(y):
+        rc = _L().vae_final_conv_fwd_tc(
+            _p(y), vec[2].data_ptr(), vec[0].data_ptr(), _f32(beta, "bn bias"), _f32(w_last, "final conv weight"),
+            _f32(b_last, "final conv bias"), _p(logits), _p(probs), B, H, W, C, slope, _stream(),
+        )
+        _lib.check(rc, "vae_final_conv_fwd_tc")
+        return logits, probs
     rc = _L().vae_final_conv_fwd(
         _p(y), vec[2].data_ptr(), vec[0].data_ptr(), _f32(beta, "bn bias"), _f32(w_last, "final conv weight"),
         _f32(b_last, "final conv bias"), _p(logits), _p(probs), B, H, W, C, slope, code(y), _stream(),
@@ -246,19 +263,33 @@ def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, s
     dstats = torch.empty(2 * C + 1, dtype=torch.float64, device=y.device)
     dw_last = torch.empty((1, C, 3, 3), dtype=torch.float32, device=y.device)
     mean, scale, rstd = vec[2].data_ptr(), vec[0].data_ptr(), vec[3].data_ptr()
-    rc = lib.vae_final_bwd_reduce(
-        _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(w_last, "final conv weight"), _p(dstats),
-        _p(dw_last), B, H, W, C, slope, code(y), _stream(),
-    )
+    tc = final_tc_supported(y)
+    if tc:
+        rc = lib.vae_final_bwd_reduce_tc(
+            _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(w_last, "final conv weight"),
+            _p(dstats), _p(dw_last), B, H, W, C, slope, _stream(),
+        )
+    else:
+        rc = lib.vae_final_bwd_reduce(
+            _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(w_last, "final conv weight"),
+            _p(dstats), _p(dw_last), B, H, W, C, slope, code(y), _stream(),
+        )
     _lib.check(rc, "vae_final_bwd_reduce")
     dy = torch.empty_like(y)
     small = torch.empty((3, C), dtype=torch.float32, device=y.device)
     db_last = torch.empty(1, dtype=torch.float32, device=y.device)
-    rc = lib.vae_final_bwd_apply(
-        _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
-        _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
-        small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, code(y), _stream(),
-    )
+    if tc:
+        rc = lib.vae_final_bwd_apply_tc(
+            _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
+            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
+            small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, _stream(),
+        )
+    else:
+        rc = lib.vae_final_bwd_apply(
+            _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
+            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
+            small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, code(y), _stream(),
+        )
     _lib.check(rc, "vae_final_bwd_apply")
     return dy, small[0], small[1], small[2], dw_last, db_last
 
