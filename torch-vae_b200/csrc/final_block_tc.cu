@@ -6,22 +6,24 @@
 //           logit[q] = bias + sum_t P[q + d(t)][t]        (a 9-point shifted sum of P)
 // and its data gradient is   da[p][c] = sum_t dl[p - d(t)] * w[t][c]   (M = pixels, N = C, K = 9 taps)
 // so every element of the big tensor y is touched by CUDA cores only for the BatchNorm /
-// LeakyReLU transform (4-8 instructions per element instead of ~26-30 in the SIMT kernels).
+// LeakyReLU transform (5-8 instructions per element instead of ~26-30 in the SIMT kernels).
 //
 // Data flow per image row (128 pixels = one UMMA M tile):
-//   TMA        y row [128 px][64 B] -> shared, 64B-swizzled (a ring of 4 rows, prefetched)
-//   workers    thread = pixel: read its 64 B, BatchNorm + LeakyReLU, write bf16 act back IN PLACE:
-//              the row buffer now IS the K-major (forward) / MN-major (weight gradient) UMMA operand
+//   TMA        y row [128 px][64 B] -> shared, 64B-swizzled (ring of rows, prefetched)
+//   workers    two threads per pixel (16 channels each): read, BatchNorm + LeakyReLU, write bf16 act
+//              back IN PLACE: the row buffer now IS the K-major (forward) / MN-major (weight
+//              gradient) UMMA operand
 //   MMA warp   one elected thread issues tcgen05.mma, accumulators in TMEM
 //   workers    tcgen05.ld their pixel's row of the accumulator and finish (shifted sum / BN backward)
 //
-//   warps 0-3 : workers (128 threads)      warp 4 : TMA producer      warp 5 : MMA issuer
+//   warps 0-7 : workers (256 threads)      warp 8 : TMA producer      warp 9 : MMA issuer
 #include "tma_util.cuh"
 
 namespace vae {
 
-constexpr int kFtThreads = 192;
-constexpr int kFtSlots = 8;      // ring of raw y rows (64 KB in flight per CTA)
+constexpr int kFtThreads = 320;
+constexpr int kFtWorkers = 256;
+constexpr int kFtSlots = 6;      // ring of raw y rows
 constexpr int kRowBytes = 8192;  // 128 pixels x 32 channels x bf16
 
 struct FinalTcParams {
@@ -39,22 +41,47 @@ struct FinalTcParams {
   bf16* dy;              // [B][H][W][C]
   double* dstats;        // [2C + 1]
   float* dw_last;        // [C][9]
-  float* dbias;          // [C]
   int B, H, W, RB, bands_per_img, total_bands, training;
   float slope;
 };
+
+// ---- shared-memory access by 32-bit shared address (keeps the compiler off generic LD/ST) ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void load8f(uint32_t a, float* v) {  // 8 consecutive floats
+  const float4 x = lds_f4(a), y = lds_f4(a + 16);
+  v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+}
 
 __device__ __forceinline__ uint32_t swz64(int row, int chunk) {  // byte offset inside a [rows][64 B] 64B-swizzled tile
   return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
 __device__ __forceinline__ void unpack8(const uint4& raw, float* v) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float* v) {
@@ -80,17 +107,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// 32 lanes x 16 columns of fp32
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // =============================================================================================
 // forward: logits = conv(lrelu(bn(y)), w_last) + b_last, probs = sigmoid(logits)
 // =============================================================================================
-__global__ void __launch_bounds__(kFtThreads, 2)
+constexpr size_t kFwdSmemBytes = 1024 + kFtSlots * kRowBytes + 2048 + 4 * 9 * 130 * 4 + 64 * 4 + 8 * (3 * kFtSlots + 4) + 16;
+
+__global__ void __launch_bounds__(kFtThreads, 3)
 final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;                                   // [4][8 KB]
+  uint8_t* ring = smem;                                   // [slots][8 KB]
   uint8_t* wimg = ring + kFtSlots * kRowBytes;            // [32 taps][64 B] swizzled, taps 9..31 zero
   float* psm = reinterpret_cast<float*>(wimg + 2048);     // [4][9][130]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(psm + 4 * 9 * 130);
+  float* cst = psm + 4 * 9 * 130;                         // scale[32], shift[32]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cst + 64);
   uint64_t* empty_bar = full_bar + kFtSlots;
   uint64_t* aready_bar = empty_bar + kFtSlots;
   uint64_t* dfull_bar = aready_bar + kFtSlots;   // [2]
@@ -98,12 +140,12 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int s = 0; s < kFtSlots; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
-        mbar_init(&aready_bar[s], 128);
+        mbar_init(&aready_bar[s], kFtWorkers);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&dfull_bar[a], 1);
@@ -114,24 +156,31 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     __syncwarp();
     tmem_alloc(tmem_ptr, 64);
   }
-  if (warp < 4) {
-    // weight image: row t (tap), 32 channels; thread -> (tap, 8-channel chunk)
-    const int t = threadIdx.x >> 2, c8 = threadIdx.x & 3;
-    float v[8];
+  if (warp < 8) {
+    const int tid = threadIdx.x;
+    if (tid < 128) {  // weight image: row t (tap), 32 channels; thread -> (tap, 8-channel chunk)
+      const int t = tid >> 2, c8 = tid & 3;
+      float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = t < 9 ? P.w_last[(c8 * 8 + k) * 9 + t] : 0.0f;
-    *reinterpret_cast<uint4*>(wimg + swz64(t, c8)) = pack8(v);
-    for (int i = threadIdx.x; i < 4 * 9 * 130; i += 128) psm[i] = 0.0f;
+      for (int k = 0; k < 8; ++k) v[k] = t < 9 ? P.w_last[(c8 * 8 + k) * 9 + t] : 0.0f;
+      *reinterpret_cast<uint4*>(wimg + swz64(t, c8)) = pack8(v);
+    } else if (tid < 160) {
+      const int c = tid - 128;
+      const float sc = P.scale[c];
+      cst[c] = sc;
+      cst[32 + c] = fmaf(-P.mean[c], sc, P.beta[c]);
+    }
+    for (int i = tid; i < 4 * 9 * 130; i += kFtWorkers) psm[i] = 0.0f;
     fence_proxy_async_smem();
   }
-  if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
+  if (warp == 8 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int H = P.H, RB = P.RB;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== producer ==============================
     if (lane == 0) {
       uint32_t n = 0;
@@ -148,7 +197,7 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================= MMA issuer =============================
     const uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
     const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wimg);
@@ -178,15 +227,11 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     }
   } else {
     // =============================== workers ==============================
-    const int p = threadIdx.x;  // pixel of the row
-    float sc[32], sh[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      sc[c] = P.scale[c];
-      sh[c] = fmaf(-P.mean[c], sc[c], P.beta[c]);
-    }
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;  // pixel of the row, channel half
     const float slope = P.slope, bias = P.b_last != nullptr ? P.b_last[0] : 0.0f;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t ring_a = smem_u32(ring), psm_a = smem_u32(psm), cst_a = smem_u32(cst);
+    const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
     uint32_t n_t = 0, n_e = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
       const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
@@ -195,18 +240,20 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         if (h < 0 || h >= H) return;
         const uint32_t slot = n_t % kFtSlots, ph = (n_t / kFtSlots) & 1u;
         mbar_wait(&full_bar[slot], ph);
-        uint8_t* row = ring + slot * kRowBytes;
+        const uint32_t row = ring_a + slot * kRowBytes;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint4* ptr = reinterpret_cast<uint4*>(row + swz64(p, c4));
-          float v[8];
-          unpack8(*ptr, v);
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t a = row + (j == 0 ? off0 : off1);
+          float v[8], sc[8], sh[8];
+          unpack8(lds128(a), v);
+          load8f(cst_a + (2 * half + j) * 32, sc);
+          load8f(cst_a + 128 + (2 * half + j) * 32, sh);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float u = fmaf(v[k], sc[c4 * 8 + k], sh[c4 * 8 + k]);
+            const float u = fmaf(v[k], sc[k], sh[k]);
             v[k] = fmaxf(u, u * slope);  // LeakyReLU for 0 < slope < 1
           }
-          *ptr = pack8(v);
+          sts128(a, pack8(v));
         }
         fence_proxy_async_smem();
         mbar_arrive(&aready_bar[slot]);
@@ -216,32 +263,35 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       for (int i = 0; i < RB + 2; ++i) {
         if (i + 1 < RB + 2) transform(i + 1);
         const int h = h0 - 1 + i;
-        float* ps = psm + (i & 3) * (9 * 130) + p + 1;
-        if (h >= 0 && h < H) {
-          const uint32_t db = n_e & 1u, dph = (n_e >> 1) & 1u;
-          mbar_wait(&dfull_bar[db], dph);
-          tc_fence_after();
-          float v[32];
-          tmem_ld_32x32(t_lane + db * 32, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&dempty_bar[db]);
-          ++n_e;
+        const bool valid = h >= 0 && h < H;
+        if (half == 0) {  // P row -> ring of fp32 rows [4][9][130]
+          const uint32_t ps = psm_a + (uint32_t)(((i & 3) * (9 * 130) + p + 1) * 4);
+          if (valid) {
+            const uint32_t db = n_e & 1u, dph = (n_e >> 1) & 1u;
+            mbar_wait(&dfull_bar[db], dph);
+            tc_fence_after();
+            float v[16];
+            tmem_ld_32x16(t_lane + db * 32, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&dempty_bar[db]);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) ps[t * 130] = v[t];
-        } else {
+            for (int t = 0; t < 9; ++t) sts_f(ps + t * 520, v[t]);
+          } else {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) ps[t * 130] = 0.0f;
+            for (int t = 0; t < 9; ++t) sts_f(ps + t * 520, 0.0f);
+          }
         }
-        named_bar_sync(1, 128);
-        if (i >= 2) {
+        if (valid) ++n_e;
+        named_bar_sync(1, kFtWorkers);
+        if (half == 1 && i >= 2) {
           const int q = h - 1;  // image row whose 3x3 window is now complete
           float acc = bias;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const float* pr = psm + ((i - 2 + kh) & 3) * (9 * 130) + p;
+            const uint32_t pr = psm_a + (uint32_t)(((((i - 2 + kh) & 3) * (9 * 130)) + p) * 4);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) acc += pr[(kh * 3 + kw) * 130 + kw];
+            for (int kw = 0; kw < 3; ++kw) acc += lds_f(pr + ((kh * 3 + kw) * 130 + kw) * 4);
           }
           const long long o = ((long long)b * H + q) * 128 + p;
           const bf16 lg = __float2bfloat16_rn(acc);
@@ -249,12 +299,12 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
           if (P.probs != nullptr) P.probs[o] = 1.0f / (1.0f + expf(-__bfloat162float(lg)));
         }
       }
-      named_bar_sync(1, 128);  // the next band reuses the P ring from slot 0
+      named_bar_sync(1, kFtWorkers);  // the next band reuses the P ring from slot 0
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 64);
   }
@@ -266,27 +316,6 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 //   A1 tile   : dlwin[p][widx] = dl[h + a - 1][p + b - 1], widx = 3a + b  (9 of 32 bf16 per 64-byte row)
 //   B1 image  : [c][widx] = w[c][8 - widx]      =>  da = A1 . B1^T  (one K = 16 MMA)
 // =============================================================================================
-__device__ __forceinline__ void load_dl_row(const bf16* __restrict__ dl, float* dlsm, int b, int h, int H, int p,
-                                            int slot) {
-  float v = 0.0f;
-  if (h >= 0 && h < H) v = __bfloat162float(dl[((long long)b * H + h) * 128 + p]);
-  dlsm[slot * 130 + p + 1] = v;
-}
-
-// writes the K = 16 part of row p of the A1 tile (chunks 0 and 1); returns the centre value
-__device__ __forceinline__ float build_a1_row(const float* dlsm, uint8_t* a1, int i, int p) {
-  float w[16];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 3; ++bb) w[a * 3 + bb] = dlsm[((i + a) & 3) * 130 + p + bb];
-#pragma unroll
-  for (int k = 9; k < 16; ++k) w[k] = 0.0f;
-  *reinterpret_cast<uint4*>(a1 + swz64(p, 0)) = pack8(w);
-  *reinterpret_cast<uint4*>(a1 + swz64(p, 1)) = pack8(w + 8);
-  return w[4];
-}
-
 struct BwdSmem {
   uint8_t* ring;    // [kFtSlots][8 KB] y rows (TMA), rewritten in place as act by pass 1
   uint8_t* a1;      // [2][8 KB]
@@ -294,12 +323,12 @@ struct BwdSmem {
   float* dlsm;      // [4][130]
   float* cst;       // per-channel constants, [5][32]
   float* red;       // [2][32] block reduction scratch (+ 8 for the bias sum)
-  uint64_t* full_bar;   // [4] TMA -> workers
-  uint64_t* empty_bar;  // [4] -> producer
+  uint64_t* full_bar;     // TMA -> workers
+  uint64_t* empty_bar;    // -> producer
   uint64_t* a1ready_bar;  // [2] workers -> MMA
   uint64_t* d1full_bar;   // [2] MMA -> workers
   uint64_t* d1empty_bar;  // [2] workers -> MMA
-  uint64_t* a2ready_bar;  // [4] workers -> MMA (pass 1)
+  uint64_t* a2ready_bar;  // workers -> MMA (pass 1)
   uint64_t* done_bar;     // [1]
   uint32_t* tmem_ptr;
 };
@@ -335,17 +364,17 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   BwdSmem S = carve_bwd(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = P.H, RB = P.RB;
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       for (int s = 0; s < kFtSlots; ++s) {
         mbar_init(&S.full_bar[s], 1);
-        mbar_init(&S.empty_bar[s], PASS == 1 ? 1 : 128);  // pass 1: freed by the MMA commit; pass 2: by the workers
-        mbar_init(&S.a2ready_bar[s], 128);
+        mbar_init(&S.empty_bar[s], PASS == 1 ? 1 : kFtWorkers);  // pass 1: freed by the MMA commit; pass 2: by the workers
+        mbar_init(&S.a2ready_bar[s], kFtWorkers);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&S.a1ready_bar[a], 128);
         mbar_init(&S.d1full_bar[a], 1);
-        mbar_init(&S.d1empty_bar[a], 128);
+        mbar_init(&S.d1empty_bar[a], kFtWorkers);
       }
       mbar_init(S.done_bar, 1);
       fence_barrier_init();
@@ -353,9 +382,9 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     __syncwarp();
     tmem_alloc(S.tmem_ptr, 128);
   }
-  if (warp < 4) {
+  if (warp < 8) {
     const int tid = threadIdx.x;
-    {  // B1 image: row c, chunk j -> widx = 8j .. 8j+7
+    if (tid < 128) {  // B1 image: row c, chunk j -> widx = 8j .. 8j+7
       const int c = tid >> 2, j = tid & 3;
       float v[8];
 #pragma unroll
@@ -364,11 +393,8 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         v[k] = widx < 9 ? P.w_last[c * 9 + (8 - widx)] : 0.0f;
       }
       *reinterpret_cast<uint4*>(S.b1 + swz64(c, j)) = pack8(v);
-    }
-    for (int i = tid; i < 2 * kRowBytes / 16; i += 128) reinterpret_cast<uint4*>(S.a1)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 4 * 130; i += 128) S.dlsm[i] = 0.0f;
-    if (tid < 32) {
-      const int c = tid;
+    } else if (tid < 160) {
+      const int c = tid - 128;
       const float sc = P.scale[c], mean = P.mean[c];
       S.cst[c] = sc;
       S.cst[32 + c] = fmaf(-mean, sc, P.beta[c]);
@@ -383,15 +409,18 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         S.cst[128 + c] = (float)k2;
       }
     }
+    for (int i = tid; i < 2 * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(S.a1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 4 * 130; i += kFtWorkers) S.dlsm[i] = 0.0f;
+    if (tid < 72) S.red[tid] = 0.0f;
     fence_proxy_async_smem();
   }
-  if (warp == 4 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
+  if (warp == 8 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *S.tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== producer ==============================
     if (lane == 0) {
       uint32_t n = 0;
@@ -405,7 +434,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================= MMA issuer =============================
     const uint32_t idesc1 = make_idesc_bf16(128, 32, 0, 0);   // da: K-major operands
     const uint32_t idesc2 = make_idesc_bf16(128, 32, 1, 1);   // weight gradient: MN-major operands
@@ -449,91 +478,104 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     }
   } else {
     // =============================== workers ==============================
-    const int p = threadIdx.x;
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
     const float slope = P.slope;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float acc1[32], acc2[32];   // pass 1: sum du, sum du*y ; pass 2: sum dy (acc1 only)
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 16);
+    const uint32_t ring_a = smem_u32(S.ring), a1_a = smem_u32(S.a1), dl_a = smem_u32(S.dlsm), cst_a = smem_u32(S.cst);
+    const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
+    const uint32_t a1off0 = swz64(p, 0), a1off1 = swz64(p, 1);
+    float acc[32];   // pass 1: [0,16) sum du, [16,32) sum du*y for this thread's 16 channels
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc1[c] = acc2[c] = 0.0f;
+    for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
     float sdl = 0.0f;
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
       const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      auto load_dl = [&](int h, int slot) {   // half 0 only
+        float v = 0.0f;
+        if (h >= 0 && h < H) v = __bfloat162float(P.dl[((long long)b * H + h) * 128 + p]);
+        sts_f(dl_a + (uint32_t)((slot * 130 + p + 1) * 4), v);
+      };
       // dl rows j = 0 .. RB+1  <->  image rows h0-1 .. h0+RB ; slot j & 3
-      load_dl_row(P.dl, S.dlsm, b, h0 - 1, H, p, 0);
-      load_dl_row(P.dl, S.dlsm, b, h0, H, p, 1);
-      load_dl_row(P.dl, S.dlsm, b, h0 + 1, H, p, 2);
-      named_bar_sync(1, 128);
-      auto stage_a1 = [&](int i, uint32_t nn) {   // builds the A1 tile of band row i (sequence number nn)
-        const uint32_t buf = nn & 1u, bph = (nn >> 1) & 1u;
+      if (half == 0) {
+        load_dl(h0 - 1, 0);
+        load_dl(h0, 1);
+        load_dl(h0 + 1, 2);
+      }
+      named_bar_sync(1, kFtWorkers);
+      auto stage_a1 = [&](int i, uint32_t nn) {   // half 0: builds the A1 tile of band row i (sequence number nn)
+        const uint32_t buf = nn & 1u;
         // A1[buf] was last read by the MMAs of row nn-2: da (observed through d1full two rows ago) and,
         // in pass 1, the weight-gradient MMAs, observed through the release of that row's ring slot
         if (PASS == 1 && nn >= 2) {
           const uint32_t m = nn - 2;
           mbar_wait(&S.empty_bar[m % kFtSlots], (m / kFtSlots) & 1u);
         }
-        (void)bph;
-        const float centre = build_a1_row(S.dlsm, S.a1 + buf * kRowBytes, i, p);
-        if (PASS == 1) sdl += centre;
+        float w[16];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) w[a * 3 + bb] = lds_f(dl_a + (uint32_t)((((i + a) & 3) * 130 + p + bb) * 4));
+#pragma unroll
+        for (int k = 9; k < 16; ++k) w[k] = 0.0f;
+        const uint32_t base = a1_a + buf * kRowBytes;
+        sts128(base + a1off0, pack8(w));
+        sts128(base + a1off1, pack8(w + 8));
+        if (PASS == 1) sdl += w[4];
         fence_proxy_async_smem();
         mbar_arrive(&S.a1ready_bar[buf]);
       };
-      stage_a1(0, n);
+      if (half == 0) stage_a1(0, n);
       for (int i = 0; i < RB; ++i, ++n) {
         // prefetch the next dl row and stage the next A1 tile so its MMA overlaps this row's math
         if (i + 1 < RB) {
-          load_dl_row(P.dl, S.dlsm, b, h0 + i + 2, H, p, (i + 3) & 3);
-          named_bar_sync(1, 128);
-          stage_a1(i + 1, n + 1);
+          if (half == 0) load_dl(h0 + i + 2, (i + 3) & 3);
+          named_bar_sync(1, kFtWorkers);
+          if (half == 0) stage_a1(i + 1, n + 1);
         }
         const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, buf = n & 1u, bph = (n >> 1) & 1u;
         mbar_wait(&S.full_bar[slot], ph);
         mbar_wait(&S.d1full_bar[buf], bph);
         tc_fence_after();
-        float da[32];
-        tmem_ld_32x32(t_lane + buf * 32, da);
+        float da[16];
+        tmem_ld_32x16(t_lane + buf * 32, da);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&S.d1empty_bar[buf]);
-        uint8_t* row = S.ring + slot * kRowBytes;
-        const long long opix = (((long long)b * H + h0 + i) * 128 + p) * 32;
+        const uint32_t row = ring_a + slot * kRowBytes;
+        const long long opix = (((long long)b * H + h0 + i) * 128 + p) * 32 + half * 16;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint4* ptr = reinterpret_cast<uint4*>(row + swz64(p, c4));
-          float y[8], o[8];
-          unpack8(*ptr, y);
-          const float4 s0 = *reinterpret_cast<const float4*>(S.cst + c4 * 8), s1 = *reinterpret_cast<const float4*>(S.cst + c4 * 8 + 4);
-          const float4 h0v = *reinterpret_cast<const float4*>(S.cst + 32 + c4 * 8), h1v = *reinterpret_cast<const float4*>(S.cst + 36 + c4 * 8);
-          const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float shv[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t a = row + (j == 0 ? off0 : off1);
+          const uint32_t cb = cst_a + (uint32_t)((2 * half + j) * 32);
+          float y[8], o[8], scv[8], shv[8];
+          unpack8(lds128(a), y);
+          load8f(cb, scv);
+          load8f(cb + 128, shv);
           if (PASS == 1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const int c = c4 * 8 + k;
+              const int c = j * 8 + k;
               const float u = fmaf(y[k], scv[k], shv[k]);
               const float du = u > 0.0f ? da[c] : da[c] * slope;
-              acc1[c] += du;
-              acc2[c] = fmaf(du, y[k], acc2[c]);
+              acc[c] += du;
+              acc[16 + c] = fmaf(du, y[k], acc[16 + c]);
               o[k] = fmaxf(u, u * slope);
             }
-            *ptr = pack8(o);   // act, in place: MN-major A operand of the weight-gradient MMA
+            sts128(a, pack8(o));   // act, in place: MN-major A operand of the weight-gradient MMA
           } else {
-            const float4 g0 = *reinterpret_cast<const float4*>(S.cst + 64 + c4 * 8), g1 = *reinterpret_cast<const float4*>(S.cst + 68 + c4 * 8);
-            const float4 a0 = *reinterpret_cast<const float4*>(S.cst + 96 + c4 * 8), a1v = *reinterpret_cast<const float4*>(S.cst + 100 + c4 * 8);
-            const float4 b0 = *reinterpret_cast<const float4*>(S.cst + 128 + c4 * 8), b1v = *reinterpret_cast<const float4*>(S.cst + 132 + c4 * 8);
-            const float gav[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float k1v[8] = {a0.x, a0.y, a0.z, a0.w, a1v.x, a1v.y, a1v.z, a1v.w};
-            const float k2v[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+            float gav[8], k1v[8], k2v[8];
+            load8f(cb + 256, gav);
+            load8f(cb + 384, k1v);
+            load8f(cb + 512, k2v);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const int c = c4 * 8 + k;
+              const int c = j * 8 + k;
               const float u = fmaf(y[k], scv[k], shv[k]);
               const float du = u > 0.0f ? da[c] : da[c] * slope;
-              const float r = fmaf(gav[k], du, -fmaf(k2v[k], y[k], k1v[k]));   // ga*(du - c1 - xhat*c2)
-              acc1[c] += r;
-              o[k] = r;
+              o[k] = fmaf(gav[k], du, -fmaf(k2v[k], y[k], k1v[k]));   // ga*(du - c1 - xhat*c2)
             }
-            *reinterpret_cast<uint4*>(P.dy + opix + c4 * 8) = pack8(o);
+            *reinterpret_cast<uint4*>(P.dy + opix + j * 8) = pack8(o);
           }
         }
         if (PASS == 1) {
@@ -543,27 +585,17 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
           mbar_arrive(&S.empty_bar[slot]);
         }
       }
-      named_bar_sync(1, 128);  // the next band restarts the dl ring
+      named_bar_sync(1, kFtWorkers);  // the next band restarts the dl ring
     }
-    // ------------------------------ reductions ------------------------------
-    warp_transpose_reduce32(acc1, lane);   // lane c now holds this warp's sum of channel c
-    if (PASS == 1) warp_transpose_reduce32(acc2, lane);
-    if (warp == 0) {
-      S.red[lane] = 0.0f;
-      S.red[32 + lane] = 0.0f;
-      if (lane < 8) S.red[64 + lane] = 0.0f;
-    }
-    named_bar_sync(1, 128);
-    atomicAdd(&S.red[lane], acc1[0]);
+    // ------------------------------ reductions (pass 1) ------------------------------
     if (PASS == 1) {
-      atomicAdd(&S.red[32 + lane], acc2[0]);
+      warp_transpose_reduce32(acc, lane);   // lane l: l < 16 -> sum du of channel 16*half + l ; else sum du*y of channel 16*half + l - 16
+      atomicAdd(&S.red[(lane >> 4) * 32 + half * 16 + (lane & 15)], acc[0]);
       const float d = warp_sum(sdl);
-      if (lane == 0) S.red[64 + warp] = d;
-    }
-    named_bar_sync(1, 128);
-    if (warp == 0) {
-      const int c = lane;
-      if (PASS == 1) {
+      if (lane == 0 && half == 0) S.red[64 + warp] = d;
+      named_bar_sync(1, kFtWorkers);
+      if (warp == 0) {
+        const int c = lane;
         const double s1 = (double)S.red[c], s2y = (double)S.red[32 + c];
         atomicAdd(&P.dstats[c], s1);
         atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2y - (double)P.mean[c] * s1));   // sum du * xhat
@@ -571,19 +603,17 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         // weight gradient of the final conv: D2 lane c, column widx -> dw[c][8 - widx]
         mbar_wait(S.done_bar, 0);
         tc_fence_after();
-        float v[32];
-        tmem_ld_32x32(tmem_base + 64, v);
+        float v[16];
+        tmem_ld_32x16(tmem_base + 64, v);
         tmem_ld_wait();
 #pragma unroll
         for (int widx = 0; widx < 9; ++widx) atomicAdd(&P.dw_last[c * 9 + (8 - widx)], v[widx]);
-      } else {
-        atomicAdd(&P.dbias[c], S.red[c]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
   }
@@ -642,13 +672,13 @@ extern "C" int vae_final_conv_fwd_tc(const void* y, const float* mean, const flo
   if (rc != VAE_OK) return rc;
   P.mean = mean; P.scale = scale; P.beta = beta; P.w_last = w_last; P.b_last = b_last;
   P.logits = (bf16*)logits; P.probs = probs; P.slope = slope;
-  const size_t smem = 1024 + kFtSlots * kRowBytes + 2048 + 4 * 9 * 130 * 4 + 8 * (3 * kFtSlots + 4) + 16;
+  const size_t smem = kFwdSmemBytes;
   static bool attr = false;
   if (!attr) {
     VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = 2 * sm_count();
+  int grid = 3 * sm_count();
   if (grid > P.total_bands) grid = P.total_bands;
   final_fwd_tc_kernel<<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
   return check_launch("final_fwd_tc");
@@ -698,12 +728,16 @@ extern "C" int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const 
                                       vae_stream_t stream);
 
 namespace vae {
-__global__ void final_small_grads_kernel(const double* __restrict__ dstats, float* dgamma, float* dbeta, float* db_last,
-                                         int C) {
+// dbias = sum over pixels of dy: identically zero through a train-mode BatchNorm (dy has its batch mean
+// removed; the reference's value is pure rounding noise), gamma*rstd*sum(du) in eval mode.
+__global__ void final_small_grads_kernel(const double* __restrict__ dstats, const float* __restrict__ gamma,
+                                         const float* __restrict__ rstd, float* dgamma, float* dbeta, float* dbias,
+                                         float* db_last, int C, int training) {
   const int c = threadIdx.x;
   if (c < C) {
     dbeta[c] = (float)dstats[c];
     dgamma[c] = (float)dstats[C + c];
+    dbias[c] = training ? 0.0f : (float)((double)gamma[c] * (double)rstd[c] * dstats[c]);
   }
   if (c == 0) db_last[0] = (float)dstats[2 * C];
 }
@@ -720,13 +754,12 @@ extern "C" int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const 
   VAE_REQUIRE(final_tc_ok(B, H, W, C, VAE_BF16), "final_bwd_apply_tc: shape not served");
   VAE_REQUIRE(slope > 0.0f && slope < 1.0f, "final_bwd_apply_tc: LeakyReLU slope must be in (0, 1)");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
-  final_small_grads_kernel<<<1, 64, 0, st>>>(dstats, dgamma, dbeta, db_last, C);
+  final_small_grads_kernel<<<1, 64, 0, st>>>(dstats, gamma, rstd, dgamma, dbeta, dbias, db_last, C, training);
   FinalTcParams P{};
   int rc = final_tc_setup(P, y, B, H, W);
   if (rc != VAE_OK) return rc;
   P.mean = mean; P.scale = scale; P.beta = beta; P.rstd = rstd; P.gamma = gamma; P.w_last = w_last;
-  P.dl = (const bf16*)dlogits; P.dstats = const_cast<double*>(dstats); P.dy = (bf16*)dy; P.dbias = dbias;
+  P.dl = (const bf16*)dlogits; P.dstats = const_cast<double*>(dstats); P.dy = (bf16*)dy;
   P.slope = slope; P.training = training;
   return final_bwd_tc_launch(2, P, st);
 }
