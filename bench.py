@@ -137,6 +137,15 @@ def algorithmic_cost(name, tag):
         B, Hi, Wi, Ci, Co, s = t[:6]
         Ho, Wo = Hi // s, Wi // s
         return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co) + 4 * 9 * Ci * Co, 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name == "vae_final_conv_fwd_tc":
+        B, H, W, C = t[:4]
+        return (B * H * W * (C * 2 + 2 + 4), 2 * B * H * W * 9 * C)
+    if name == "vae_final_bwd_reduce_tc":
+        B, H, W, C = t[:4]
+        return (B * H * W * (C + 1) * 2, 4 * B * H * W * 9 * C)
+    if name == "vae_final_bwd_apply_tc":
+        B, H, W, C = t[:4]
+        return (B * H * W * (2 * C + 1) * 2, 2 * B * H * W * 9 * C)
     if name == "vae_final_conv_fwd":  # reads y, writes logits (+ fp32 probabilities)
         B, H, W, C, d = t[:5]
         return (B * H * W * (C * _sz(d) + _sz(d) + 4), 2 * B * H * W * 9 * C)
@@ -303,7 +312,7 @@ def b200_arm(a):
                                     "alg_bytes": algorithmic_cost(*k)[0], "alg_flops": algorithmic_cost(*k)[1]} for k, n, ms in rows]}, f, indent=1)
 
     # -- optional CUDA-graph capture of the whole step -------------------------
-    use_graph = not a.no_graph and world == 1
+    use_graph = not a.no_graph  # NCCL all-reduces on the side stream are captured with the step
     graph = None
     static_x = x_dev.clone()
     if use_graph:
@@ -419,8 +428,13 @@ def b200_arm(a):
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Captured graphs hold NCCL kernels; tearing the communicator down under them can block, so
+        # the ranks meet at a barrier, drain the device and leave without running destructors.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
