@@ -248,6 +248,24 @@ int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const float* mean
                            vae_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * Fused AdamW: one launch for all tensors of the reference's two
+ * parameter groups; state layout of torch.optim.AdamW(capturable=True).
+ * replaces: optimizer.step() at train.py:656 (torch.optim.AdamW built at :210-228)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  void* p;          /* parameter, fp32, n elements (device) */
+  const void* g;    /* gradient */
+  void* m;          /* exp_avg */
+  void* v;          /* exp_avg_sq */
+  float* step;      /* device scalar, float */
+  long long n;
+  float lr;
+  float wd;
+} vae_adamw_tensor;
+int vae_adamw_step(const vae_adamw_tensor* tensors /* host array */, int count, double beta1, double beta2,
+                   double eps, vae_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Skinny GEMMs of the latent heads for L <= 16 (models.py:55-59,137,141,162 and their
  * gradients inside train.py:650).  fp32 master weights are used in place:
  * W(n, k) = W[n*wsn + k*wsk] covers both [L,F] (fc_mu / fc_var) and [F,L]

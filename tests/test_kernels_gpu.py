@@ -397,3 +397,32 @@ def test_skinny_head_gemms(tv, shape, dtype):
     assert rel_err(out.float(), d0.double() @ w_fl.double().t() + b_f.double()) <= tol
     out = ops.skinny_expand(dev(d0), dev(w_lf), dev(d1), dev(w_lf * 0.5), None, Fd, 1, Fd, dtype)
     assert rel_err(out.float(), (d0.double() + 0.5 * d1.double()) @ w_lf.double()) <= tol
+
+
+def test_fused_adamw_matches_torch(tv):
+    """FusedAdamW == torch.optim.AdamW (same groups, lrs, weight decay) over several steps,
+    and its state_dict loads into the stock optimizer."""
+    torch.manual_seed(3)
+    shapes = [(32, 1, 3, 3), (32,), (64, 32, 3, 3), (64,), (7, 5)]
+    ref_p = [torch.randn(s, device="cuda") for s in shapes]
+    got_p = [p.clone() for p in ref_p]
+    def groups(ps):
+        return [{"params": ps[:2], "lr": 3e-3}, {"params": ps[2:], "lr": 1e-3, "weight_decay": 0.05}]
+    ref_p = [p.requires_grad_(True) for p in ref_p]
+    got_p = [p.requires_grad_(True) for p in got_p]
+    ref = torch.optim.AdamW(groups(ref_p), lr=1e-3, weight_decay=0.01)
+    got = tv.FusedAdamW(groups(got_p), lr=1e-3, weight_decay=0.01)
+    for it in range(5):
+        for a, b in zip(ref_p, got_p):
+            g = torch.randn_like(a) * (0.1 + it)
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        got.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ref_p, got_p):
+        assert rel_err(b, a) <= 2e-6
+    for a, b in zip(ref_p, got_p):
+        assert rel_err(got.state[b]["exp_avg_sq"], ref.state[a]["exp_avg_sq"]) <= 2e-6
+        assert float(got.state[b]["step"]) == 5.0
+    ref2 = torch.optim.AdamW(groups(got_p), lr=1e-3, weight_decay=0.01)
+    ref2.load_state_dict(got.state_dict())  # checkpoint compatibility (train.py:445-460)

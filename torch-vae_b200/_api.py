@@ -1,12 +1,15 @@
 """Public surface of the B200-native VanillaVAE training path."""
 
-from . import config, data_transformations, engine, ops, parallel  # noqa: F401
+from . import config, data_transformations, engine, ops, optim, parallel  # noqa: F401
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .models import VanillaVAE
+from .optim import FusedAdamW
 from .types_helpers import EncoderOutput, LossOutput, ModelOutput
 
 __all__ = [
     "VanillaVAE",
+    "FusedAdamW",
+    "optim",
     "EncoderOutput",
     "ModelOutput",
     "LossOutput",

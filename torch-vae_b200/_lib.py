@@ -60,6 +60,7 @@ PROTOTYPES = {
     "vae_final_bwd_reduce_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "vae_final_bwd_apply_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f,
                                _i, _vp],
+    "vae_adamw_step": [_vp, _i, C.c_double, C.c_double, C.c_double, _vp],
     "vae_heads_supported": [_i, _i],
     "vae_skinny_reduce": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_skinny_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
@@ -79,6 +80,13 @@ PROTOTYPES = {
 }
 _RESTYPES = {"vae_last_error": C.c_char_p, "vae_umma_packed_elems": C.c_longlong, "vae_umma_tma_packed_elems": C.c_longlong,
              "vae_umma_rw_packed_elems": C.c_longlong}
+
+
+
+class AdamWTensor(C.Structure):
+    """include/vae_b200.h: vae_adamw_tensor"""
+    _fields_ = [("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("step", _vp), ("n", _ll), ("lr", _f), ("wd", _f)]
+
 
 _lib = None
 

@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        --expt-relaxed-constexpr -Xptxas -v)
 mkdir -p "${HERE}/obj"
 pids=()
-for f in runtime elementwise elbo conv_simt conv_edge final_block final_block_tc heads gemm_simt conv_umma conv_umma_tma conv_umma_rw conv_umma_wgrad conv_wgrad_tma; do
+for f in runtime adamw elementwise elbo conv_simt conv_edge final_block final_block_tc heads gemm_simt conv_umma conv_umma_tma conv_umma_rw conv_umma_wgrad conv_wgrad_tma; do
   "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/obj/${f}.o" > "${HERE}/obj/${f}.log" 2>&1 &
   pids+=($!)
 done

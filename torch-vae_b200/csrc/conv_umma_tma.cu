@@ -111,6 +111,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][256]
   float* s_bias = s_stats + 512;                            // [256]
+  uint32_t* s_taps = reinterpret_cast<uint32_t*>(s_bias + 256);  // [4 phases][dw pack, dh pack, sub-tiles, -]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
@@ -136,6 +137,18 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   }
   if (warp == 0 && lane == 0)
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap) : "memory");
+  if (threadIdx.x < 4) {  // tap offsets of a phase, 2 bits each (value + 1)
+    const TapTable& tt = P.g.phase[threadIdx.x];
+    uint32_t dwp = 0, dhp = 0;
+    for (int t = 0; t < tt.ntaps; ++t) {
+      dwp |= (uint32_t)(tt.dw[t] + 1) << (2 * t);
+      dhp |= (uint32_t)(tt.dh[t] + 1) << (2 * t);
+    }
+    s_taps[threadIdx.x * 4] = dwp;
+    s_taps[threadIdx.x * 4 + 1] = dhp;
+    s_taps[threadIdx.x * 4 + 2] = (uint32_t)(tt.ntaps * P.cin_chunks);
+    s_taps[threadIdx.x * 4 + 3] = 0u;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -144,35 +157,44 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
 
   if (warp == 0) {
     // ============================== producer ==============================
+    // One thread issues every load; its instruction stream is latency-bound (one warp, dependent
+    // scalar code), so everything that can be hoisted is: parameters live in registers, the tap
+    // offsets of a phase are two packed words, (tap, channel chunk) advance incrementally.
     if (lane == 0) {
       int stage = 0, seq = 0;
       uint32_t ph = 0;
-      const uint32_t b_bytes = (uint32_t)P.b_stage_bytes;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int phase = tile / P.tiles_per_phase;
-        const int mt = tile - phase * P.tiles_per_phase;
-        const TapTable& tt = g.phase[phase];
+      const uint32_t b_bytes = (uint32_t)P.b_stage_bytes, sub_a = (uint32_t)P.sub_a_bytes;
+      const uint32_t a_stage = (uint32_t)P.a_stage_bytes, stage_b = (uint32_t)stage_bytes;
+      const int sps = P.sps, cin_chunks = P.cin_chunks, kc = P.kc, in_mul = g.in_mul;
+      const uint32_t Wj = (uint32_t)g.Wj, Hj = (uint32_t)g.Hj;
+      const int tpp = P.tiles_per_phase, total = P.total_tiles;
+      const uint32_t smem_a = smem_u32(smem);
+      (void)smem_a;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int phase = tile / tpp;
+        const int mt = tile - phase * tpp;
+        const uint32_t dwp = s_taps[phase * 4], dhp = s_taps[phase * 4 + 1];
+        int rem = (int)s_taps[phase * 4 + 2];  // sub-tiles of this tile: taps x channel chunks
         const uint32_t m0 = (uint32_t)mt * kTTileM;
-        const uint32_t jw0 = m0 % (uint32_t)g.Wj, t2 = m0 / (uint32_t)g.Wj;
-        const uint32_t jh0 = t2 % (uint32_t)g.Hj, b0 = t2 / (uint32_t)g.Hj;
-        const int nsub_total = tt.ntaps * P.cin_chunks;
-        const bf16* wsrc = P.wpk + P.b_off[phase];
-        const int nkb = P.nkb[phase];
-        for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t jw0 = m0 % Wj, t2 = m0 / Wj;
+        const int jh0 = (int)(t2 % Hj), b0 = (int)(t2 / Hj);
+        const int cw = (int)jw0 * in_mul, ch = jh0 * in_mul;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.wpk + P.b_off[phase]);
+        int tap_i = 0, cc = 0;
+        while (rem > 0) {
           VAE_TTRACE(0, seq);
           mbar_wait(&empty_bar[stage], ph ^ 1u);
-          uint8_t* a_st = smem + stage * stage_bytes;
-          const int q0 = kb * P.sps;
-          const int nsub = min(P.sps, nsub_total - q0);
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nsub * P.sub_a_bytes) + b_bytes);
+          uint8_t* a_st = smem + (uint32_t)stage * stage_b;
+          const int nsub = rem < sps ? rem : sps;
+          rem -= nsub;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)nsub * sub_a + b_bytes);
           for (int sub = 0; sub < nsub; ++sub) {
-            const int q = q0 + sub;
-            const int tap_i = q / P.cin_chunks;
-            const int cc = q - tap_i * P.cin_chunks;
-            tma_load_4d(a_st + sub * P.sub_a_bytes, &P.tmap, &full_bar[stage], cc * P.kc,
-                        (int)jw0 * g.in_mul + tt.dw[tap_i], (int)jh0 * g.in_mul + tt.dh[tap_i], (int)b0);
+            const int dw = (int)((dwp >> (2 * tap_i)) & 3u) - 1, dh = (int)((dhp >> (2 * tap_i)) & 3u) - 1;
+            tma_load_4d(a_st + (uint32_t)sub * sub_a, &P.tmap, &full_bar[stage], cc * kc, cw + dw, ch + dh, b0);
+            if (++cc == cin_chunks) { cc = 0; ++tap_i; }
           }
-          bulk_g2s(a_st + P.a_stage_bytes, wsrc + (long long)kb * P.sps * P.sub_b_elems, b_bytes, &full_bar[stage]);
+          bulk_g2s(a_st + a_stage, wsrc, b_bytes, &full_bar[stage]);
+          wsrc += b_bytes;
           VAE_TTRACE(1, seq);
           ++seq;
           if (++stage == kStages) { stage = 0; ph ^= 1u; }
@@ -184,36 +206,47 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const uint32_t idesc = make_idesc_bf16(kTTileM, (uint32_t)N, 0, 0);
     const uint32_t layout = P.kc == 32 ? 4u : 2u;        // SWIZZLE_64B : SWIZZLE_128B
     const uint32_t sbo = P.kc == 32 ? 512u : 1024u;      // 8 rows of 64 / 128 bytes
-    const int ksteps = P.kc / 16;
+    // descriptor = {hi: SBO | version | swizzle, lo: address >> 4 | LBO(=1) << 16}; addresses < 256 KB, so
+    // a descriptor is advanced with one 32-bit add on its low word
+    const uint32_t hi = ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+    const int ksteps = P.kc / 16, sps = P.sps;
+    const uint32_t sub_a16 = (uint32_t)P.sub_a_bytes >> 4, sub_b16 = (uint32_t)(P.sub_b_elems * 2) >> 4;
+    const uint32_t a_stage = (uint32_t)P.a_stage_bytes, stage_b = (uint32_t)stage_bytes;
+    const uint32_t smem_a = smem_u32(smem);
+    const int tpp = P.tiles_per_phase, total = P.total_tiles;
     int stage = 0, seq = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const int phase = tile / P.tiles_per_phase;
-      const int nkb = P.nkb[phase];
-      const int nsub_total = g.phase[phase].ntaps * P.cin_chunks;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int phase = tile / tpp;
+      int rem = (int)s_taps[phase * 4 + 2];
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
-      for (int kb = 0; kb < nkb; ++kb) {
+      uint32_t accum = 0u;
+      while (rem > 0) {
         mbar_wait(&full_bar[stage], ph);
         VAE_TTRACE(2, seq);
         tc_fence_after();
+        const int nsub = rem < sps ? rem : sps;
+        rem -= nsub;
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + (uint32_t)P.a_stage_bytes;
-          const int nsub = min(P.sps, nsub_total - kb * P.sps);
+          const uint32_t a_addr = smem_a + (uint32_t)stage * stage_b;
+          uint32_t lo_a = (a_addr >> 4) | (1u << 16);
+          uint32_t lo_b = ((a_addr + a_stage) >> 4) | (1u << 16);
           for (int sub = 0; sub < nsub; ++sub) {
             for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_desc_sw(a_addr + sub * P.sub_a_bytes + k * 32, sbo, layout);
-              const uint64_t bd = make_desc_sw(b_addr + sub * P.sub_b_elems * 2 + k * 32, sbo, layout);
-              mma_bf16_ss(d_tmem, ad, bd, idesc, (kb > 0 || sub > 0 || k > 0) ? 1u : 0u);
+              mma_bf16_ss(d_tmem, ((uint64_t)hi << 32) | (lo_a + 2u * k), ((uint64_t)hi << 32) | (lo_b + 2u * k), idesc,
+                          accum);
+              accum = 1u;
             }
+            lo_a += sub_a16;
+            lo_b += sub_b16;
           }
           mma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) mma_commit(&tfull_bar[acc]);
+          if (rem == 0) mma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         VAE_TTRACE(3, seq);
@@ -442,7 +475,7 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
   P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
   P.trace = umma_trace_ptr();
-  size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4;
+  size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     VAE_CUDA(cudaFuncSetAttribute(umma_tma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
