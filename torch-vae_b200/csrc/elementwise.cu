@@ -54,26 +54,88 @@ __device__ __forceinline__ float bn_affine(float y, float mean, float scale, flo
 }
 
 // ------------------------------------------------------------ BN apply + lrelu
-template <typename T>
-__global__ void bn_apply_lrelu_vec8(const T* __restrict__ y, const float* __restrict__ scale,
-                                    const float* __restrict__ mean, const float* __restrict__ beta,
-                                    T* __restrict__ act, long long n_vec, int C, float slope) {
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    long long e = i * 8;
-    int c = (int)(e % C);
-    Vec8<T> v;
-    v.load(y + e);
-    Vec8<float> s, m, b;
-    s.load(scale + c);
-    m.load(mean + c);
-    b.load(beta + c);
+// Raw (unconverted) channel vector: loads stay 4 / 8 registers wide until they are consumed, so
+// several of them can be in flight per thread without the fp32 copies occupying registers.
+template <typename T, int V>
+struct RawVec;
+template <>
+struct RawVec<bf16, 8> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float* v) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float u = bn_affine(v.v[k], m.v[k], s.v[k], b.v[k]);
-      v.v[k] = u > 0.0f ? u : u * slope;
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
     }
-    v.store(act + e);
+  }
+};
+template <>
+struct RawVec<float, 8> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <typename T>
+struct RawVec<T, 1> {
+  T r;
+  __device__ __forceinline__ void load(const T* p) { r = p[0]; }
+  __device__ __forceinline__ void get(float* v) const { v[0] = to_f(r); }
+};
+template <typename T>
+struct BnUnroll {
+  static constexpr int U = sizeof(T) == 2 ? 4 : 2;
+};
+
+// Thread layout of the vectorised BatchNorm passes: a block owns `lanes` pixel lanes times G = C/8
+// channel groups; a thread keeps its 8 channels for the whole kernel (per-channel constants in
+// registers) and has kBnUnroll independent 16-byte loads per tensor in flight per iteration.
+constexpr int kBnUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_lrelu_vec8(const T* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ mean, const float* __restrict__ beta,
+                    T* __restrict__ act, long long n_pix, int C, float slope) {
+  const int G = C / 8;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  if (lane >= lanes) return;
+  float sc[8], mu[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale[g * 8 + k];
+    mu[k] = mean[g * 8 + k];
+    be[k] = beta[g * 8 + k];
+  }
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * kBnUnroll) {
+    RawVec<T, 8> v[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long p = p0 + u * step;
+      if (p < n_pix) v[u].load(y + p * C + g * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long p = p0 + u * step;
+      if (p < n_pix) {
+        Vec8<T> o;
+        v[u].get(o.v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float uu = bn_affine(o.v[k], mu[k], sc[k], be[k]);
+          o.v[k] = uu > 0.0f ? uu : uu * slope;
+        }
+        o.store(act + p * C + g * 8);
+      }
+    }
   }
 }
 
@@ -119,7 +181,7 @@ struct ChanVec {
 };
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
                      const float* __restrict__ scale, const float* __restrict__ beta,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -140,18 +202,33 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
       mu[k] = mean[g * V + k];
       rs[k] = rstd[g * V + k];
     }
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < n_pix;
-         p += (long long)gridDim.x * lanes) {
-      ChanVec<T, V> d, yy;
-      d.load(dact + p * C + g * V);
-      yy.load(y + p * C + g * V);
+    const long long step = (long long)gridDim.x * lanes;
+    constexpr int U = BnUnroll<T>::U;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * U) {
+      RawVec<T, V> d[U], yy[U];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float u = bn_affine(yy.v[k], mu[k], sc[k], sh[k]);
-        float du = u > 0.0f ? d.v[k] : d.v[k] * slope;
-        float xh = (yy.v[k] - mu[k]) * rs[k];
-        s1[k] += du;
-        s2[k] = fmaf(du, xh, s2[k]);
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < n_pix) {
+          d[u].load(dact + p * C + g * V);
+          yy[u].load(y + p * C + g * V);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p0 + u * step < n_pix) {
+          float dv[V], yv[V];
+          d[u].get(dv);
+          yy[u].get(yv);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            float uu = bn_affine(yv[k], mu[k], sc[k], sh[k]);
+            float du = uu > 0.0f ? dv[k] : dv[k] * slope;
+            float xh = (yv[k] - mu[k]) * rs[k];
+            s1[k] += du;
+            s2[k] = fmaf(du, xh, s2[k]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -172,7 +249,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, const T* __restrict__ y,
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
                     const float* __restrict__ scale, const float* __restrict__ beta,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -206,21 +283,38 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
       c1[k] = training ? (float)(dstats[c] * inv_m) : 0.0f;
       c2[k] = training ? (float)(dstats[C + c] * inv_m) : 0.0f;
     }
-    for (long long p = (long long)blockIdx.x * lanes + lane; p < n_pix;
-         p += (long long)gridDim.x * lanes) {
-      ChanVec<T, V> d, yy, o;
-      d.load(dact + p * C + g * V);
-      yy.load(y + p * C + g * V);
+    const long long step = (long long)gridDim.x * lanes;
+    constexpr int U = BnUnroll<T>::U;
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * U) {
+      RawVec<T, V> d[U], yy[U];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        float u = bn_affine(yy.v[k], mu[k], sc[k], sh[k]);
-        float du = u > 0.0f ? d.v[k] : d.v[k] * slope;
-        float xh = (yy.v[k] - mu[k]) * rs[k];
-        float r = a[k] * (du - c1[k] - xh * c2[k]);
-        o.v[k] = r;
-        sdy[k] += r;
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < n_pix) {
+          d[u].load(dact + p * C + g * V);
+          yy[u].load(y + p * C + g * V);
+        }
       }
-      o.store(dy + p * C + g * V);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < n_pix) {
+          float dv[V], yv[V];
+          d[u].get(dv);
+          yy[u].get(yv);
+          ChanVec<T, V> o;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            float uu = bn_affine(yv[k], mu[k], sc[k], sh[k]);
+            float du = uu > 0.0f ? dv[k] : dv[k] * slope;
+            float xh = (yv[k] - mu[k]) * rs[k];
+            float r = a[k] * (du - c1[k] - xh * c2[k]);
+            o.v[k] = r;
+            sdy[k] += r;
+          }
+          o.store(dy + p * C + g * V);
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) red[(lane * G + g) * V + k] = sdy[k];
@@ -429,13 +523,20 @@ extern "C" int vae_bn_apply_lrelu(const void* y, const float* scale, const float
   long long n = n_pix * C;
   cudaStream_t st = as_stream(stream);
   if (C % 8 == 0) {
-    long long nv = n / 8;
-    int grid = grid_for(nv, 256);
-    if (dtype == VAE_BF16)
-      bn_apply_lrelu_vec8<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, mean, beta, (bf16*)act, nv, C, slope);
-    else
-      bn_apply_lrelu_vec8<float><<<grid, 256, 0, st>>>((const float*)y, scale, mean, beta, (float*)act, nv, C, slope);
-  } else {
+    const int G = C / 8;
+    if (G <= 256) {
+      const int lanes = 256 / G;
+      long long blocks = (n_pix + (long long)lanes * kBnUnroll - 1) / ((long long)lanes * kBnUnroll);
+      const long long cap = (long long)sm_count() * 8;
+      const int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+      if (dtype == VAE_BF16)
+        bn_apply_lrelu_vec8<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, mean, beta, (bf16*)act, n_pix, C, slope);
+      else
+        bn_apply_lrelu_vec8<float><<<grid, 256, 0, st>>>((const float*)y, scale, mean, beta, (float*)act, n_pix, C, slope);
+      return check_launch("bn_apply_lrelu");
+    }
+  }
+  {
     int grid = grid_for(n, 256);
     if (dtype == VAE_BF16)
       bn_apply_lrelu_scalar<bf16><<<grid, 256, 0, st>>>((const bf16*)y, scale, mean, beta, (bf16*)act, n, C, slope);
@@ -455,7 +556,7 @@ static bool bwd_cfg(long long n_pix, int C, BwdCfg* cfg) {
   if (cfg->G > 256) return false;
   cfg->lanes = 256 / cfg->G;
   long long blocks = (n_pix + cfg->lanes * 4 - 1) / (cfg->lanes * 4);
-  long long cap = (long long)sm_count() * 4;
+  long long cap = (long long)sm_count() * 2;
   cfg->grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
   return true;
 }
