@@ -51,7 +51,12 @@ struct RwCfg {
   static constexpr uint32_t LAYOUT = KC == 32 ? 4u : 2u;          // SWIZZLE_64B : SWIZZLE_128B
   static constexpr uint32_t SBO = KC == 32 ? 512u : 1024u;
   static constexpr int KS = KC / 16;
-  static constexpr int TAIL = 8 * 24 + 16 + 4 * (2 * 64 + 64);
+  // MODE 1: per epilogue warp a [32 pixels][128 B + 16 B pad] staging tile that turns the per-thread
+  // 128-byte rows of the accumulator into fully coalesced 512-byte global stores
+  static constexpr int ROWB = MODE == 1 ? 128 : N * 2;   // contiguous global bytes a thread produces per output row
+  static constexpr int EPI_PITCH = ROWB + 16;
+  static constexpr int EPI = 8 * 32 * EPI_PITCH;
+  static constexpr int TAIL = 8 * 24 + 16 + 4 * (2 * 64 + 64) + EPI;
   static size_t smem_bytes(int stages) { return 1024 + (size_t)stages * STAGE + WBYTES + TAIL; }
 };
 
@@ -88,6 +93,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 24);  // barrier block padded to 192 B
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][64]
   float* s_bias = s_stats + 128;                            // [64]
+  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_bias + 64);  // [8 epilogue warps][32 rows][EPI_PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 128; i += kRwThreads) s_stats[i] = 0.0f;
@@ -236,9 +242,8 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
         }
-        // channel base of this chunk / destination offset in elements
+        // channel base of this chunk
         const int cbase = MODE == 0 ? ci * 32 : 0;
-        const long long doff = MODE == 0 ? ci * 32 : ((long long)(ci >> 1) * P.Wout * N + (ci & 1) * N);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
@@ -247,14 +252,35 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           v[i + 2] = valid ? v[i + 2] + b4.z : 0.0f;
           v[i + 3] = valid ? v[i + 3] + b4.w : 0.0f;
         }
-        if (valid) {
+        {
+          // A thread's accumulator row is ROWB contiguous bytes of the output (MODE 0: its pixel's N channels;
+          // MODE 1: the two column-parity pixels of one output row) and the 32 threads of a warp own 32 such
+          // rows back to back.  Stage them, then let consecutive lanes store consecutive 16-byte pieces.
+          uint8_t* st = s_epi + (warp - 2) * (32 * Cfg::EPI_PITCH);
+          const int cpos = MODE == 1 ? (ci & 1) * 64 : ci * 64;   // byte position of this chunk in the row
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 pk;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
             for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
-            *reinterpret_cast<uint4*>(dst + doff + i) = pk;
+            *reinterpret_cast<uint4*>(st + lane * Cfg::EPI_PITCH + cpos + i * 2) = pk;
+          }
+          const bool row_done = MODE == 1 ? (ci & 1) != 0 : ci == NCHUNK - 1;
+          if (row_done) {
+            __syncwarp();
+            const unsigned long long my = reinterpret_cast<unsigned long long>(dst);  // 0 when the row is out of range
+            const long long roff = MODE == 1 ? (long long)(ci >> 1) * P.Wout * N : 0;
+            constexpr int PPR = Cfg::ROWB / 16;   // 16-byte pieces per row
+#pragma unroll
+            for (int j = 0; j < PPR; ++j) {
+              const int c = lane + 32 * j;
+              const int src = c / PPR, sub = c % PPR;
+              const unsigned long long d = __shfl_sync(0xffffffffu, my, src);
+              const uint4 pk = *reinterpret_cast<const uint4*>(st + src * Cfg::EPI_PITCH + sub * 16);
+              if (d != 0ull) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d) + roff + sub * 8) = pk;
+            }
+            __syncwarp();
           }
         }
         if (P.stats != nullptr) {
@@ -352,7 +378,7 @@ static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const fl
   P.B = B; P.Hj = pl.Hj; P.Wj = pl.Wj; P.in_mul = pl.in_mul; P.Hout = pl.Hout; P.Wout = pl.Wout;
   const long long M = (long long)B * pl.Hj * pl.Wj;
   P.total_tiles = (int)((M + 127) / 128);
-  int stages = (int)((220 * 1024 - 1024 - Cfg::WBYTES - Cfg::TAIL) / Cfg::STAGE);
+  int stages = (int)((226 * 1024 - 1024 - Cfg::WBYTES - Cfg::TAIL) / Cfg::STAGE);
   if (stages > kRwMaxStages) stages = kRwMaxStages;
   VAE_REQUIRE(stages >= 2, "conv_umma_rw: shared memory budget");
   P.stages = stages;

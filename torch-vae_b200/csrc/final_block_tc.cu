@@ -28,6 +28,7 @@ constexpr int kRowBytes = 8192;  // 128 pixels x 32 channels x bf16
 
 struct FinalTcParams {
   CUtensorMap tmap_y;
+  CUtensorMap tmap_dy;   // pass 2: same geometry as y, used for the TMA store of dy rows
   const float* mean;
   const float* scale;
   const float* beta;
@@ -106,6 +107,16 @@ __device__ __forceinline__ uint64_t make_desc_mn_tc(uint32_t smem_addr, uint32_t
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// shared -> global tensor store (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // 32 lanes x 16 columns of fp32
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
@@ -323,6 +334,7 @@ struct BwdSmem {
   float* dlsm;      // [4][130]
   float* cst;       // per-channel constants, [5][32]
   float* red;       // [2][32] block reduction scratch (+ 8 for the bias sum)
+  int* coord;       // [slots][2] (h, b) of the row held by a slot (pass 2 store)
   uint64_t* full_bar;     // TMA -> workers
   uint64_t* empty_bar;    // -> producer
   uint64_t* a1ready_bar;  // [2] workers -> MMA
@@ -334,7 +346,7 @@ struct BwdSmem {
 };
 
 constexpr size_t kBwdSmemBytes = 1024 + kFtSlots * kRowBytes + 2 * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
-                                 2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 8 * (3 * kFtSlots + 7) + 16;
+                                 2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 7) + 16;
 
 __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
   BwdSmem s;
@@ -344,7 +356,8 @@ __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
   s.dlsm = reinterpret_cast<float*>(s.b1 + 2048);
   s.cst = s.dlsm + 4 * 130;
   s.red = s.cst + 5 * 32;
-  s.full_bar = reinterpret_cast<uint64_t*>(s.red + 72);
+  s.coord = reinterpret_cast<int*>(s.red + 72);
+  s.full_bar = reinterpret_cast<uint64_t*>(s.coord + 2 * kFtSlots);
   s.empty_bar = s.full_bar + kFtSlots;
   s.a1ready_bar = s.empty_bar + kFtSlots;
   s.d1full_bar = s.a1ready_bar + 2;
@@ -424,14 +437,37 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     // ============================== producer ==============================
     if (lane == 0) {
       uint32_t n = 0;
+      if (PASS == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_dy) : "memory");
+      // pass 2: the workers overwrite a y row IN PLACE with dy; this thread then sends the row to
+      // global memory with one TMA tensor store (coalesced by the copy engine) and only afterwards
+      // recycles the slot for a new load
+      auto store_row = [&](uint32_t m) {
+        const uint32_t slot = m % kFtSlots;
+        mbar_wait(&S.a2ready_bar[slot], (m / kFtSlots) & 1u);
+        tma_store_4d(&P.tmap_dy, S.ring + slot * kRowBytes, 0, 0, S.coord[2 * slot], S.coord[2 * slot + 1]);
+        bulk_commit_group();
+      };
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
         const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
         for (int i = 0; i < RB; ++i, ++n) {
           const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u;
-          mbar_wait(&S.empty_bar[slot], ph ^ 1u);
+          if (PASS == 1) {
+            mbar_wait(&S.empty_bar[slot], ph ^ 1u);
+          } else if (n >= kFtSlots) {
+            store_row(n - kFtSlots);
+            bulk_wait_group_read0();  // the store has finished reading the slot
+          }
+          if (PASS == 2) {
+            S.coord[2 * slot] = h0 + i;
+            S.coord[2 * slot + 1] = b;
+          }
           mbar_arrive_expect_tx(&S.full_bar[slot], kRowBytes);
           tma_load_4d(S.ring + slot * kRowBytes, &P.tmap_y, &S.full_bar[slot], 0, 0, h0 + i, b);
         }
+      }
+      if (PASS == 2) {
+        for (uint32_t m = n > kFtSlots ? n - kFtSlots : 0; m < n; ++m) store_row(m);
+        bulk_wait_group0();
       }
     }
   } else if (warp == 9) {
@@ -491,19 +527,28 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
       const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
-      auto load_dl = [&](int h, int slot) {   // half 0 only
-        float v = 0.0f;
-        if (h >= 0 && h < H) v = __bfloat162float(P.dl[((long long)b * H + h) * 128 + p]);
-        sts_f(dl_a + (uint32_t)((slot * 130 + p + 1) * 4), v);
+      // dlogits window of a pixel: rows j = 0 .. RB+1 of the band <-> image rows h0-1 .. h0+RB, columns
+      // p-1, p, p+1.  Each half-0 thread keeps a sliding 3 x 3 window in registers and loads the three
+      // values of the next row one iteration ahead (L1-resident after the first touch), so there is no
+      // shared-memory exchange and no block barrier on the per-row path.
+      auto fetch3 = [&](int h, float* v) {
+        if (h >= 0 && h < H) {
+          const bf16* row = P.dl + ((long long)b * H + h) * 128;
+          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          v[1] = __bfloat162float(row[p]);
+          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+        } else {
+          v[0] = v[1] = v[2] = 0.0f;
+        }
       };
-      // dl rows j = 0 .. RB+1  <->  image rows h0-1 .. h0+RB ; slot j & 3
+      float r0[3], r1[3], r2[3], pf[3];
       if (half == 0) {
-        load_dl(h0 - 1, 0);
-        load_dl(h0, 1);
-        load_dl(h0 + 1, 2);
+        fetch3(h0 - 1, r0);
+        fetch3(h0, r1);
+        fetch3(h0 + 1, r2);
+        fetch3(h0 + 2, pf);
       }
-      named_bar_sync(1, kFtWorkers);
-      auto stage_a1 = [&](int i, uint32_t nn) {   // half 0: builds the A1 tile of band row i (sequence number nn)
+      auto stage_a1 = [&](uint32_t nn) {   // half 0: builds the A1 tile (sequence number nn) from the window r0..r2
         const uint32_t buf = nn & 1u;
         // A1[buf] was last read by the MMAs of row nn-2: da (observed through d1full two rows ago) and,
         // in pass 1, the weight-gradient MMAs, observed through the release of that row's ring slot
@@ -513,9 +558,11 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         }
         float w[16];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int bb = 0; bb < 3; ++bb) w[a * 3 + bb] = lds_f(dl_a + (uint32_t)((((i + a) & 3) * 130 + p + bb) * 4));
+        for (int k = 0; k < 3; ++k) {
+          w[k] = r0[k];
+          w[3 + k] = r1[k];
+          w[6 + k] = r2[k];
+        }
 #pragma unroll
         for (int k = 9; k < 16; ++k) w[k] = 0.0f;
         const uint32_t base = a1_a + buf * kRowBytes;
@@ -525,13 +572,18 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         fence_proxy_async_smem();
         mbar_arrive(&S.a1ready_bar[buf]);
       };
-      if (half == 0) stage_a1(0, n);
+      if (half == 0) stage_a1(n);
       for (int i = 0; i < RB; ++i, ++n) {
-        // prefetch the next dl row and stage the next A1 tile so its MMA overlaps this row's math
-        if (i + 1 < RB) {
-          if (half == 0) load_dl(h0 + i + 2, (i + 3) & 3);
-          named_bar_sync(1, kFtWorkers);
-          if (half == 0) stage_a1(i + 1, n + 1);
+        // stage the next row's A1 tile first so that its MMA overlaps this row's elementwise math
+        if (i + 1 < RB && half == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            r0[k] = r1[k];
+            r1[k] = r2[k];
+            r2[k] = pf[k];
+          }
+          fetch3(h0 + i + 3, pf);
+          stage_a1(n + 1);
         }
         const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, buf = n & 1u, bph = (n >> 1) & 1u;
         mbar_wait(&S.full_bar[slot], ph);
@@ -543,7 +595,6 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         tc_fence_before();
         mbar_arrive(&S.d1empty_bar[buf]);
         const uint32_t row = ring_a + slot * kRowBytes;
-        const long long opix = (((long long)b * H + h0 + i) * 128 + p) * 32 + half * 16;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint32_t a = row + (j == 0 ? off0 : off1);
@@ -575,17 +626,12 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
               const float du = u > 0.0f ? da[c] : da[c] * slope;
               o[k] = fmaf(gav[k], du, -fmaf(k2v[k], y[k], k1v[k]));   // ga*(du - c1 - xhat*c2)
             }
-            *reinterpret_cast<uint4*>(P.dy + opix + j * 8) = pack8(o);
+            sts128(a, pack8(o));   // dy, in place; the producer thread stores the row with TMA
           }
         }
-        if (PASS == 1) {
-          fence_proxy_async_smem();
-          mbar_arrive(&S.a2ready_bar[slot]);
-        } else {
-          mbar_arrive(&S.empty_bar[slot]);
-        }
+        fence_proxy_async_smem();
+        mbar_arrive(&S.a2ready_bar[slot]);   // pass 1: act operand ready; pass 2: dy row ready to store
       }
-      named_bar_sync(1, kFtWorkers);  // the next band restarts the dl ring
     }
     // ------------------------------ reductions (pass 1) ------------------------------
     if (PASS == 1) {
@@ -759,6 +805,12 @@ extern "C" int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const 
   int rc = final_tc_setup(P, y, B, H, W);
   if (rc != VAE_OK) return rc;
   P.mean = mean; P.scale = scale; P.beta = beta; P.rstd = rstd; P.gamma = gamma; P.w_last = w_last;
+  {
+    FinalTcParams Q{};
+    rc = final_tc_setup(Q, dy, B, H, W);
+    if (rc != VAE_OK) return rc;
+    P.tmap_dy = Q.tmap_y;
+  }
   P.dl = (const bf16*)dlogits; P.dstats = const_cast<double*>(dstats); P.dy = (bf16*)dy;
   P.slope = slope; P.training = training;
   return final_bwd_tc_launch(2, P, st);
