@@ -1,0 +1,13 @@
+import os, sys, math, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch_vae_b200 as tv
+ops = tv.ops
+B = int(os.environ.get("B", "256")); H = W = 128; C = 32
+y = torch.randn(B, H, W, C, device="cuda").bfloat16()
+gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+w_last = torch.randn(1, C, 3, 3, device="cuda") / math.sqrt(9 * C)
+dl = (torch.randn(B, 1, H, W, device="cuda") / (B * H * W)).bfloat16()
+vec = torch.stack([torch.ones(C), torch.zeros(C), torch.zeros(C), torch.ones(C)]).cuda()
+for _ in range(2):
+    ops.final_block_backward(dl, y, vec, gamma, beta, w_last, True)
+torch.cuda.synchronize(); print("ok")

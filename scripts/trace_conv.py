@@ -3,7 +3,8 @@ import os, sys, math, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch_vae_b200 as tv
 ops = tv.ops
-B, H, W, Ci, Co = 512, 128, 128, 32, 32
+import os
+B, H, W, Ci, Co = [int(v) for v in os.environ.get('SHAPE', '512,128,128,32,32').split(',')]
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 x = torch.randn(B, H, W, Ci, device="cuda").bfloat16()
 y = torch.randn(B, H // 2, W // 2, Co, device="cuda").bfloat16()

@@ -25,6 +25,7 @@ constexpr int kFtThreads = 320;
 constexpr int kFtWorkers = 256;
 constexpr int kFtSlots = 6;      // ring of raw y rows
 constexpr int kRowBytes = 8192;  // 128 pixels x 32 channels x bf16
+constexpr int kA1Bufs = 3;       // dlogits-window tiles in flight (backward)
 
 struct FinalTcParams {
   CUtensorMap tmap_y;
@@ -329,7 +330,7 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 // =============================================================================================
 struct BwdSmem {
   uint8_t* ring;    // [kFtSlots][8 KB] y rows (TMA), rewritten in place as act by pass 1
-  uint8_t* a1;      // [2][8 KB]
+  uint8_t* a1;      // [kA1Bufs][8 KB]
   uint8_t* b1;      // [32][64 B]
   float* dlsm;      // [4][130]
   float* cst;       // per-channel constants, [5][32]
@@ -345,14 +346,14 @@ struct BwdSmem {
   uint32_t* tmem_ptr;
 };
 
-constexpr size_t kBwdSmemBytes = 1024 + kFtSlots * kRowBytes + 2 * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
-                                 2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 7) + 16;
+constexpr size_t kBwdSmemBytes = 1024 + kFtSlots * kRowBytes + kA1Bufs * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
+                                 2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 8) + 16;
 
 __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
   BwdSmem s;
   s.ring = smem;
   s.a1 = s.ring + kFtSlots * kRowBytes;
-  s.b1 = s.a1 + 2 * kRowBytes + 8192;
+  s.b1 = s.a1 + kA1Bufs * kRowBytes + 8192;
   s.dlsm = reinterpret_cast<float*>(s.b1 + 2048);
   s.cst = s.dlsm + 4 * 130;
   s.red = s.cst + 5 * 32;
@@ -360,7 +361,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
   s.full_bar = reinterpret_cast<uint64_t*>(s.coord + 2 * kFtSlots);
   s.empty_bar = s.full_bar + kFtSlots;
   s.a1ready_bar = s.empty_bar + kFtSlots;
-  s.d1full_bar = s.a1ready_bar + 2;
+  s.d1full_bar = s.a1ready_bar + kA1Bufs;
   s.d1empty_bar = s.d1full_bar + 2;
   s.a2ready_bar = s.d1empty_bar + 2;
   s.done_bar = s.a2ready_bar + kFtSlots;
@@ -384,8 +385,8 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         mbar_init(&S.empty_bar[s], PASS == 1 ? 1 : kFtWorkers);  // pass 1: freed by the MMA commit; pass 2: by the workers
         mbar_init(&S.a2ready_bar[s], kFtWorkers);
       }
+      for (int a = 0; a < kA1Bufs; ++a) mbar_init(&S.a1ready_bar[a], 128);
       for (int a = 0; a < 2; ++a) {
-        mbar_init(&S.a1ready_bar[a], 128);
         mbar_init(&S.d1full_bar[a], 1);
         mbar_init(&S.d1empty_bar[a], kFtWorkers);
       }
@@ -422,7 +423,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         S.cst[128 + c] = (float)k2;
       }
     }
-    for (int i = tid; i < 2 * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(S.a1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kA1Bufs * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(S.a1)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 4 * 130; i += kFtWorkers) S.dlsm[i] = 0.0f;
     if (tid < 72) S.red[tid] = 0.0f;
     fence_proxy_async_smem();
@@ -478,12 +479,13 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     uint32_t total = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) total += (uint32_t)RB;
     auto issue_da = [&](uint32_t n) {
-      const uint32_t buf = n & 1u, bph = (n >> 1) & 1u;
-      mbar_wait(&S.a1ready_bar[buf], bph);
+      const uint32_t buf = n & 1u, bph = (n >> 1) & 1u;          // TMEM accumulator of da
+      const uint32_t ab = n % kA1Bufs, aph = (n / kA1Bufs) & 1u;  // A1 tile
+      mbar_wait(&S.a1ready_bar[ab], aph);
       mbar_wait(&S.d1empty_bar[buf], bph ^ 1u);
       tc_fence_after();
       if (elect_one()) {
-        mma_bf16_ss(tmem_base + buf * 32, make_desc_sw(a1_a + buf * kRowBytes, 512, 4), make_desc_sw(b1_a, 512, 4),
+        mma_bf16_ss(tmem_base + buf * 32, make_desc_sw(a1_a + ab * kRowBytes, 512, 4), make_desc_sw(b1_a, 512, 4),
                     idesc1, 0u);
         mma_commit(&S.d1full_bar[buf]);
       }
@@ -493,14 +495,14 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     for (uint32_t n = 0; n < total; ++n) {
       if (n + 1 < total) issue_da(n + 1);   // the next row's da runs under this row's elementwise math
       if (PASS == 1) {
-        const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, buf = n & 1u;
+        const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, ab = n % kA1Bufs;
         mbar_wait(&S.a2ready_bar[slot], ph);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
             const uint64_t ad = make_desc_mn_tc(ring_a + slot * kRowBytes + ks * 1024, kRowBytes, 512, 4);
-            const uint64_t bd = make_desc_mn_tc(a1_a + buf * kRowBytes + ks * 1024, kRowBytes, 512, 4);
+            const uint64_t bd = make_desc_mn_tc(a1_a + ab * kRowBytes + ks * 1024, kRowBytes, 512, 4);
             mma_bf16_ss(tmem_base + 64, ad, bd, idesc2, (n > 0 || ks > 0) ? 1u : 0u);
           }
           mma_commit(&S.empty_bar[slot]);
@@ -549,11 +551,12 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         fetch3(h0 + 2, pf);
       }
       auto stage_a1 = [&](uint32_t nn) {   // half 0: builds the A1 tile (sequence number nn) from the window r0..r2
-        const uint32_t buf = nn & 1u;
-        // A1[buf] was last read by the MMAs of row nn-2: da (observed through d1full two rows ago) and,
-        // in pass 1, the weight-gradient MMAs, observed through the release of that row's ring slot
-        if (PASS == 1 && nn >= 2) {
-          const uint32_t m = nn - 2;
+        const uint32_t buf = nn % kA1Bufs;
+        // A1[buf] was last read by the MMAs of row nn - kA1Bufs: da (observed through d1full by this thread,
+        // in program order) and, in pass 1, the weight-gradient MMAs, observed through the release of that
+        // row's ring slot.  With three tiles the wait is for work issued two rows ago, off the critical path.
+        if (PASS == 1 && nn >= (uint32_t)kA1Bufs) {
+          const uint32_t m = nn - kA1Bufs;
           mbar_wait(&S.empty_bar[m % kFtSlots], (m / kFtSlots) & 1u);
         }
         float w[16];
