@@ -168,6 +168,16 @@ int vae_bn_apply_lrelu(const void* y, const float* scale, const float* mean, con
                        void* act, long long n_pix, int C, float slope, int dtype,
                        vae_stream_t stream);
 
+/* vae_bn_finalize + vae_bn_apply_lrelu in one launch (C % 8 == 0): vec_out[4][C] receives
+ * (scale, shift, mean, rstd); num_batches_tracked (int64 device scalar, may be NULL) is
+ * incremented when training.
+ * replaces: aten::native_batch_norm + aten::leaky_relu (models.py:46-47,69-70) */
+int vae_bn_finalize_apply_lrelu(const void* y, const double* stats, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, long long* num_batches_tracked,
+                                float* vec_out, void* act, long long n_pix, int C, long long count,
+                                float momentum, float eps, int training, float slope, int dtype,
+                                vae_stream_t stream);
+
 /* Pass 1 of the backward: du = dact * lrelu'((y-mean)*scale+beta);
  * dstats[0:C] += sum du, dstats[C:2C] += sum du * xhat (double; zeroed by this call).
  * replaces: aten::leaky_relu_backward + the reductions of native_batch_norm_backward */

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "vae_umma_wgrad_supported": [_i, _i],
     "vae_conv_wgrad_umma": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "vae_bn_finalize": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _f, _f, _i, _vp],
+    "vae_bn_finalize_apply_lrelu": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _ll, _f, _f, _i, _f, _i, _vp],
     "vae_bn_apply_lrelu": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp],

@@ -139,6 +139,89 @@ bn_apply_lrelu_vec8(const T* __restrict__ y, const float* __restrict__ scale,
   }
 }
 
+// finalize + apply in one launch: every thread derives the constants of ITS 8 channels from the
+// fp64 statistics (a dozen flops), block 0 also publishes the (scale, shift, mean, rstd) vectors the
+// backward pass needs and performs the running-statistics update exactly as bn_finalize_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_finalize_apply_vec8(const T* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float* __restrict__ vec_out, T* __restrict__ act,
+                       long long n_pix, int C, double count, float momentum, float eps, int training, float slope) {
+  const int G = C / 8;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  float sc[8], mu[8], be[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = g * 8 + k;
+    float mean, rstd;
+    if (training) {
+      const double m = stats[c] / count;
+      double var = stats[C + c] / count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      mean = running_mean[c];
+      rstd = 1.0f / sqrtf(running_var[c] + eps);
+    }
+    mu[k] = mean;
+    sc[k] = gamma[c] * rstd;
+    be[k] = beta[c];
+  }
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mean, rstd;
+      if (training) {
+        const double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        rstd = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean != nullptr) {
+          const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+          running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+          running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+      } else {
+        mean = running_mean[c];
+        rstd = 1.0f / sqrtf(running_var[c] + eps);
+      }
+      const float s_ = gamma[c] * rstd;
+      vec_out[c] = s_;
+      vec_out[C + c] = beta[c] - mean * s_;
+      vec_out[2 * C + c] = mean;
+      vec_out[3 * C + c] = rstd;
+    }
+    if (threadIdx.x == 0 && training && num_batches_tracked != nullptr) num_batches_tracked[0] += 1;
+  }
+  if (lane >= lanes) return;
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * kBnUnroll) {
+    RawVec<T, 8> v[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long p = p0 + u * step;
+      if (p < n_pix) v[u].load(y + p * C + g * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long p = p0 + u * step;
+      if (p < n_pix) {
+        Vec8<T> o;
+        v[u].get(o.v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float uu = bn_affine(o.v[k], mu[k], sc[k], be[k]);
+          o.v[k] = uu > 0.0f ? uu : uu * slope;
+        }
+        o.store(act + p * C + g * 8);
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void bn_apply_lrelu_scalar(const T* __restrict__ y, const float* __restrict__ scale,
                                       const float* __restrict__ mean, const float* __restrict__ beta,
@@ -346,6 +429,28 @@ __global__ void transpose_kernel(const TS* __restrict__ src, TD* __restrict__ ds
   }
 }
 
+// bf16 -> bf16 with both extents multiples of 64: 16-byte global accesses on both sides
+__global__ void __launch_bounds__(256)
+transpose_bf16_tile64(const bf16* __restrict__ src, bf16* __restrict__ dst, int R, int Cc) {
+  __shared__ __align__(16) bf16 tile[64][72];
+  const long long base = (long long)blockIdx.z * R * Cc;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int r = i >> 3, ch = i & 7;
+    *reinterpret_cast<uint4*>(&tile[r][ch * 8]) =
+        *reinterpret_cast<const uint4*>(src + base + (long long)(r0 + r) * Cc + c0 + ch * 8);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    const int c = i & 63, ch = i >> 6;   // consecutive threads: consecutive columns (conflict-free 2-byte reads)
+    uint4 pk;
+    bf16* o = reinterpret_cast<bf16*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = tile[ch * 8 + k][c];
+    *reinterpret_cast<uint4*>(dst + base + (long long)(c0 + c) * R + r0 + ch * 8) = pk;
+  }
+}
+
 // ------------------------------------------------------- reparam / rng / sigmoid
 __global__ void philox_randn_kernel(float* __restrict__ out, long long n, unsigned long long seed,
                                     unsigned long long offset) {
@@ -516,6 +621,31 @@ extern "C" int vae_bn_finalize(const double* stats, const float* gamma, const fl
   return check_launch("bn_finalize");
 }
 
+extern "C" int vae_bn_finalize_apply_lrelu(const void* y, const double* stats, const float* gamma, const float* beta,
+                                           float* running_mean, float* running_var, long long* num_batches_tracked,
+                                           float* vec_out, void* act, long long n_pix, int C, long long count,
+                                           float momentum, float eps, int training, float slope, int dtype,
+                                           vae_stream_t stream) {
+  VAE_REQUIRE(y && gamma && beta && vec_out && act && n_pix > 0 && C > 0 && C % 8 == 0 && C / 8 <= 256,
+              "bn_finalize_apply_lrelu: bad argument (C must be a multiple of 8, <= 2048)");
+  VAE_REQUIRE(training ? (stats != nullptr && count > 0) : (running_mean && running_var),
+              "bn_finalize_apply_lrelu: training needs stats, eval needs running buffers");
+  cudaStream_t st = as_stream(stream);
+  const int G = C / 8, lanes = 256 / G;
+  long long blocks = (n_pix + (long long)lanes * kBnUnroll - 1) / ((long long)lanes * kBnUnroll);
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+  if (dtype == VAE_BF16)
+    bn_finalize_apply_vec8<bf16><<<grid, 256, 0, st>>>((const bf16*)y, stats, gamma, beta, running_mean, running_var,
+                                                       num_batches_tracked, vec_out, (bf16*)act, n_pix, C, (double)count,
+                                                       momentum, eps, training, slope);
+  else
+    bn_finalize_apply_vec8<float><<<grid, 256, 0, st>>>((const float*)y, stats, gamma, beta, running_mean, running_var,
+                                                        num_batches_tracked, vec_out, (float*)act, n_pix, C, (double)count,
+                                                        momentum, eps, training, slope);
+  return check_launch("bn_finalize_apply_lrelu");
+}
+
 extern "C" int vae_bn_apply_lrelu(const void* y, const float* scale, const float* mean,
                                   const float* beta, void* act, long long n_pix, int C, float slope,
                                   int dtype, vae_stream_t stream) {
@@ -622,6 +752,11 @@ static int launch_transpose(const void* src, void* dst, int B, int R, int Cc, cu
 
 static int transpose_dispatch(const void* src, void* dst, int B, int R, int Cc, int dt_src,
                               int dt_dst, cudaStream_t st) {
+  if (dt_src == VAE_BF16 && dt_dst == VAE_BF16 && R % 64 == 0 && Cc % 64 == 0) {
+    dim3 grid(Cc / 64, R / 64, B);
+    transpose_bf16_tile64<<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, R, Cc);
+    return check_launch("transpose_bf16_tile64");
+  }
   if (dt_src == VAE_F32 && dt_dst == VAE_F32) return launch_transpose<float, float>(src, dst, B, R, Cc, st);
   if (dt_src == VAE_BF16 && dt_dst == VAE_BF16) return launch_transpose<bf16, bf16>(src, dst, B, R, Cc, st);
   if (dt_src == VAE_F32 && dt_dst == VAE_BF16) return launch_transpose<float, bf16>(src, dst, B, R, Cc, st);

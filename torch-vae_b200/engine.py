@@ -52,6 +52,13 @@ def _bn_vectors(y, stats, gamma, beta, bn, training: bool):
 
 def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     count = y.numel() // y.shape[-1]
+    C = y.shape[-1]
+    if C % 8 == 0 and C // 8 <= 256:
+        use_batch = training or bn.running_mean is None
+        nbt = bn.num_batches_tracked if (training and bn.num_batches_tracked is not None) else None
+        return ops.bn_finalize_apply_lrelu(
+            y, stats if use_batch else None, gamma, beta, bn.running_mean, bn.running_var, nbt, count, use_batch,
+            momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps)
     use_batch = training or bn.running_mean is None
     vec = ops.bn_finalize(
         stats if use_batch else None, gamma, beta, bn.running_mean, bn.running_var, count, use_batch,

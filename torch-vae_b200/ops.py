@@ -187,6 +187,22 @@ def bn_finalize(stats, gamma, beta, running_mean, running_var, count: int, train
     return vec
 
 
+def bn_finalize_apply_lrelu(y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, count: int,
+                            training: bool, momentum: float = BN_MOMENTUM, eps: float = BN_EPS,
+                            slope: float = LRELU_SLOPE):
+    """BatchNorm statistics -> vectors AND normalise + LeakyReLU in one launch -> (vec[4,C], act)."""
+    C = y.shape[-1]
+    vec = torch.empty((4, C), dtype=torch.float32, device=y.device)
+    act = torch.empty_like(y)
+    rc = _L().vae_bn_finalize_apply_lrelu(
+        _p(y), _p(stats), _f32(gamma, "bn weight"), _f32(beta, "bn bias"), _f32(running_mean, "running_mean"),
+        _f32(running_var, "running_var"), _p(num_batches_tracked), _p(vec), _p(act), y.numel() // C, C, count,
+        momentum, eps, 1 if training else 0, slope, code(y), _stream(),
+    )
+    _lib.check(rc, "vae_bn_finalize_apply_lrelu")
+    return vec, act
+
+
 def bn_apply_lrelu(y, vec, beta, slope: float = LRELU_SLOPE):
     C = y.shape[-1]
     act = torch.empty_like(y)
