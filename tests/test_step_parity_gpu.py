@@ -49,7 +49,10 @@ CASES = [
     ("roll_128", 128, 128, [32, 64, 128, 256], 10, 4, 1.0),
     ("rect_small", 32, 64, [8, 16, 32, 64], 6, 4, 0.00025),
     ("odd_widths", 32, 32, [8, 24, 40, 64], 5, 3, 0.5),
+    # BASELINE.json configs[3]: long-context rolls 1x128x1024, wider channels, latent 256
+    ("wide_long_1024", 128, 1024, [64, 128, 256, 512], 256, 2, 1.0),
 ]
+BF16_CASES = CASES[:3] + CASES[4:]
 
 
 def build(tv, H, W, hidden, L, kldw, dtype, params):
@@ -94,8 +97,11 @@ def test_train_step_fp32(tv, case):
 
 
 def check_fp32(name, out, losses, grads, bufs, r64, r32, TOL):
+    # Losses: against the fp64 oracle, or -- when a logit saturates fp32 sigmoid (|logit| > ~17: the
+    # reference's F.binary_cross_entropy then hits its -100 log clamp, which exact arithmetic does not,
+    # SURVEY.md section 7 "BCE semantics") -- against the reference's own fp32 arithmetic.
     for key, got in (("loss", losses["loss"]), ("reconstruction_loss", losses["reconstruction_loss"]), ("kld_loss", losses["kld_loss"])):
-        assert vo.rel_err(got, r64[key]) <= TOL, key
+        assert min(vo.rel_err(got, r64[key]), vo.rel_err(got, r32[key])) <= TOL, key
     for key, got in (("mu", out["encoded"]["mu"]), ("log_var", out["encoded"]["log_var"]), ("latents", out["latents"]),
                      ("pre_latents", out["encoded"]["pre_latents"]), ("output", out["output"]), ("logits", out["logits"])):
         assert vo.rel_err(got, r64[key].reshape(got.shape)) <= TOL, key
@@ -208,7 +214,7 @@ def test_train_step_bf16_realistic_workload(tv):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("case", CASES[:3], ids=[c[0] for c in CASES[:3]])
+@pytest.mark.parametrize("case", BF16_CASES, ids=[c[0] for c in BF16_CASES])
 def test_train_step_bf16(tv, case):
     name, H, W, hidden, L, B, kldw = case
     params = vo.closed_form_params(vo.param_shapes(1, L, H, W, list(hidden)))
