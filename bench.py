@@ -156,6 +156,13 @@ def algorithmic_cost(name, tag):
     if name == "vae_final_bwd_apply":  # reads y and dlogits, writes dy
         B, H, W, C, _, d = t[:6]
         return (B * H * W * (2 * C + 1) * _sz(d), 2 * B * H * W * 9 * C)
+    if name == "vae_bn_finalize_apply_lrelu":
+        n, C = t[:2]
+        d = t[5] if len(t) > 5 else 1
+        return (2 * n * C * _sz(d), 3 * n * C)
+    if name in ("vae_skinny_reduce", "vae_skinny_wgrad", "vae_skinny_expand"):
+        M, N, K = t[:3]
+        return (2 * M * K + 4 * N * K + 4 * M * N, 2 * M * N * K)
     if name == "vae_bn_apply_lrelu":
         n, C, d = t[:3]
         return (2 * n * C * _sz(d), 3 * n * C)
@@ -180,6 +187,26 @@ def algorithmic_cost(name, tag):
         M, N, K = t[:3]
         return (4 * (M * K + K * N + M * N), 2 * M * N * K)
     return (0, 0)
+
+
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can dominate
+# the B=512 step, from ONE `ncu --set full` capture per kernel: profiles/r01d_ncu_full_top_kernels.csv
+# (scripts/profile_top.py).  Keyed by (C-ABI entry point, leading integer arguments).
+NCU_TRAFFIC_BYTES = {
+    ("vae_final_conv_fwd_tc", (512, 128, 128, 32)): 559.68e6 + 46.51e6,
+    ("vae_final_bwd_reduce_tc", (512, 128, 128, 32)): 553.97e6 + 4.15e6,
+    ("vae_final_bwd_apply_tc", (512, 128, 128, 32)): 554.84e6 + 493.99e6,
+    ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 1)): 134.34e6 + 479.14e6,
+    ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 0)): 536.98e6 + 118.96e6,
+    ("vae_conv_wgrad_tma", (512, 128, 128, 32, 32, 2)): 671.55e6 + 6.08e6,
+}
+
+
+def measured_traffic(name, tag):
+    for (n, prefix), b in NCU_TRAFFIC_BYTES.items():
+        if n == name and tuple(tag[:len(prefix)]) == prefix:
+            return b
+    return None
 
 
 def load_peaks():
@@ -393,7 +420,7 @@ def b200_arm(a):
     else:
         achieved, peak, unit = top_flops / avg_s / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
     roofline = {"bound": "hbm" if hbm_bound else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": None, "kernel": top_key[0], "kernel_args": list(top_key[1]),
+                "frac": achieved / peak, "traffic": measured_traffic(*top_key), "kernel": top_key[0], "kernel_args": list(top_key[1]),
                 "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": top_bytes, "alg_flops_per_launch": top_flops,
                 "share_of_step_kernel_time": rows[0][2] / n_prof / total_kernel_ms, "peak_source": peaks["source"]}
 
