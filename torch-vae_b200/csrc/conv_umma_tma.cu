@@ -372,10 +372,14 @@ static bool tma_plan(TmaConvParams& P, const GatherGeom& g) {
   P.N = g.Nout;
   P.kc = g.Cin == 32 ? 32 : 64;
   P.cin_chunks = g.Cin / P.kc;
-  P.sps = P.kc == 32 ? 2 : 1;
   P.sub_a_bytes = kTTileM * P.kc * 2;
   P.sub_b_elems = g.Nout * P.kc;
-  P.a_stage_bytes = P.sps * P.sub_a_bytes;                                     // 16 KB
+  // sub-tiles per stage: as many as keep >= 3 stages in flight (each producer / issuer iteration costs
+  // several hundred cycles of single-thread issue latency, so stages should carry 32 KB or more)
+  const int sub_bytes = P.sub_a_bytes + P.sub_b_elems * 2;
+  P.sps = P.kc == 32 ? 4 : 2;
+  while (P.sps > 1 && (190 * 1024) / (P.sps * sub_bytes) < 3) P.sps /= 2;
+  P.a_stage_bytes = P.sps * P.sub_a_bytes;
   P.b_stage_bytes = (P.sps * P.sub_b_elems * 2 + 1023) / 1024 * 1024;
   P.stages = (190 * 1024) / (P.a_stage_bytes + P.b_stage_bytes);
   if (P.stages > kTStagesMax) P.stages = kTStagesMax;
