@@ -367,7 +367,8 @@ def b200_arm(a):
 
     def run_step(x):
         if graph is not None:
-            static_x.copy_(x, non_blocking=True)
+            if x is not static_x:
+                static_x.copy_(x, non_blocking=True)
             graph.replay()
             return static_losses
         return train_step(x)
@@ -456,7 +457,8 @@ def b200_arm(a):
         prefetch(k ^ 1)
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[k])
-        xd = train_tf(dev_rolls[k])
+        # the transform writes straight into the step's input buffer (the captured graph's static input)
+        xd = train_tf(dev_rolls[k], out=static_x if graph is not None else None)
         freed[k].record(cur)
         losses = run_step(xd)
         losses_host[0:1].copy_(losses["loss"].detach().reshape(1), non_blocking=True)

@@ -241,7 +241,7 @@ extern "C" int vae_skinny_reduce(const void* A, const float* W, const float* bia
   cudaStream_t st = as_stream(stream);
   fill_rows_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(out, bias, M, N);
   int kpw = 1024;
-  while (kpw > 256 && (long long)((M + 3) / 4) * ((K + kpw - 1) / kpw) < 8LL * sm_count()) kpw /= 2;
+  while (kpw > 256 && (long long)((M + 3) / 4) * ((K + kpw - 1) / kpw) < 32LL * sm_count()) kpw /= 2;
   const long long warps = (long long)((M + 3) / 4) * ((K + kpw - 1) / kpw);
   const int grid = (int)((warps + 7) / 8);
   VAE_N_SWITCH(N, {

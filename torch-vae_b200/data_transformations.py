@@ -51,7 +51,7 @@ class RollTransform:
     def manual_seed(self, seed: int, rank: int = 0) -> None:
         self.seed, self.offset = int(seed) + int(rank), 0
 
-    def __call__(self, rolls: torch.Tensor) -> torch.Tensor:
+    def __call__(self, rolls: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if rolls.dim() == 4 and rolls.shape[1] == 1:
             rolls = rolls[:, 0]
         if rolls.shape[1] < self.height or rolls.shape[2] < self.width:
@@ -59,7 +59,7 @@ class RollTransform:
         out = ops.roll_transform(
             rolls.contiguous(), self.height, self.width, 1 if self.random_crop else 0,
             self.max_pitch_shift if self.random_crop else 0, self.binarize_threshold, self.mean, self.std,
-            self.seed, self.offset,
+            self.seed, self.offset, out=out,
         )
         self.offset += rolls.shape[0]
         return out

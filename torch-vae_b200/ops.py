@@ -487,11 +487,14 @@ def sigmoid_bwd(dprobs, probs, dlogits=None, dtype=torch.float32):
 
 # ------------------------------------------------------------------ transforms
 def roll_transform(rolls, H: int, W: int, crop_mode: int, max_pitch_shift: int,
-                   binarize_threshold: float, mean: float, std: float, seed: int, offset: int):
+                   binarize_threshold: float, mean: float, std: float, seed: int, offset: int, out=None):
     if rolls.dtype != torch.uint8 or rolls.dim() != 3:
         raise RuntimeError("roll_transform expects uint8 rolls of shape [B, Hs, Ws]")
     B, Hs, Ws = rolls.shape
-    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=rolls.device)
+    if out is None:
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=rolls.device)
+    elif out.shape != (B, 1, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise RuntimeError("roll_transform: out must be a contiguous float32 [B, 1, H, W] tensor")
     rc = _L().vae_roll_transform(
         _p(rolls), _p(out), B, Hs, Ws, H, W, crop_mode, max_pitch_shift, binarize_threshold, mean, std,
         seed, offset, _stream(),
