@@ -669,9 +669,247 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 }
 
 // =============================================================================================
+// backward pass 1, all-GEMM form.  With b = [u > 0] (u = scale*y + shift), q = slope + (1-slope)*b:
+//     du  = q * da,   da[p][c] = sum_w dlwin[p][w] * wf[c][w]        (wf[c][w] = w_last[c][8 - w])
+//   sum_p du[p][c]        = sum_w wf[c][w] * G1[c][w],    G1 = q^T . dlwin
+//   sum_p du[p][c]*y[p][c]= sum_w wf[c][w] * G2[c][w],    G2 = (q*y)^T . dlwin
+//   dW_last[c][8 - w]     = sum_p lrelu(u)[p][c] * dlwin[p][w] = scale[c]*G2[c][w] + shift[c]*G1[c][w]
+// and q^T.dlwin = slope * colsum(dlwin) + (1-slope) * b^T.dlwin,  (q*y)^T.dlwin = slope * y^T.dlwin + (1-slope) * (b*y)^T.dlwin.
+// So the whole pass is ONE accumulating GEMM per image row,  [y | b | b*y]^T (96 x 128 pixels) . dlwin (128 x 9),
+// with exact bf16 operands (y is the stored tensor, b is 0/1, b*y is y or 0, dlwin is the stored dlogits):
+// the workers only derive b and b*y (6 instructions per element, no per-thread accumulators, no da).
+// Shared memory: three rings at a common stride L -- [y rows (TMA)] [b rows] [b*y rows] -- so that one
+// MN-major descriptor with LBO = L addresses the three 32-channel groups of a row as M = 96 (+32 unused):
+// 8 MMAs per row (an M = 128, K = 16 MMA costs ~58 cycles whatever N <= 64 is: scripts/micro/mma_cost.cu).
+// =============================================================================================
+constexpr int kP1Slots = 3;
+constexpr int kP1Ring = kP1Slots * kRowBytes;   // L
+constexpr size_t kP1SmemBytes = 1024 + 3 * kP1Ring + kA1Bufs * kRowBytes + 8192 + 64 * 4 + (3 * 32 * 9 + 16) * 4 +
+                                8 * (3 * kP1Slots + kA1Bufs + 1) + 16;
+
+__global__ void __launch_bounds__(kFtThreads, 2)
+final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* yring = smem;                         // [slots][8 KB]   (b ring at +L, b*y ring at +2L)
+  uint8_t* a1 = smem + 3 * kP1Ring;              // [kA1Bufs][8 KB] dlwin tiles; + 8 KB pad (unused M group of the last slot)
+  float* cst = reinterpret_cast<float*>(a1 + kA1Bufs * kRowBytes + 8192);   // scale[32], shift[32]
+  float* gsm = cst + 64;                         // [3][32][9] accumulators, [16] column sums of dlwin
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(gsm + 3 * 32 * 9 + 16);
+  uint64_t* empty_bar = full_bar + kP1Slots;
+  uint64_t* opready_bar = empty_bar + kP1Slots;
+  uint64_t* a1ready_bar = opready_bar + kP1Slots;
+  uint64_t* done_bar = a1ready_bar + kA1Bufs;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, RB = P.RB;
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int s = 0; s < kP1Slots; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+        mbar_init(&opready_bar[s], kFtWorkers);
+      }
+      for (int a = 0; a < kA1Bufs; ++a) mbar_init(&a1ready_bar[a], 128);
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 32);
+  }
+  if (warp < 8) {
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+      const float sc = P.scale[tid];
+      cst[tid] = sc;
+      cst[32 + tid] = fmaf(-P.mean[tid], sc, P.beta[tid]);
+    }
+    for (int i = tid; i < kA1Bufs * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(a1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 16; i += kFtWorkers) gsm[3 * 32 * 9 + i] = 0.0f;
+    fence_proxy_async_smem();
+  }
+  if (warp == 8 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  uint32_t total = 0;
+  for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) total += (uint32_t)RB;
+
+  if (warp == 8) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
+        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        for (int i = 0; i < RB; ++i, ++n) {
+          const uint32_t slot = n % kP1Slots, ph = (n / kP1Slots) & 1u;
+          mbar_wait(&empty_bar[slot], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[slot], kRowBytes);
+          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, 0, h0 + i, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================= MMA issuer =============================
+    const uint32_t idesc = make_idesc_bf16(128, 32, 1, 1);   // both operands MN-major
+    const uint32_t y_a = smem_u32(yring), a1_a = smem_u32(a1);
+    for (uint32_t n = 0; n < total; ++n) {
+      const uint32_t slot = n % kP1Slots, ph = (n / kP1Slots) & 1u, ab = n % kA1Bufs, aph = (n / kA1Bufs) & 1u;
+      mbar_wait(&a1ready_bar[ab], aph);
+      mbar_wait(&opready_bar[slot], ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
+          const uint64_t ad = make_desc_mn_tc(y_a + slot * kRowBytes + ks * 1024, kP1Ring, 512, 4);
+          const uint64_t bd = make_desc_mn_tc(a1_a + ab * kRowBytes + ks * 1024, kRowBytes, 512, 4);
+          mma_bf16_ss(tmem_base, ad, bd, idesc, (n > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[slot]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // =============================== workers ==============================
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const uint32_t y_a = smem_u32(yring), a1_a = smem_u32(a1), cst_a = smem_u32(cst);
+    const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
+    const uint32_t a1off0 = swz64(p, 0), a1off1 = swz64(p, 1);
+    float colsum[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) colsum[k] = 0.0f;
+    uint32_t n = 0;
+    for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
+      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      auto fetch3 = [&](int h, float* v) {
+        if (h >= 0 && h < H) {
+          const bf16* row = P.dl + ((long long)b * H + h) * 128;
+          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          v[1] = __bfloat162float(row[p]);
+          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+        } else {
+          v[0] = v[1] = v[2] = 0.0f;
+        }
+      };
+      float r0[3], r1[3], r2[3], pf[3];
+      if (half == 0) {
+        fetch3(h0 - 1, r0);
+        fetch3(h0, r1);
+        fetch3(h0 + 1, r2);
+        fetch3(h0 + 2, pf);
+      }
+      auto stage_a1 = [&](uint32_t nn) {   // half 0: dlwin tile of row nn from the register window
+        const uint32_t buf = nn % kA1Bufs;
+        if (nn >= (uint32_t)kA1Bufs) {     // the MMAs of row nn - kA1Bufs have finished reading this tile
+          const uint32_t m = nn - kA1Bufs;
+          mbar_wait(&empty_bar[m % kP1Slots], (m / kP1Slots) & 1u);
+        }
+        float w[16];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          w[k] = r0[k];
+          w[3 + k] = r1[k];
+          w[6 + k] = r2[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) colsum[k] += w[k];
+#pragma unroll
+        for (int k = 9; k < 16; ++k) w[k] = 0.0f;
+        const uint32_t base = a1_a + buf * kRowBytes;
+        sts128(base + a1off0, pack8(w));
+        sts128(base + a1off1, pack8(w + 8));
+        fence_proxy_async_smem();
+        mbar_arrive(&a1ready_bar[buf]);
+      };
+      if (half == 0) stage_a1(n);
+      for (int i = 0; i < RB; ++i, ++n) {
+        if (i + 1 < RB && half == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            r0[k] = r1[k];
+            r1[k] = r2[k];
+            r2[k] = pf[k];
+          }
+          fetch3(h0 + i + 3, pf);
+          stage_a1(n + 1);
+        }
+        const uint32_t slot = n % kP1Slots, ph = (n / kP1Slots) & 1u;
+        mbar_wait(&full_bar[slot], ph);
+        const uint32_t row = y_a + slot * kRowBytes;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t a = row + (j == 0 ? off0 : off1);
+          const uint32_t cb = cst_a + (uint32_t)((2 * half + j) * 32);
+          float y[8], scv[8], shv[8], bb[8], by[8];
+          unpack8(lds128(a), y);
+          load8f(cb, scv);
+          load8f(cb + 128, shv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const bool pos = fmaf(y[k], scv[k], shv[k]) > 0.0f;
+            bb[k] = pos ? 1.0f : 0.0f;
+            by[k] = pos ? y[k] : 0.0f;
+          }
+          sts128(a + kP1Ring, pack8(bb));
+          sts128(a + 2 * kP1Ring, pack8(by));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&opready_bar[slot]);
+      }
+    }
+    // ------------------------------ reductions ------------------------------
+    if (half == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float v = warp_sum(colsum[k]);
+        if (lane == 0) atomicAdd(&gsm[3 * 32 * 9 + k], v);
+      }
+    }
+    if (warp < 3 && total > 0) {   // TMEM lanes 32w..32w+31 = rows of [y | b | b*y]^T . dlwin
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      float v[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gsm[(warp * 32 + lane) * 9 + k] = v[k];
+    }
+    named_bar_sync(1, kFtWorkers);
+    if (warp == 0 && total > 0) {
+      const int c = lane;
+      const float sl = P.slope, om = 1.0f - P.slope, sc = cst[c], sh = cst[32 + c];
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float g1 = sl * gsm[3 * 32 * 9 + k] + om * gsm[(32 + c) * 9 + k];          // q^T . dlwin
+        const float g2 = sl * gsm[c * 9 + k] + om * gsm[(64 + c) * 9 + k];               // (q*y)^T . dlwin
+        const float wf = P.w_last[c * 9 + (8 - k)];
+        s1 += (double)wf * (double)g1;
+        s2 += (double)wf * (double)g2;
+        atomicAdd(&P.dw_last[c * 9 + (8 - k)], fmaf(sc, g2, sh * g1));
+      }
+      atomicAdd(&P.dstats[c], s1);
+      atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
+      if (c == 0) atomicAdd(&P.dstats[64], (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 static bool g_final_tc_enabled = true;
+static bool g_final_gemm_reduce = true;   // pass 1 as one accumulating GEMM (final_bwd_reduce_gemm_kernel)
 
 static bool final_tc_ok(int B, int H, int W, int C, int dtype) {
   return g_final_tc_enabled && dtype == VAE_BF16 && C == 32 && W == 128 && B > 0 && H >= 16 && H % 16 == 0 &&
@@ -745,6 +983,15 @@ static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
   }
   int grid = 2 * sm_count();
   if (grid > P.total_bands) grid = P.total_bands;
+  if (pass == 1 && g_final_gemm_reduce) {
+    static bool attr3 = false;
+    if (!attr3) {
+      VAE_CUDA(cudaFuncSetAttribute(final_bwd_reduce_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP1SmemBytes));
+      attr3 = true;
+    }
+    final_bwd_reduce_gemm_kernel<<<grid, kFtThreads, kP1SmemBytes, st>>>(P);
+    return check_launch("final_bwd_reduce_gemm");
+  }
   if (pass == 1) final_bwd_tc_kernel<1><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
   else final_bwd_tc_kernel<2><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
   return check_launch(pass == 1 ? "final_bwd_reduce_tc" : "final_bwd_apply_tc");
