@@ -173,7 +173,7 @@ umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
   } else if (nkb > 0) {
     // ============================== epilogue ==============================
     const int lg = warp & 3;  // TMEM lane group
-    mbar_wait(done_bar, 0);
+    mbar_wait_sleep(done_bar, 0, 1000);  // idle for the whole main loop: do not compete with warps 0 / 1 for issue slots
     tc_fence_after();
     const int rows = P.TG * P.Ci;
     for (int mt = 0; mt < P.mtiles; ++mt) {
