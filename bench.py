@@ -39,7 +39,7 @@ FLOPS_PER_SAMPLE_TRAIN = {(128, 128): 0.9419e9}  # BASELINE.md §2 (FlopCounterM
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -80,9 +80,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken while the timed region [t0, t1] ran (nvidia-smi is started before
+        the warm-up so that it is already streaming; if the region is shorter than one sampling period the
+        samples within 150 ms of it are used)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
@@ -92,7 +95,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        picked = self.samples
+        if t0 is not None and t1 is not None:
+            picked = [x for x in self.samples if t0 <= x[0] <= t1 + 0.02]
+            if not picked:
+                picked = [x for x in self.samples if t0 - 0.15 <= x[0] <= t1 + 0.15]
+        for _, s in picked:
             f = [t.strip() for t in s.split(",")]
             if len(f) < 6:
                 continue
@@ -392,15 +400,21 @@ def b200_arm(a):
         return float(ms)
 
     # -- device-resident timing (value) -----------------------------------------
-    for _ in range(max(3, a.warmup)):
-        run_step(x_dev)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(3, a.warmup)):
+        run_step(x_dev)
+    if rank == 0:  # let nvidia-smi reach its streaming state before the (possibly very short) timed region
+        t_wait = time.time()
+        while not clocks.samples and time.time() - t_wait < 2.0:
+            time.sleep(0.01)  # (no extra steps here: with N > 1 every step is a collective)
     l0 = ops.LAUNCHES
+    t_region0 = time.time()
     ms_total = timed(lambda: run_step(x_dev), a.steps)
+    t_region1 = time.time()
     eager_launches = ops.LAUNCHES - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
     ms_per_step = ms_total / a.steps
     value = B * world * a.steps / (ms_total / 1e3)
 
