@@ -490,7 +490,7 @@ def b200_arm(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "height": H, "width": W, "batch_per_gpu": B, "global_batch": B * world,
-                       "hidden_dims": HIDDEN, "latent": LATENT, "parallelism": f"dp{world}", "cuda_graph": bool(graph is not None),
+                       "parallelism": f"dp{world}", "cuda_graph": bool(graph is not None),
                        "optimizer": ("torch.optim.AdamW" if a.torch_adamw else "FusedAdamW (one launch, torch.optim.AdamW state layout)")
                                     + " over encoder+decoder groups (train.py:210-228), inside the timed step",
                        "l2": f"per-step working set {(4.13e6*3*B)/1e6:.0f} MB of activations >> 126 MB L2 (inputs larger than L2)"},
