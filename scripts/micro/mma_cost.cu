@@ -17,14 +17,15 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t s
   return d;
 }
 
-__global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int layout, int reps, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int layout, int reps, long long* out, int commit_every) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy[8];
   __shared__ uint32_t tptr;
   for (int i = threadIdx.x; i < 128 * 1024 / 16; i += 128) ((uint4*)smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 8; ++i) mbar_init(&dummy[i], 1); fence_barrier_init(); }
     __syncwarp();
     tmem_alloc(&tptr, 256);
   }
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(128, 1) k(int N, int a_mn, int b_mn, int layou
         const uint32_t ka = a_mn ? (uint32_t)(r & 7) * 16u * row : (uint32_t)(r & (row / 32 - 1)) * 32u;
         const uint32_t kb = b_mn ? (uint32_t)(r & 7) * 16u * row : (uint32_t)(r & (row / 32 - 1)) * 32u;
         mma_bf16_ss(tm, desc(a0 + ka, 8192, 8 * row, layout), desc(b0 + kb, 8192, 8 * row, layout), idesc, r > 0);
+        if (commit_every > 0 && (r % commit_every) == commit_every - 1) mma_commit(&dummy[(r / commit_every) & 7]);
       }
       mma_commit(&bar);
     }
@@ -64,13 +66,15 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int reps = 512;
-  for (int layout : {4, 2})
-    for (int am = 0; am < 2; ++am)
-      for (int bm = 0; bm < 2; ++bm)
-        for (int N : {32, 64, 128, 256}) {
+  for (int ce : {0, 8, 2, 1})
+  for (int layout : {4})
+    for (int am = 1; am < 2; ++am)
+      for (int bm = 1; bm < 2; ++bm)
+        for (int N : {32, 256}) {
           long long h = 0;
+          printf("commit every %d MMAs: ", ce);
           for (int it = 0; it < 2; ++it) {
-            k<<<148, 128, 130 * 1024>>>(N, am, bm, layout, reps, d);
+            k<<<148, 128, 130 * 1024>>>(N, am, bm, layout, reps, d, ce);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
             cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);

@@ -42,6 +42,7 @@ struct WgradTmaParams {
   int mtiles, tmem_cols;
   int kblocks, kb_per_split;
   int layout_x, layout_y;    // UMMA swizzle codes (4 = 64B, 2 = 128B)
+  int rows_w, rows_h, rows_n;  // a k-block = rows_n images x rows_h rows x rows_w pixels of the Ho x Wo grid
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -53,6 +54,21 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout_type << 61;
   return d;
+}
+
+template <int KSTEPS, int MTILES>
+__device__ __forceinline__ void issue_stage(uint32_t tmem_base, uint32_t hi_x, uint32_t hi_y, uint32_t lo_x, uint32_t lo_y,
+                                            uint32_t kstep_x, uint32_t kstep_y, uint32_t mt_step, uint32_t co_tile,
+                                            uint32_t idesc, uint32_t accum_first) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint64_t bd = ((uint64_t)hi_y << 32) | (lo_y + (uint32_t)ks * kstep_y);
+#pragma unroll
+    for (int mt = 0; mt < MTILES; ++mt) {
+      const uint64_t ad = ((uint64_t)hi_x << 32) | (lo_x + (uint32_t)ks * kstep_x + (uint32_t)mt * mt_step);
+      mma_bf16_ss(tmem_base + (uint32_t)mt * co_tile, ad, bd, idesc, ks > 0 ? 1u : accum_first);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kWtThreads, 1)
@@ -107,11 +123,19 @@ umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
       // taps of this CTA: consecutive taps of one kernel row (TG = 3) or a single tap (TG = 1)
       const int tap0 = tg * TG;
       const int kh0 = tap0 / 3, kw0 = tap0 - kh0 * 3;
+      // position of the first k-block (the only divisions of this thread); later k-blocks advance it
+      // incrementally -- an integer division costs this lone, latency-bound thread ~150 cycles
+      int jw0, jh0, b0;
+      {
+        const uint32_t m0 = (uint32_t)kb_begin * (uint32_t)P.KP;
+        jw0 = (int)(m0 % Wo);
+        const uint32_t t2 = m0 / Wo;
+        jh0 = (int)(t2 % Ho);
+        b0 = (int)(t2 / Ho);
+      }
+      const int rows_w = P.rows_w, rows_h = P.rows_h, rows_n = P.rows_n, iWo = P.Wo, iHo = P.Ho;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const uint32_t m0 = (uint32_t)kb * (uint32_t)P.KP;
-        const uint32_t jw0 = m0 % Wo, t2 = m0 / Wo;
-        const int jh0 = (int)(t2 % Ho), b0 = (int)(t2 / Ho);
-        const int xw = (int)jw0 * s + kw0 - 1, xh = jh0 * s + kh0 - 1;
+        const int xw = jw0 * s + kw0 - 1, xh = jh0 * s + kh0 - 1;
         mbar_wait(&empty_bar[stage], ph ^ 1u);
         uint8_t* st = smem + stage * P.stage_bytes;
         mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -121,8 +145,17 @@ umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
             tma_load_4d(dstp, &P.tmap_x, &full_bar[stage], g * cx, xw + tl, xh, b0);
         dstp = st + x_bytes;
         for (int g = 0; g < ypr; ++g, dstp += y_region)
-          tma_load_4d(dstp, &P.tmap_y, &full_bar[stage], co_base + g * cy, (int)jw0, jh0, b0);
+          tma_load_4d(dstp, &P.tmap_y, &full_bar[stage], co_base + g * cy, jw0, jh0, b0);
         if (++stage == P.stages) { stage = 0; ph ^= 1u; }
+        jw0 += rows_w;
+        if (jw0 >= iWo) {
+          jw0 = 0;
+          jh0 += rows_h;
+          if (jh0 >= iHo) {
+            jh0 = 0;
+            b0 += rows_n;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -148,22 +181,25 @@ umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
       tc_fence_after();
       if (elect_one()) {
         const uint32_t xa = smem0 + (uint32_t)stage * stage_bytes;
-        uint32_t lo_x = (xa >> 4) | lbo_x;
-        uint32_t lo_y = ((xa + xb) >> 4) | lbo_y;
-        uint32_t accum = kb > 0 ? 1u : 0u;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t bd = ((uint64_t)hi_y << 32) | lo_y;
-          uint32_t lo_a = lo_x, d = tmem_base;
-          for (int mt = 0; mt < mtiles; ++mt) {
-            mma_bf16_ss(d, ((uint64_t)hi_x << 32) | lo_a, bd, idesc, accum);
-            lo_a += mt_step;
-            d += co_tile;
-          }
-          accum = 1u;
-          lo_x += kstep_x;
-          lo_y += kstep_y;
+        const uint32_t lo_x = (xa >> 4) | lbo_x;
+        const uint32_t lo_y = ((xa + xb) >> 4) | lbo_y;
+        const uint32_t accum = kb > 0 ? 1u : 0u;
+        // straight-line issue: the single issuing thread is latency-bound, so the (k-step, M-tile) loops are
+        // compile-time unrolled and every descriptor is base + constant * index (no loop-carried chain)
+#define VAE_WT_ISSUE(KS_, MT_) \
+        issue_stage<KS_, MT_>(tmem_base, hi_x, hi_y, lo_x, lo_y, kstep_x, kstep_y, mt_step, co_tile, idesc, accum)
+        if (ksteps == 8) {
+          if (mtiles == 1) VAE_WT_ISSUE(8, 1);
+          else if (mtiles == 2) VAE_WT_ISSUE(8, 2);
+          else if (mtiles == 3) VAE_WT_ISSUE(8, 3);
+          else VAE_WT_ISSUE(8, 4);
+        } else {
+          if (mtiles == 1) VAE_WT_ISSUE(4, 1);
+          else if (mtiles == 2) VAE_WT_ISSUE(4, 2);
+          else if (mtiles == 3) VAE_WT_ISSUE(4, 3);
+          else VAE_WT_ISSUE(4, 4);
         }
+#undef VAE_WT_ISSUE
         mma_commit(&empty_bar[stage]);
         if (kb == nkb - 1) mma_commit(done_bar);
       }
@@ -278,6 +314,7 @@ static bool wgrad_tma_plan(WtPlan& pl, int B, int Hi, int Wi, int Ci, int Co, in
       const long long J = (long long)B * P.Ho * P.Wo;
       if (J >= (1LL << 31)) return false;
       P.kblocks = (int)((J + P.KP - 1) / P.KP);
+      P.rows_w = pl.rw; P.rows_h = pl.rh; P.rows_n = pl.rn;
       return true;
     }
   }
