@@ -130,11 +130,23 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
       int stage = 0;
       uint32_t ph = 0;
       const int im = P.in_mul;
+      // tile -> (image, row, column) of its first pixel: divisions only for the first tile, then the
+      // per-CTA tile stride is added with carries (this lone thread pays ~150 cycles per division)
+      int jw0, jh0, b0, dw0, dh0, db0;
+      {
+        const uint32_t m0 = (uint32_t)blockIdx.x * 128u;
+        jw0 = (int)(m0 % Wj);
+        const uint32_t t2 = m0 / Wj;
+        jh0 = (int)(t2 % Hj);
+        b0 = (int)(t2 / Hj);
+        const uint32_t d0 = (uint32_t)gridDim.x * 128u;
+        dw0 = (int)(d0 % Wj);
+        const uint32_t d2 = d0 / Wj;
+        dh0 = (int)(d2 % Hj);
+        db0 = (int)(d2 / Hj);
+      }
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const uint32_t m0 = (uint32_t)tile * 128u;
-        const uint32_t jw0 = m0 % Wj, t2 = m0 / Wj;
-        const int jh0 = (int)(t2 % Hj), b0 = (int)(t2 / Hj);
-        const int cw = (int)jw0 * im, ch = jh0 * im;
+        const int cw = jw0 * im, ch = jh0 * im;
 #pragma unroll
         for (int st = 0; st < Cfg::SPT; ++st) {
           mbar_wait(&empty_bar[stage], ph ^ 1u);
@@ -151,6 +163,11 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           }
           if (++stage == kStages) { stage = 0; ph ^= 1u; }
         }
+        jw0 += dw0;
+        if (jw0 >= (int)Wj) { jw0 -= (int)Wj; ++jh0; }
+        jh0 += dh0;
+        if (jh0 >= (int)Hj) { jh0 -= (int)Hj; ++b0; }
+        b0 += db0;
       }
     }
   } else if (warp == 1) {
