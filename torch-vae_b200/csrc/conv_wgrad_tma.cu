@@ -42,6 +42,7 @@ struct WgradTmaParams {
   int mtiles, tmem_cols;
   int kblocks, kb_per_split;
   int layout_x, layout_y;    // UMMA swizzle codes (4 = 64B, 2 = 128B)
+  int ctas_per_sm;
   int rows_w, rows_h, rows_n;  // a k-block = rows_n images x rows_h rows x rows_w pixels of the Ho x Wo grid
 };
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_base, uint32_t hi_x, u
   }
 }
 
-__global__ void __launch_bounds__(kWtThreads, 1)
+__global__ void __launch_bounds__(kWtThreads, 2)
 umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -294,8 +295,12 @@ static bool wgrad_tma_plan(WtPlan& pl, int B, int Hi, int Wi, int Ci, int Co, in
     P.n_tap_groups = 9 / P.TG;
     P.mtiles = (P.TG * Ci + 127) / 128;
     if (P.mtiles * P.co_tile > 512) continue;
-    for (int kp_try = 0; kp_try < 2; ++kp_try) {
-      P.KP = kp_try == 0 ? 128 : 64;
+    // Preference: configurations that leave room for TWO CTAs per SM (the per-CTA chain TMA gather -> MMA ->
+    // commit -> slot reuse is latency-bound; two interleaved chains hide it: 234 -> 142 us on the 32->32
+    // layer at 128x128), larger k-blocks first; then one CTA per SM.
+    for (int attempt = 0; attempt < 4; ++attempt) {
+      const int want_ctas = attempt < 2 ? 2 : 1;
+      P.KP = (attempt & 1) == 0 ? 128 : 64;
       if (!kblock_rows(P.Ho, P.Wo, P.KP, &pl.rw, &pl.rh, &pl.rn)) continue;
       if (pl.rw * s > 256 || pl.rh * s > 256 || pl.rn > 256) continue;
       P.x_region = P.KP * P.cx * 2; P.y_region = P.KP * P.cy * 2;
@@ -305,9 +310,11 @@ static bool wgrad_tma_plan(WtPlan& pl, int B, int Hi, int Wi, int Ci, int Co, in
       int y_bytes = P.ypr * P.y_region;
       if (pad_regions * P.x_region > y_bytes) y_bytes = pad_regions * P.x_region;
       P.stage_bytes = (x_regions * P.x_region + y_bytes + 1023) / 1024 * 1024;
-      P.stages = (200 * 1024) / P.stage_bytes;
+      P.ctas_per_sm = want_ctas;
+      P.stages = ((want_ctas == 2 ? 111 : 200) * 1024 - 2048) / P.stage_bytes;
       if (P.stages > kWtMaxStages) P.stages = kWtMaxStages;
       if (P.stages < 3) continue;
+      if (want_ctas == 2 && 2 * P.mtiles * P.co_tile > 512) continue;  // TMEM columns of two resident CTAs
       int cols = 32;
       while (cols < P.mtiles * P.co_tile) cols *= 2;
       P.tmem_cols = cols;
@@ -373,7 +380,7 @@ extern "C" int vae_conv_wgrad_tma(const void* x, const void* dy, float* dw, floa
   VAE_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
   P.ws = ws;
   const int combos = P.n_tap_groups * P.n_co_tiles;
-  int splits = sm_count() / combos;
+  int splits = P.ctas_per_sm * sm_count() / combos;
   if (splits < 1) splits = 1;
   if (splits > P.kblocks) splits = P.kblocks;
   P.kb_per_split = (P.kblocks + splits - 1) / splits;
