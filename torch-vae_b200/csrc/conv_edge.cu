@@ -13,6 +13,17 @@ namespace vae {
 
 constexpr int kStrip = 4;
 
+// 16-byte shared-memory load the compiler may not hoist out of the strip loop: keeping the 9 x 8
+// tap weights in registers costs 72 registers per thread and halves the resident warps, while
+// re-reading them is one broadcast wavefront per load.
+__device__ __forceinline__ float4 lds128_volatile(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
 // tap index (kh*3+kw) that pairs with window offset (a, b) in {-1,0,1}^2:
 // forward conv: (kh, kw) = (a+1, b+1); data gradient of a stride-1 conv: (1-a, 1-b)
 template <bool FLIP>
@@ -25,7 +36,7 @@ __device__ __forceinline__ constexpr int tap_of(int a, int b) {
 //     Out[b][out_mul... == 1][jh][jw][n] = bias[n] + sum_{a,b} In1[MUL*jh + a][MUL*jw + b] * W[n][tap(a,b)]
 // ---------------------------------------------------------------------------
 template <typename TI, typename TW, typename TO, int MUL, bool FLIP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 cin1_strip_kernel(const TI* __restrict__ In, const TW* __restrict__ Wq, const float* __restrict__ bias,
                   TO* __restrict__ Out, double* __restrict__ stats, int B, int Hin, int Win, int Hj, int Wj, int N) {
   constexpr int NC = MUL * (kStrip - 1) + 3;  // window columns a strip touches
@@ -72,8 +83,8 @@ cin1_strip_kernel(const TI* __restrict__ In, const TW* __restrict__ Wq, const fl
         }
 #pragma unroll
         for (int bb = -1; bb <= 1; ++bb) {
-          const float4* wp4 = reinterpret_cast<const float4*>(wsm + tap_of<FLIP>(a, bb) * N + gidx * 8);
-          const float4 w0 = wp4[0], w1 = wp4[1];
+          const float* wp = wsm + tap_of<FLIP>(a, bb) * N + gidx * 8;
+          const float4 w0 = lds128_volatile(wp), w1 = lds128_volatile(wp + 4);
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int i = 0; i < kStrip; ++i) {
@@ -121,7 +132,7 @@ cin1_strip_kernel(const TI* __restrict__ In, const TW* __restrict__ Wq, const fl
 //     enc.conv0: Mc = dY, S1 = x, MUL = 2, FLIP = false; final conv: Mc = act, S1 = dlogits, MUL = 1, FLIP = true
 // ---------------------------------------------------------------------------
 template <typename TM, typename TS, int MUL, bool FLIP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 c1_wgrad_strip_kernel(const TM* __restrict__ Mc, const TS* __restrict__ S1, float* __restrict__ dW, int B, int Hm,
                       int Wm, int N, int Hs, int Ws) {
   constexpr int NC = MUL * (kStrip - 1) + 3;

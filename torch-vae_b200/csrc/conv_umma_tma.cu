@@ -445,7 +445,12 @@ extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, 
                            : geom_dgrad(1, 128 * stride, 128 * stride, Ci, Co, stride);
   TmaConvParams P{};
   VAE_REQUIRE(tma_plan(P, g), "umma_tma_pack_weight: shape not served by the TMA path");
-  dim3 grid(64, g.nphase);
+  long long n_max = 0;  // one element per thread: the OIHW reads are scattered, parallelism hides them
+  for (int ph = 0; ph < g.nphase; ++ph) {
+    const long long n = (long long)P.nkb[ph] * P.sps * P.sub_b_elems;
+    if (n > n_max) n_max = n;
+  }
+  dim3 grid((unsigned)((n_max + 255) / 256), g.nphase);
   pack_tma_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (bf16*)out, P, Co, Ci, mode);
   return check_launch("pack_tma_weight");
 }

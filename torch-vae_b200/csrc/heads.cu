@@ -52,56 +52,73 @@ struct WChunk {
 };
 
 // ---------------------------------------------------------------------------------------------
-// out[m][n] += sum_{k in slice} A[m][k] * W(n, k): a warp owns 4 rows x a K slice; lanes stride K in
-// 8-element chunks; warp-shuffle reduction, one atomic per (row, n).  `out` must be pre-filled
-// (bias or zero) by the caller's init kernel.
+// out[m][n] += sum_{k in slice} A[m][k] * W(n, k).  A block owns 8 warps x ROWS rows and one K
+// slice whose weights it stages ONCE in shared memory as [N][ks_len]; a warp streams its rows'
+// 16-byte chunks (lanes stride K), accumulates over the whole slice in registers, and finishes
+// with warp-shuffle sums + one atomic per (row, n).  `out` is zeroed by the caller (memset node);
+// the slice-0 blocks add the bias.
 // ---------------------------------------------------------------------------------------------
-template <typename TA, int N>
+template <typename TA, int N, int ROWS>
 __global__ void __launch_bounds__(256)
-skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, float* __restrict__ out, int M, int K,
-                     long long wsn, long long wsk, int k_per_warp) {
-  const int warp_global = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int kslices = (K + k_per_warp - 1) / k_per_warp;
-  const int mt = warp_global / kslices, ks = warp_global - mt * kslices;
-  const int m0 = mt * 4;
+skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+                     float* __restrict__ out, int M, int K, long long wsn, long long wsk, int ks_len) {
+  extern __shared__ __align__(16) float w_s[];  // [N][ks_len]
+  const int kslices = (K + ks_len - 1) / ks_len;
+  const int ks = blockIdx.x % kslices, mb = blockIdx.x / kslices;
+  const int k_begin = ks * ks_len, k_len = min(ks_len, K - k_begin);  // multiples of 8
+  if (wsk == 1 && (wsn & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < N * k_len; i += 1024) {
+      const int n = i / k_len, kk = i - n * k_len;
+      *reinterpret_cast<float4*>(&w_s[n * ks_len + kk]) =
+          *reinterpret_cast<const float4*>(W + n * wsn + k_begin + kk);
+    }
+  } else {
+    for (int i = threadIdx.x; i < N * k_len; i += 256) {
+      const int kk = i / N, n = i - kk * N;
+      w_s[n * ks_len + kk] = W[n * wsn + (long long)(k_begin + kk) * wsk];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (mb * 8 + warp) * ROWS;
   if (m0 >= M) return;
-  const int k_begin = ks * k_per_warp, k_end = min(K, k_begin + k_per_warp);
-  float acc[4][N];
+  float acc[ROWS][N];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[r][n] = 0.0f;
-  for (int k = k_begin + lane * 8; k < k_end; k += 256) {
-    Vec8<TA> a[4];
+  const TA* a_base = A + (long long)m0 * K + k_begin;
+  for (int kk = lane * 8; kk < k_len; kk += 256) {
+    Vec8<TA> a[ROWS];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (m0 + r < M) a[r].load(A + (long long)(m0 + r) * K + k);
+    for (int r = 0; r < ROWS; ++r) {
+      if (m0 + r < M) a[r].load(a_base + (long long)r * K + kk);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[r].v[j] = 0.0f;
       }
     }
-    WChunk<N> wc;
-    wc.load(W, k, wsn, wsk);
-#pragma unroll
-    for (int n = 0; n < N; ++n)
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][n] = fmaf(a[r].v[j], wc.w[n][j], acc[r][n]);
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      const float v = warp_sum(acc[r][n]);
-      if (lane == ((r * N + n) & 31) && m0 + r < M) atomicAdd(&out[(long long)(m0 + r) * N + n], v);
+      const float4 w0 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + kk]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + kk + 4]);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][n] = fmaf(a[r].v[j], w[j], acc[r][n]);
     }
-}
-
-__global__ void fill_rows_kernel(float* __restrict__ out, const float* __restrict__ bias, int M, int N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < M * N) out[i] = bias != nullptr ? bias[i % N] : 0.0f;
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      float v = warp_sum(acc[r][n]);
+      if (lane == ((r * N + n) & 31) && m0 + r < M) {
+        if (ks == 0 && bias != nullptr) v += bias[n];
+        atomicAdd(&out[(long long)(m0 + r) * N + n], v);
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -123,7 +140,26 @@ skinny_wgrad_kernel(const float* __restrict__ D, const TA* __restrict__ A, float
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[n][j] = 0.0f;
   if (k < K) {
-    for (int m = m_begin + rg; m < m_end; m += 8) {
+    // four rows (one per 8-row stride) in flight per thread; same accumulation order as a plain loop
+    int m = m_begin + rg;
+    for (; m + 24 < m_end; m += 32) {
+      Vec8<TA> a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u].load(A + (long long)(m + 8 * u) * K + k);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* d = D + (long long)(m + 8 * u) * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          const float dv = __ldg(d + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[n][j] = fmaf(dv, a[u].v[j], acc[n][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[N][j] += a[u].v[j];
+      }
+    }
+    for (; m < m_end; m += 8) {
       Vec8<TA> a;
       a.load(A + (long long)m * K + k);
       const float* d = D + (long long)m * N;
@@ -158,50 +194,62 @@ skinny_wgrad_kernel(const float* __restrict__ D, const TA* __restrict__ A, float
 }
 
 // ---------------------------------------------------------------------------------------------
-// out[m][k] = bias[k] + sum_n D0[m][n] * W0(n, k) (+ sum_n D1[m][n] * W1(n, k)); a thread owns
-// 4 rows x 8 columns so each weight chunk is loaded once per 4 rows.
+// out[m][k] = bias[k] + sum_n D0[m][n] * W0(n, k) (+ sum_n D1[m][n] * W1(n, k)); a thread owns 8
+// columns, keeps their weight chunk(s) in registers and walks the block's rows, whose D rows sit
+// in shared memory (broadcast reads); a warp stores 512 contiguous bytes per row.
 // ---------------------------------------------------------------------------------------------
-template <typename TO, int N>
+constexpr int kExpandRows = 32;
+
+template <typename TO, int N, bool PAIR>
 __global__ void __launch_bounds__(256)
 skinny_expand_kernel(const float* __restrict__ D0, const float* __restrict__ W0, const float* __restrict__ D1,
                      const float* __restrict__ W1, const float* __restrict__ bias, TO* __restrict__ out, int M, int K,
                      long long wsn, long long wsk) {
-  const int kchunks = K / 8;
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-  const int kc = (int)(t % kchunks);
-  const int m0 = (int)(t / kchunks) * 4;
-  if (m0 >= M) return;
-  const int k = kc * 8;
-  float acc[4][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float b = bias != nullptr ? bias[k + j] : 0.0f;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r][j] = b;
+  constexpr int NP = (N + 3) & ~3;
+  __shared__ __align__(16) float d_s[PAIR ? 2 : 1][kExpandRows][NP];
+  const int m_begin = blockIdx.y * kExpandRows;
+  const int rows = min(kExpandRows, M - m_begin);
+  for (int i = threadIdx.x; i < rows * N; i += 256) {
+    const int r = i / N, n = i - r * N;
+    d_s[0][r][n] = D0[(long long)(m_begin + r) * N + n];
+    if (PAIR) d_s[PAIR ? 1 : 0][r][n] = D1[(long long)(m_begin + r) * N + n];
   }
+  __syncthreads();
+  const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (k >= K) return;
+  WChunk<N> w0, w1;
+  w0.load(W0, k, wsn, wsk);
+  if (PAIR) w1.load(W1, k, wsn, wsk);
+  float b[8];
 #pragma unroll
-  for (int pair = 0; pair < 2; ++pair) {
-    const float* D = pair == 0 ? D0 : D1;
-    const float* W = pair == 0 ? W0 : W1;
-    if (D == nullptr) continue;
-    WChunk<N> wc;
-    wc.load(W, k, wsn, wsk);
+  for (int j = 0; j < 8; ++j) b[j] = bias != nullptr ? bias[k + j] : 0.0f;
+  TO* o = out + (long long)m_begin * K + k;
+#pragma unroll 2
+  for (int r = 0; r < rows; ++r) {
+    float dv0[NP], dv1[NP];
+#pragma unroll
+    for (int q = 0; q < NP / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(&d_s[0][r][4 * q]);
+      dv0[4 * q] = t.x; dv0[4 * q + 1] = t.y; dv0[4 * q + 2] = t.z; dv0[4 * q + 3] = t.w;
+      if (PAIR) {
+        const float4 u = *reinterpret_cast<const float4*>(&d_s[PAIR ? 1 : 0][r][4 * q]);
+        dv1[4 * q] = u.x; dv1[4 * q + 1] = u.y; dv1[4 * q + 2] = u.z; dv1[4 * q + 3] = u.w;
+      }
+    }
+    Vec8<TO> acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = b[j];
 #pragma unroll
     for (int n = 0; n < N; ++n)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float dv = m0 + r < M ? __ldg(D + (long long)(m0 + r) * N + n) : 0.0f;
+      for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(dv0[n], w0.w[n][j], acc.v[j]);
+    if (PAIR) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][j] = fmaf(dv, wc.w[n][j], acc[r][j]);
-      }
-  }
+      for (int n = 0; n < N; ++n)
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    if (m0 + r >= M) break;
-    Vec8<TO> o;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = acc[r][j];
-    o.store(out + (long long)(m0 + r) * K + k);
+        for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(dv1[n], w1.w[n][j], acc.v[j]);
+    }
+    acc.store(o + (long long)r * K);
   }
 }
 
@@ -239,16 +287,23 @@ extern "C" int vae_skinny_reduce(const void* A, const float* W, const float* bia
                                  long long wsn, long long wsk, int dtA, vae_stream_t stream) {
   VAE_REQUIRE(A && W && out && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL, "skinny_reduce: bad argument");
   cudaStream_t st = as_stream(stream);
-  fill_rows_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(out, bias, M, N);
-  int kpw = 1024;
-  while (kpw > 256 && (long long)((M + 3) / 4) * ((K + kpw - 1) / kpw) < 32LL * sm_count()) kpw /= 2;
-  const long long warps = (long long)((M + 3) / 4) * ((K + kpw - 1) / kpw);
-  const int grid = (int)((warps + 7) / 8);
+  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st));
+  constexpr int kRows = 8;
+  const int row_blocks = (M + 8 * kRows - 1) / (8 * kRows);
+  int ks_len = 1024;  // K slice per block: enough blocks to cover the SMs, at most 64 KB of weights
+  while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) < sm_count()) ks_len /= 2;
+  const int grid = row_blocks * ((K + ks_len - 1) / ks_len);
+  const size_t smem = sizeof(float) * (size_t)N * ks_len;
   VAE_N_SWITCH(N, {
-    if (dtA == VAE_BF16)
-      skinny_reduce_kernel<bf16, NN><<<grid, 256, 0, st>>>((const bf16*)A, W, out, M, K, wsn, wsk, kpw);
-    else
-      skinny_reduce_kernel<float, NN><<<grid, 256, 0, st>>>((const float*)A, W, out, M, K, wsn, wsk, kpw);
+    if (dtA == VAE_BF16) {
+      auto kern = skinny_reduce_kernel<bf16, NN, kRows>;
+      if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      kern<<<grid, 256, smem, st>>>((const bf16*)A, W, bias, out, M, K, wsn, wsk, ks_len);
+    } else {
+      auto kern = skinny_reduce_kernel<float, NN, kRows>;
+      if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      kern<<<grid, 256, smem, st>>>((const float*)A, W, bias, out, M, K, wsn, wsk, ks_len);
+    }
   });
   return check_launch("skinny_reduce");
 }
@@ -285,13 +340,17 @@ extern "C" int vae_skinny_expand(const float* D0, const float* W0, const float* 
                                  int dtO, vae_stream_t stream) {
   VAE_REQUIRE(D0 && W0 && out && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL, "skinny_expand: bad argument");
   cudaStream_t st = as_stream(stream);
-  const long long threads = (long long)((M + 3) / 4) * (K / 8);
-  const int grid = (int)((threads + 255) / 256);
+  dim3 grid((K / 8 + 255) / 256, (M + kExpandRows - 1) / kExpandRows);
+  const bool pair = D1 != nullptr;
+  VAE_REQUIRE(!pair || W1 != nullptr, "skinny_expand: D1 without W1");
   VAE_N_SWITCH(N, {
-    if (dtO == VAE_BF16)
-      skinny_expand_kernel<bf16, NN><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (bf16*)out, M, K, wsn, wsk);
-    else
-      skinny_expand_kernel<float, NN><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (float*)out, M, K, wsn, wsk);
+    if (dtO == VAE_BF16) {
+      if (pair) skinny_expand_kernel<bf16, NN, true><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (bf16*)out, M, K, wsn, wsk);
+      else skinny_expand_kernel<bf16, NN, false><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (bf16*)out, M, K, wsn, wsk);
+    } else {
+      if (pair) skinny_expand_kernel<float, NN, true><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (float*)out, M, K, wsn, wsk);
+      else skinny_expand_kernel<float, NN, false><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (float*)out, M, K, wsn, wsk);
+    }
   });
   return check_launch("skinny_expand");
 }
