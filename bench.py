@@ -185,6 +185,9 @@ def algorithmic_cost(name, tag):
         n, B, L, d = t[0], t[1], t[2], t[3]
         per = (_sz(d) + 4) if name == "vae_elbo_fwd" else (2 * _sz(d) + 4)
         return (n * per + 6 * B * L * 4, 20 * n)
+    if name == "vae_elbo_fused":  # logits + fp32 target in, dlogits out, six latent vectors
+        n, B, L, d = t[0], t[1], t[2], t[3]
+        return (n * (2 * _sz(d) + 4) + 6 * B * L * 4, 30 * n)
     if name == "vae_sigmoid":
         n, d = t[:2]
         return (n * (_sz(d) + 4), 4 * n)

@@ -359,6 +359,20 @@ int vae_elbo_bwd(const void* logits, const float* target, const float* mu, const
                  long long n_elem, int B, int L, float kld_weight, int dtype, int input_is_prob,
                  vae_stream_t stream);
 
+/* Forward and gradient of the ELBO in ONE pass over logits + target (north-star item 2): writes
+ * the three losses like vae_elbo_fwd and dlogits / dmu / dlogvar like vae_elbo_bwd for an upstream
+ * gradient of 1.  bf16 logits use MUFU exp / log / reciprocal (same clamps and saturation points);
+ * fp32 logits use the exact functions of the two calls above.
+ * replaces: models.py:208-216 plus their autograd backward nodes (train.py:650) */
+int vae_elbo_fused(const void* logits, const float* target, const float* mu, const float* logvar,
+                   float* losses, double* scratch, void* dlogits, float* dmu, float* dlogvar,
+                   long long n_elem, int B, int L, float kld_weight, int dtype, int input_is_prob,
+                   vae_stream_t stream);
+/* dlogits, dmu, dlogvar *= *gscale in place (the upstream gradient of train.py:650's backward());
+ * a no-op launch when *gscale == 1. */
+int vae_elbo_scale_grads(const float* gscale, void* dlogits, float* dmu, float* dlogvar,
+                         long long n_elem, long long n_lat, int dtype, vae_stream_t stream);
+
 /* probs(fp32) = sigmoid(logits).  replaces: aten::sigmoid at models.py:81 */
 int vae_sigmoid(const void* logits, float* probs, long long n, int dtype, vae_stream_t stream);
 /* dlogits (+)= dprobs * p * (1-p)  (for user losses defined on probabilities). */

@@ -243,6 +243,73 @@ def test_fused_elbo_matches_reference_semantics(tv, dtype, kldw):
     assert rel_err(dp.cpu(), pr.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(6, 10, 16, 24), (3, 7, 5, 9), (64, 10, 128, 128)])
+def test_one_pass_elbo_equals_forward_plus_backward(tv, dtype, shape):
+    """vae_elbo_fused == vae_elbo_fwd + vae_elbo_bwd (the reference-semantics pair tested above),
+    including the clamp / saturation edge; vae_elbo_scale_grads applies the upstream gradient."""
+    ops = tv.ops
+    B, L, H, W = shape
+    logits = rnd(B, 1, H, W, seed=1, scale=3.0)
+    logits[0, 0, 0, :4] = torch.tensor([25.0, -25.0, 110.0, -110.0])
+    x = (torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(2)) < 0.3).float()
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.0, 1.0])
+    mu, lv = rnd(B, L, seed=3), rnd(B, L, seed=4) * 0.5
+    ld, xd, md, vd = dev(logits).to(dtype), dev(x), dev(mu), dev(lv)
+    one = torch.tensor(1.0, device="cuda")
+    ref_losses = ops.elbo_fwd(ld, xd, md, vd, 0.5, False)
+    ref_dl, ref_dmu, ref_dlv = ops.elbo_bwd(ld, xd, md, vd, one, 0.5, False)
+    losses, dl, dmu, dlv = ops.elbo_fused(ld, xd, md, vd, 0.5, False)
+    ltol = 2e-6 if dtype == torch.float32 else 5e-5   # bf16 path: MUFU log / exp
+    for i in range(3):
+        assert abs(float(losses[i]) - float(ref_losses[i])) <= ltol * abs(float(ref_losses[i])) + 1e-7
+    gtol = 1e-6 if dtype == torch.float32 else 2e-3   # one bf16 rounding of nearly equal values
+    assert rel_err(dl.float().cpu(), ref_dl.float().cpu().double()) <= gtol
+    assert torch.equal(dl[0, 0, 0, 2:4].float().cpu(), ref_dl[0, 0, 0, 2:4].float().cpu())  # saturated: exactly 0 / clamp
+    assert rel_err(dmu.cpu(), ref_dmu.cpu().double()) <= 1e-6 and rel_err(dlv.cpu(), ref_dlv.cpu().double()) <= 1e-6
+    # upstream gradient: 1 leaves the buffers untouched, 1.7 scales them in place
+    keep = dl.clone()
+    ops.elbo_scale_grads(one, dl, dmu, dlv)
+    assert torch.equal(dl, keep)
+    ops.elbo_scale_grads(torch.tensor(1.7, device="cuda"), dl, dmu, dlv)
+    ref_dl, ref_dmu, ref_dlv = ops.elbo_bwd(ld, xd, md, vd, torch.tensor(1.7, device="cuda"), 0.5, False)
+    assert rel_err(dl.float().cpu(), ref_dl.float().cpu().double()) <= max(gtol, 4e-3 if dtype != torch.float32 else 0)
+    assert rel_err(dmu.cpu(), ref_dmu.cpu().double()) <= 1e-6
+    # probabilities as input (hand-built ModelOutput)
+    pd = torch.sigmoid(ld.float())
+    lp, dp, _, _ = ops.elbo_fused(pd, xd, md, vd, 0.5, True)
+    rp = ops.elbo_fwd(pd, xd, md, vd, 0.5, True)
+    rdp, _, _ = ops.elbo_bwd(pd, xd, md, vd, one, 0.5, True)
+    assert abs(float(lp[0]) - float(rp[0])) <= 2e-6 * abs(float(rp[0])) + 1e-7
+    assert rel_err(dp.cpu(), rdp.cpu().double()) <= 1e-6
+
+
+def test_elbo_autograd_second_backward_and_scaled_grad(tv):
+    """ElboFn: the cached one-pass gradients serve the first backward (any upstream gradient);
+    a second backward through a retained graph recomputes them."""
+    from torch_vae_b200 import engine
+    B, L, H, W = 4, 10, 16, 16
+    logits = dev(rnd(B, 1, H, W, seed=5, scale=2.0)).requires_grad_(True)
+    x = dev((torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(6)) < 0.3).float())
+    mu, lv = dev(rnd(B, L, seed=7)).requires_grad_(True), dev(rnd(B, L, seed=8) * 0.5).requires_grad_(True)
+    loss, _ = engine.ElboFn.apply(logits, x, mu, lv, 0.7, False)
+    (loss * 3.0).backward(retain_graph=True)
+    g1 = [t.grad.clone() for t in (logits, mu, lv)]
+    for t in (logits, mu, lv):
+        t.grad = None
+    (loss * 3.0).backward()
+    for a, t in zip(g1, (logits, mu, lv)):
+        assert rel_err(t.grad.cpu(), a.cpu().double()) <= 1e-6
+    lr = logits.detach().cpu().clone().requires_grad_(True)
+    mr, vr = mu.detach().cpu().clone().requires_grad_(True), lv.detach().cpu().clone().requires_grad_(True)
+    ref = F.binary_cross_entropy(torch.sigmoid(lr), x.cpu()) + 0.7 * (-0.5 * torch.mean(torch.sum(1 + vr - mr**2 - torch.exp(vr), dim=-1)))
+    (ref * 3.0).backward()
+    assert rel_err(g1[0].cpu(), lr.grad) <= 1e-5 and rel_err(g1[1].cpu(), mr.grad) <= 1e-5 and rel_err(g1[2].cpu(), vr.grad) <= 1e-5
+    with torch.no_grad():
+        l2, _ = engine.ElboFn.apply(logits, x, mu, lv, 0.7, False)
+    assert abs(float(l2) - float(ref)) <= 1e-5 * abs(float(ref))
+
+
 def test_sigmoid_and_backward(tv):
     ops = tv.ops
     l = rnd(4, 1, 8, 8, seed=1, scale=4.0)

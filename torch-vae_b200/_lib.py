@@ -75,6 +75,8 @@ PROTOTYPES = {
     "vae_reparam_bwd": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp],
     "vae_elbo_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _i, _vp],
     "vae_elbo_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _i, _vp],
+    "vae_elbo_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _f, _i, _i, _vp],
+    "vae_elbo_scale_grads": [_vp, _vp, _vp, _vp, _ll, _ll, _i, _vp],
     "vae_sigmoid": [_vp, _vp, _ll, _i, _vp],
     "vae_sigmoid_bwd": [_vp, _vp, _vp, _ll, _i, _i, _vp],
     "vae_roll_transform": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _ull, _ull, _vp],

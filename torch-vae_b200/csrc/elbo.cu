@@ -124,6 +124,153 @@ elbo_bwd_kernel(const T* __restrict__ logits, const float* __restrict__ target,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward and gradient in ONE pass (north-star item 2): the loss is the root of the graph, so
+// dlogits = (p - x) / n (clamp / saturation emulated), dmu and dlogvar are known as soon as the
+// logits are read.  Bytes per element: logits + target in, dlogits out (3*H*W*sizeof
+// with an fp32 target: 2 + 4 + 2 B in bf16).  The gradients are written for an upstream grad of 1;
+// elbo_scale_grads_kernel rescales them in place only when the actual grad differs.
+// FAST (bf16 path, tolerance 2e-2): MUFU-based exp / log / reciprocal -- four special-function
+// ops per element instead of ~60 instructions of exact libm code, which made the exact kernel
+// issue-bound at 1.7 TB/s.  The clamps and the fp32 saturation points are the same (p rounds to
+// 1 for logit > 17.3 and log(0) = -inf is clamped to -100 in both).  The fp32 instantiation keeps
+// the exact functions of the two-kernel path (1e-5 parity).
+// ---------------------------------------------------------------------------------------------
+template <bool FAST>
+__device__ __forceinline__ void elbo_point(float v, float t, int input_is_prob, float gn, float& bce, float& d) {
+  if (FAST && !input_is_prob) {
+    const float e = __expf(-v);
+    const float p = __frcp_rn(1.0f + e);
+    const float om = 1.0f - p;
+    const float l1 = fmaxf(__logf(om), -100.0f), l0 = fmaxf(__logf(p), -100.0f);
+    bce = (t - 1.0f) * l1 - t * l0;
+    const float pq = p * om, dd = gn * (p - t);
+    d = pq >= 1e-12f ? dd : dd * pq * 1e12f;
+  } else {
+    const float p = prob_of(v, input_is_prob);
+    bce = bce_term(p, t);
+    const float pq = p * (1.0f - p);
+    const float dd = gn * (p - t) / fmaxf(pq, 1e-12f);
+    d = input_is_prob ? dd : dd * pq;
+  }
+}
+
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256)
+elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target, const float* __restrict__ mu,
+                  const float* __restrict__ logvar, float* __restrict__ losses, double* __restrict__ scratch,
+                  T* __restrict__ dlogits, float* __restrict__ dmu, float* __restrict__ dlogvar, long long n_elem,
+                  int B, int L, float kld_weight, int input_is_prob) {
+  __shared__ double red[2][8];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const float gn = 1.0f / (float)n_elem;
+  float bce = 0.0f;
+  const long long n_vec = n_elem / 8;
+  // two independent 8-element vectors in flight per thread
+  for (long long i = tid; i < n_vec; i += 2 * nthreads) {
+    const long long i1 = i + nthreads;
+    const bool two = i1 < n_vec;
+    Vec8<T> lg0, lg1;
+    Vec8<float> tg0, tg1;
+    lg0.load(logits + i * 8);
+    tg0.load(target + i * 8);
+    if (two) {
+      lg1.load(logits + i1 * 8);
+      tg1.load(target + i1 * 8);
+    }
+    float part = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float b_, d_;
+      elbo_point<FAST>(lg0.v[k], tg0.v[k], input_is_prob, gn, b_, d_);
+      part += b_;
+      lg0.v[k] = d_;
+    }
+    lg0.store(dlogits + i * 8);
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float b_, d_;
+        elbo_point<FAST>(lg1.v[k], tg1.v[k], input_is_prob, gn, b_, d_);
+        part += b_;
+        lg1.v[k] = d_;
+      }
+      lg1.store(dlogits + i1 * 8);
+    }
+    bce += part;
+  }
+  for (long long i = n_vec * 8 + tid; i < n_elem; i += nthreads) {
+    float b_, d_;
+    elbo_point<FAST>(to_f(logits[i]), target[i], input_is_prob, gn, b_, d_);
+    bce += b_;
+    dlogits[i] = from_f<T>(d_);
+  }
+
+  float kl = 0.0f;
+  const long long n_lat = (long long)B * L;
+  const float kb = kld_weight / (float)B;
+  for (long long i = tid; i < n_lat; i += nthreads) {
+    const float m = mu[i], lv = logvar[i], ev = expf(lv);
+    kl += 1.0f + lv - m * m - ev;
+    dmu[i] = kb * m;
+    dlogvar[i] = kb * 0.5f * (ev - 1.0f);
+  }
+
+  double dbce = warp_sum((double)bce), dkl = warp_sum((double)kl);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = dbce;
+    red[1][warp] = dkl;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      s0 += red[0][w];
+      s1 += red[1][w];
+    }
+    atomicAdd(&scratch[0], s0);
+    atomicAdd(&scratch[1], s1);
+    __threadfence();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(&scratch[2]);
+    unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      double t0 = atomicAdd(&scratch[0], 0.0), t1 = atomicAdd(&scratch[1], 0.0);
+      float recon = (float)(t0 / (double)n_elem);
+      float kld = (float)(-0.5 * t1 / (double)B);
+      losses[0] = recon + kld_weight * kld;
+      losses[1] = recon;
+      losses[2] = -kld;
+    }
+  }
+}
+
+// in-place rescale of the cached gradients by the upstream grad; exits at once when it is 1
+template <typename T>
+__global__ void __launch_bounds__(256)
+elbo_scale_grads_kernel(const float* __restrict__ gscale, T* __restrict__ dlogits, float* __restrict__ dmu,
+                        float* __restrict__ dlogvar, long long n_elem, long long n_lat) {
+  const float g = *gscale;
+  if (g == 1.0f) return;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long n_vec = n_elem / 8;
+  for (long long i = tid; i < n_vec; i += nthreads) {
+    Vec8<T> v;
+    v.load(dlogits + i * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] *= g;
+    v.store(dlogits + i * 8);
+  }
+  for (long long i = n_vec * 8 + tid; i < n_elem; i += nthreads) dlogits[i] = from_f<T>(to_f(dlogits[i]) * g);
+  for (long long i = tid; i < n_lat; i += nthreads) {
+    dmu[i] *= g;
+    dlogvar[i] *= g;
+  }
+}
+
 static int elbo_grid(long long n_elem) {
   long long blocks = (n_elem / 8 + 255) / 256;
   long long cap = (long long)sm_count() * 8;
@@ -172,4 +319,47 @@ extern "C" int vae_elbo_bwd(const void* logits, const float* target, const float
                                                  (float*)dlogits, dmu, dlogvar, n_elem, B, L,
                                                  kld_weight, input_is_prob);
   return check_launch("elbo_bwd");
+}
+
+/* vae_elbo_fwd and vae_elbo_bwd in one pass for an upstream gradient of 1: losses as vae_elbo_fwd,
+ * dlogits / dmu / dlogvar as vae_elbo_bwd with *gscale == 1.  vae_elbo_scale_grads applies the
+ * actual upstream gradient afterwards (a no-op launch when it is 1).
+ * replaces: models.py:208-216 and their autograd nodes (train.py:650) */
+extern "C" int vae_elbo_fused(const void* logits, const float* target, const float* mu, const float* logvar,
+                              float* losses, double* scratch, void* dlogits, float* dmu, float* dlogvar,
+                              long long n_elem, int B, int L, float kld_weight, int dtype, int input_is_prob,
+                              vae_stream_t stream) {
+  VAE_REQUIRE(logits && target && mu && logvar && losses && scratch && dlogits && dmu && dlogvar && n_elem > 0 &&
+                  B > 0 && L > 0,
+              "elbo_fused: bad argument");
+  cudaStream_t st = as_stream(stream);
+  VAE_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
+  // every thread walks the same number (+-1) of vector pairs; 4 blocks per SM stay resident
+  long long blocks = (n_elem / 16 + 255) / 256;
+  const long long cap = (long long)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int grid = (int)blocks;
+  if (dtype == VAE_BF16)
+    elbo_fused_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)logits, target, mu, logvar, losses, scratch,
+                                                        (bf16*)dlogits, dmu, dlogvar, n_elem, B, L, kld_weight,
+                                                        input_is_prob);
+  else
+    elbo_fused_kernel<float, false><<<grid, 256, 0, st>>>((const float*)logits, target, mu, logvar, losses, scratch,
+                                                          (float*)dlogits, dmu, dlogvar, n_elem, B, L, kld_weight,
+                                                          input_is_prob);
+  return check_launch("elbo_fused");
+}
+
+/* dlogits, dmu, dlogvar *= *gscale, in place; returns without touching memory when *gscale == 1 */
+extern "C" int vae_elbo_scale_grads(const float* gscale, void* dlogits, float* dmu, float* dlogvar, long long n_elem,
+                                    long long n_lat, int dtype, vae_stream_t stream) {
+  VAE_REQUIRE(gscale && dlogits && dmu && dlogvar && n_elem > 0 && n_lat > 0, "elbo_scale_grads: bad argument");
+  cudaStream_t st = as_stream(stream);
+  const int grid = elbo_grid(n_elem);
+  if (dtype == VAE_BF16)
+    elbo_scale_grads_kernel<bf16><<<grid, 256, 0, st>>>(gscale, (bf16*)dlogits, dmu, dlogvar, n_elem, n_lat);
+  else
+    elbo_scale_grads_kernel<float><<<grid, 256, 0, st>>>(gscale, (float*)dlogits, dmu, dlogvar, n_elem, n_lat);
+  return check_launch("elbo_scale_grads");
 }

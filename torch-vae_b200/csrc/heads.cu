@@ -53,55 +53,66 @@ struct WChunk {
 
 // ---------------------------------------------------------------------------------------------
 // out[m][n] += sum_{k in slice} A[m][k] * W(n, k).  A block owns 8 warps x ROWS rows and one K
-// slice whose weights it stages ONCE in shared memory as [N][ks_len]; a warp streams its rows'
-// 16-byte chunks (lanes stride K), accumulates over the whole slice in registers, and finishes
-// with warp-shuffle sums + one atomic per (row, n).  `out` is zeroed by the caller (memset node);
-// the slice-0 blocks add the bias.
+// slice whose weights it stages ONCE in shared memory; a warp streams its rows' 16-byte chunks
+// (lanes stride K), accumulates over the whole slice in registers, and finishes with warp-shuffle
+// sums + one atomic per (row, n).  The first chunk of every row is requested before the weights are
+// staged, so the two latencies overlap.  Shared layout [N][2][ks_len / 2]: the low and the high four
+// floats of a lane's 8-wide chunk live in separate planes, which makes both 16-byte reads of a warp
+// contiguous (no bank conflicts).  `out` is zeroed by the caller (memset node); the slice-0 blocks add
+// the bias.
 // ---------------------------------------------------------------------------------------------
 template <typename TA, int N, int ROWS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                      float* __restrict__ out, int M, int K, long long wsn, long long wsk, int ks_len) {
-  extern __shared__ __align__(16) float w_s[];  // [N][ks_len]
+  extern __shared__ __align__(16) float w_s[];  // [N][2][ks_len / 2]
   const int kslices = (K + ks_len - 1) / ks_len;
   const int ks = blockIdx.x % kslices, mb = blockIdx.x / kslices;
   const int k_begin = ks * ks_len, k_len = min(ks_len, K - k_begin);  // multiples of 8
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (mb * 8 + warp) * ROWS;
+  const int half_len = ks_len >> 1;
+  const TA* a_base = A + (long long)m0 * K + k_begin;
+  Vec8<TA> a[ROWS];
+  auto load_rows = [&](int kk) {
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      if (m0 + r < M && kk < k_len) a[r].load(a_base + (long long)r * K + kk);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[r].v[j] = 0.0f;
+      }
+    }
+  };
+  load_rows(lane * 8);
   if (wsk == 1 && (wsn & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < N * k_len; i += 1024) {
-      const int n = i / k_len, kk = i - n * k_len;
-      *reinterpret_cast<float4*>(&w_s[n * ks_len + kk]) =
-          *reinterpret_cast<const float4*>(W + n * wsn + k_begin + kk);
+    for (int kk = threadIdx.x * 4; kk < k_len; kk += 1024) {
+      const int dst = ((kk >> 2) & 1) * half_len + (kk >> 3) * 4;
+      float4 v[N];
+#pragma unroll
+      for (int n = 0; n < N; ++n) v[n] = *reinterpret_cast<const float4*>(W + n * wsn + k_begin + kk);
+#pragma unroll
+      for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(&w_s[n * ks_len + dst]) = v[n];
     }
   } else {
     for (int i = threadIdx.x; i < N * k_len; i += 256) {
       const int kk = i / N, n = i - kk * N;
-      w_s[n * ks_len + kk] = W[n * wsn + (long long)(k_begin + kk) * wsk];
+      w_s[n * ks_len + ((kk >> 2) & 1) * half_len + (kk >> 3) * 4 + (kk & 3)] = W[n * wsn + (long long)(k_begin + kk) * wsk];
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = (mb * 8 + warp) * ROWS;
   if (m0 >= M) return;
   float acc[ROWS][N];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[r][n] = 0.0f;
-  const TA* a_base = A + (long long)m0 * K + k_begin;
   for (int kk = lane * 8; kk < k_len; kk += 256) {
-    Vec8<TA> a[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      if (m0 + r < M) a[r].load(a_base + (long long)r * K + kk);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[r].v[j] = 0.0f;
-      }
-    }
+    if (kk != lane * 8) load_rows(kk);
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + kk]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + kk + 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + (kk >> 1)]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + half_len + (kk >> 1)]);
       const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
       for (int r = 0; r < ROWS; ++r)
@@ -127,7 +138,7 @@ skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, cons
 // row groups, partials are combined in shared memory, one atomic per (n, k) and block.
 // ---------------------------------------------------------------------------------------------
 template <typename TA, int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (N <= 11 ? 2 : 1))   // (N + 1) x 8 accumulators per thread
 skinny_wgrad_kernel(const float* __restrict__ D, const TA* __restrict__ A, float* __restrict__ G,
                     float* __restrict__ colsum, int M, int K, long long gsn, long long gsk, int m_per_block) {
   __shared__ __align__(16) float red[8][256];
@@ -204,7 +215,7 @@ template <typename TO, int N, bool PAIR>
 __global__ void __launch_bounds__(256)
 skinny_expand_kernel(const float* __restrict__ D0, const float* __restrict__ W0, const float* __restrict__ D1,
                      const float* __restrict__ W1, const float* __restrict__ bias, TO* __restrict__ out, int M, int K,
-                     long long wsn, long long wsk) {
+                     long long wsn, long long wsk, int accumulate) {
   constexpr int NP = (N + 3) & ~3;
   __shared__ __align__(16) float d_s[PAIR ? 2 : 1][kExpandRows][NP];
   const int m_begin = blockIdx.y * kExpandRows;
@@ -237,8 +248,14 @@ skinny_expand_kernel(const float* __restrict__ D0, const float* __restrict__ W0,
       }
     }
     Vec8<TO> acc;
+    if (accumulate) {
+      acc.load(o + (long long)r * K);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = b[j];
+      for (int j = 0; j < 8; ++j) acc.v[j] += b[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] = b[j];
+    }
 #pragma unroll
     for (int n = 0; n < N; ++n)
 #pragma unroll
@@ -288,10 +305,10 @@ extern "C" int vae_skinny_reduce(const void* A, const float* W, const float* bia
   VAE_REQUIRE(A && W && out && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL, "skinny_reduce: bad argument");
   cudaStream_t st = as_stream(stream);
   VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st));
-  constexpr int kRows = 8;
+  constexpr int kRows = 4;
   const int row_blocks = (M + 8 * kRows - 1) / (8 * kRows);
-  int ks_len = 1024;  // K slice per block: enough blocks to cover the SMs, at most 64 KB of weights
-  while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) < sm_count()) ks_len /= 2;
+  int ks_len = 1024;  // K slice per block: one wave of two blocks per SM where the shape allows it
+  while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) * 2 <= 2LL * sm_count()) ks_len /= 2;
   const int grid = row_blocks * ((K + ks_len - 1) / ks_len);
   const size_t smem = sizeof(float) * (size_t)N * ks_len;
   VAE_N_SWITCH(N, {
@@ -316,7 +333,7 @@ extern "C" int vae_skinny_wgrad(const float* D, const void* A, float* G, float* 
   VAE_REQUIRE(D && A && G && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL, "skinny_wgrad: bad argument");
   cudaStream_t st = as_stream(stream);
   const int kblocks = (K + 255) / 256;
-  int msplit = (2 * sm_count() + kblocks - 1) / kblocks;
+  int msplit = (N <= 11 ? 2 : 1) * sm_count() / kblocks;  // one wave of resident blocks
   if (msplit > (M + 15) / 16) msplit = (M + 15) / 16;
   if (msplit < 1) msplit = 1;
   int mpb = (M + msplit - 1) / msplit;
@@ -343,13 +360,25 @@ extern "C" int vae_skinny_expand(const float* D0, const float* W0, const float* 
   dim3 grid((K / 8 + 255) / 256, (M + kExpandRows - 1) / kExpandRows);
   const bool pair = D1 != nullptr;
   VAE_REQUIRE(!pair || W1 != nullptr, "skinny_expand: D1 without W1");
+  // two weight chunks in registers fit up to N = 10 (2 x 80); wider pairs run as two accumulating passes
   VAE_N_SWITCH(N, {
+    constexpr bool kPairFits = NN <= 10;
     if (dtO == VAE_BF16) {
-      if (pair) skinny_expand_kernel<bf16, NN, true><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (bf16*)out, M, K, wsn, wsk);
-      else skinny_expand_kernel<bf16, NN, false><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (bf16*)out, M, K, wsn, wsk);
+      bf16* o = (bf16*)out;
+      if (pair && kPairFits) {
+        skinny_expand_kernel<bf16, NN, kPairFits><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, o, M, K, wsn, wsk, 0);
+      } else {
+        skinny_expand_kernel<bf16, NN, false><<<grid, 256, 0, st>>>(D0, W0, nullptr, nullptr, bias, o, M, K, wsn, wsk, 0);
+        if (pair) skinny_expand_kernel<bf16, NN, false><<<grid, 256, 0, st>>>(D1, W1, nullptr, nullptr, nullptr, o, M, K, wsn, wsk, 1);
+      }
     } else {
-      if (pair) skinny_expand_kernel<float, NN, true><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (float*)out, M, K, wsn, wsk);
-      else skinny_expand_kernel<float, NN, false><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, (float*)out, M, K, wsn, wsk);
+      float* o = (float*)out;
+      if (pair && kPairFits) {
+        skinny_expand_kernel<float, NN, kPairFits><<<grid, 256, 0, st>>>(D0, W0, D1, W1, bias, o, M, K, wsn, wsk, 0);
+      } else {
+        skinny_expand_kernel<float, NN, false><<<grid, 256, 0, st>>>(D0, W0, nullptr, nullptr, bias, o, M, K, wsn, wsk, 0);
+        if (pair) skinny_expand_kernel<float, NN, false><<<grid, 256, 0, st>>>(D1, W1, nullptr, nullptr, nullptr, o, M, K, wsn, wsk, 1);
+      }
     }
   });
   return check_launch("skinny_expand");

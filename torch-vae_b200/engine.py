@@ -307,7 +307,11 @@ class DecodeFn(torch.autograd.Function):
 
 
 class ElboFn(torch.autograd.Function):
-    """loss = mean BCE(sigmoid(logits), x) + kld_weight * KL  (models.py:190-225)."""
+    """loss = mean BCE(sigmoid(logits), x) + kld_weight * KL  (models.py:190-225).
+
+    When a gradient will be asked for, forward runs the one-pass kernel that also writes
+    dlogits / dmu / dlogvar (the loss is the root of the graph); the first backward only
+    rescales them by the upstream gradient (a no-op launch for ``loss.backward()``)."""
 
     @staticmethod
     def forward(ctx, pred, target, mu, log_var, kld_weight: float, input_is_prob: bool):
@@ -316,7 +320,13 @@ class ElboFn(torch.autograd.Function):
         if target.dtype != torch.float32:
             target = target.float()
         mu, log_var = mu.contiguous(), log_var.contiguous()
-        losses = ops.elbo_fwd(pred, target, mu, log_var, kld_weight, input_is_prob)
+        fp32_latents = mu.dtype == torch.float32 and log_var.dtype == torch.float32
+        if fp32_latents and (ctx.needs_input_grad[0] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]):
+            losses, dpred, dmu, dlv = ops.elbo_fused(pred, target, mu, log_var, kld_weight, input_is_prob)
+            ctx.cached = (dpred, dmu, dlv)
+        else:
+            losses = ops.elbo_fwd(pred, target, mu, log_var, kld_weight, input_is_prob)
+            ctx.cached = None
         ctx.save_for_backward(pred, target, mu, log_var)
         ctx.kld_weight, ctx.input_is_prob = kld_weight, input_is_prob
         ctx.mark_non_differentiable(losses)
@@ -325,7 +335,12 @@ class ElboFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g, _unused):
-        pred, target, mu, log_var = ctx.saved_tensors
         g = g.to(torch.float32).contiguous()
-        dpred, dmu, dlv = ops.elbo_bwd(pred, target, mu, log_var, g, ctx.kld_weight, ctx.input_is_prob)
+        cached, ctx.cached = ctx.cached, None
+        if cached is not None:
+            dpred, dmu, dlv = cached
+            ops.elbo_scale_grads(g, dpred, dmu, dlv)
+        else:  # a second backward through a retained graph, or latents that were not fp32
+            pred, target, mu, log_var = ctx.saved_tensors
+            dpred, dmu, dlv = ops.elbo_bwd(pred, target, mu, log_var, g, ctx.kld_weight, ctx.input_is_prob)
         return dpred, None, dmu, dlv, None, None

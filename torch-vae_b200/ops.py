@@ -466,6 +466,31 @@ def elbo_bwd(logits, target, mu, logvar, gscale, kld_weight: float, input_is_pro
     return dlogits, dmu, dlv
 
 
+def elbo_fused(logits, target, mu, logvar, kld_weight: float, input_is_prob: bool):
+    """Losses and, for an upstream gradient of 1, (dlogits, dmu, dlogvar) in one pass."""
+    losses = torch.empty(3, dtype=torch.float32, device=logits.device)
+    scratch = torch.empty(4, dtype=torch.float64, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    dmu = torch.empty_like(mu)
+    dlv = torch.empty_like(mu)
+    B, L = mu.shape
+    rc = _L().vae_elbo_fused(
+        _p(logits), _f32(target, "input"), _f32(mu, "mu"), _f32(logvar, "log_var"), _p(losses), _p(scratch),
+        _p(dlogits), _p(dmu), _p(dlv), logits.numel(), B, L, kld_weight, code(logits),
+        1 if input_is_prob else 0, _stream(),
+    )
+    _lib.check(rc, "vae_elbo_fused")
+    return losses, dlogits, dmu, dlv
+
+
+def elbo_scale_grads(gscale, dlogits, dmu, dlv):
+    """In-place ``*= gscale`` (device scalar) of the cached ELBO gradients; free when it is 1."""
+    rc = _L().vae_elbo_scale_grads(
+        _f32(gscale, "grad"), _p(dlogits), _p(dmu), _p(dlv), dlogits.numel(), dmu.numel(), code(dlogits), _stream(),
+    )
+    _lib.check(rc, "vae_elbo_scale_grads")
+
+
 def sigmoid(logits):
     probs = torch.empty(logits.shape, dtype=torch.float32, device=logits.device)
     rc = _L().vae_sigmoid(_p(logits), _p(probs), logits.numel(), code(logits), _stream())
