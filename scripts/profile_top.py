@@ -10,7 +10,7 @@ gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 w_last = torch.randn(1, C, 3, 3, device=dev) / math.sqrt(9 * C); b_last = torch.zeros(1, device=dev)
 dl = (torch.randn(B, 1, H, W, device=dev) / (B * H * W)).bfloat16()
 vec = torch.stack([torch.ones(C), torch.zeros(C), torch.zeros(C), torch.ones(C)]).to(dev)
-for rep in range(2):  # first round warms up (attribute setup, tensor maps)
+for rep in range(int(os.environ.get("REPS", "2"))):  # first round warms up (attribute setup, tensor maps)
     ops.final_conv_fwd(y, vec, beta, w_last, b_last)
     ops.final_block_backward(dl, y, vec, gamma, beta, w_last, True)
     x64 = torch.randn(B, 64, 64, 32, device=dev).bfloat16()
@@ -23,5 +23,34 @@ for rep in range(2):  # first round warms up (attribute setup, tensor maps)
     a64 = torch.randn(B, 64, 64, 32, device=dev).bfloat16()
     ops.bn_apply_lrelu(a64, vec, beta)
     ops.bn_lrelu_backward(a64, x64, vec, gamma, beta, True)
+    # kernels revised late in round 1: edge layer, latent heads, one-pass ELBO, wide (tensor-bound) layers
+    x0 = (torch.rand(B, H, W, 1, device=dev) < 0.1).float()
+    w0 = torch.randn(32, 1, 3, 3, device=dev) / 3.0
+    cw0 = ops.ConvWeights(w0, torch.bfloat16, 2)
+    st0 = torch.empty(64, dtype=torch.float64, device=dev)
+    y0 = ops.conv_forward(x0, cw0, torch.zeros(32, device=dev), st0, Ci=1)      # enc.conv0 forward
+    ops.conv_weight_grad(x0, y0, 2, 1, 32, H, W)                                # enc.conv0 weight gradient
+    F_, L_ = 16384, 10
+    pre = torch.randn(B, F_, device=dev).bfloat16()
+    w_lf = torch.randn(L_, F_, device=dev) / 128.0
+    w_fl = torch.randn(F_, L_, device=dev) / 3.0
+    d0, d1 = torch.randn(B, L_, device=dev), torch.randn(B, L_, device=dev)
+    ops.skinny_reduce(pre, w_lf, torch.zeros(L_, device=dev), F_, 1, L_)        # fc_mu / fc_var
+    ops.skinny_reduce(pre, w_fl, None, 1, L_, L_)                               # dz
+    ops.skinny_expand(d0, w_fl, None, None, torch.zeros(F_, device=dev), 1, L_, F_, torch.bfloat16)   # decoder_input
+    ops.skinny_expand(d0, w_lf, d1, w_lf, None, F_, 1, F_, torch.bfloat16)      # d_pre of the two heads
+    ops.skinny_wgrad(d0, pre, (L_, F_), F_, 1, False)
+    ops.skinny_wgrad(d0, pre, (F_, L_), 1, L_, True)
+    lg = torch.randn(B, 1, H, W, device=dev).bfloat16()
+    ops.elbo_fused(lg, x0.view(B, 1, H, W), d0, d1 * 0.1, 1.0, False)
+    for (ci, co, hh) in ((64, 128, 32), (128, 256, 16)):
+        xa = torch.randn(B, hh, hh, ci, device=dev).bfloat16()
+        wa = torch.randn(co, ci, 3, 3, device=dev) / math.sqrt(9 * ci)
+        cwa = ops.ConvWeights(wa, torch.bfloat16, 2)
+        sta = torch.empty(2 * co, dtype=torch.float64, device=dev)
+        ya = ops.conv_forward(xa, cwa, torch.zeros(co, device=dev), sta)        # streamed-weight conv, mode 0
+        stb = torch.empty(2 * ci, dtype=torch.float64, device=dev)
+        ops.conv_data_grad(ya, cwa, torch.zeros(ci, device=dev), stb)           # mode 1 (ConvTranspose forward)
+        ops.conv_weight_grad(xa, ya, 2, ci, co, hh, hh)
 torch.cuda.synchronize()
 print("ok")

@@ -73,7 +73,7 @@ class EncodeFn(torch.autograd.Function):
     """encoder convs -> flatten -> fc_mu / fc_var  (models.py:107-145)."""
 
     @staticmethod
-    def forward(ctx, specs: List[ConvBlockSpec], dtype, training, sink, x, w_mu, b_mu, w_var, b_var, *conv_params):
+    def forward(ctx, specs: List[ConvBlockSpec], dtype, training, sink, cws, x, w_mu, b_mu, w_var, b_var, *conv_params):
         ctx.set_materialize_grads(False)
         ctx.sink = sink
         B, Cin = x.shape[0], x.shape[1]
@@ -86,7 +86,7 @@ class EncodeFn(torch.autograd.Function):
         saved = []
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
-            cw = ops.ConvWeights(w, dtype, 2)
+            cw = cws[i] if cws is not None else ops.ConvWeights(w, dtype, 2)
             stats = torch.empty(2 * sp.co, dtype=torch.float64, device=h.device) if training else None
             y = ops.conv_forward(h, cw, b, stats, Ci=sp.ci)
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
@@ -154,7 +154,7 @@ class EncodeFn(torch.autograd.Function):
             elif ctx.x_needs_grad:
                 dx = ops.nhwc_to_nchw(ops.conv_data_grad(dy, cw), torch.float32).view(B, sp.ci, Hi, Wi)
         ctx.saved = None
-        return (None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
+        return (None, None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
 
 
 class ReparamFn(torch.autograd.Function):
@@ -184,7 +184,7 @@ class DecodeFn(torch.autograd.Function):
     (models.py:147-175).  Returns (probabilities fp32, logits in compute dtype)."""
 
     @staticmethod
-    def forward(ctx, specs: List[ConvBlockSpec], feat, dtype, training, sink, z, w_in, b_in, w_last, b_last, *conv_params):
+    def forward(ctx, specs: List[ConvBlockSpec], feat, dtype, training, sink, cws, z, w_in, b_in, w_last, b_last, *conv_params):
         ctx.set_materialize_grads(False)
         ctx.sink = sink
         z = z.contiguous()
@@ -202,7 +202,7 @@ class DecodeFn(torch.autograd.Function):
         fused_last = False
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
-            cw = ops.ConvWeights(w, dtype, 2)
+            cw = cws[i] if cws is not None else ops.ConvWeights(w, dtype, 2)
             stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
             y = ops.conv_data_grad(h, cw, b, stats)  # ConvTranspose2d forward
             if i == len(specs) - 1 and ops.final_block_supported(B, y.shape[1], y.shape[2], sp.ci):
@@ -303,7 +303,7 @@ class DecodeFn(torch.autograd.Function):
             dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32)
         ctx.saved = None
         ctx.last = None
-        return (None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
+        return (None, None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
 
 
 class ElboFn(torch.autograd.Function):

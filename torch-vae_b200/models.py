@@ -162,16 +162,43 @@ class VanillaVAE(nn.Module):
             )
 
     # ---------------------------------------------------------------- public API
-    def encode(self, x: Tensor) -> EncoderOutput:
+    def _prepack(self, x: Tensor):
+        """Weight images of every tensor-core conv layer for this step, packed on a side stream
+        (ops.PackBatch).  Returns (encoder ConvWeights, decoder ConvWeights) or (None, None)."""
+        if self.compute_dtype != torch.bfloat16 or not x.is_cuda or not ops.umma_available():
+            return None, None
+        B, H, W = x.shape[0], x.shape[2], x.shape[3]
+        bwd = torch.is_grad_enabled()
+        batch = ops.PackBatch()
+        enc, dec = [], []
+        h, w = H, W
+        for i, blk in enumerate(self.encoder):
+            cw = ops.ConvWeights(blk[0].weight, self.compute_dtype, 2)
+            batch.add(cw, B, h, w, 0)
+            if bwd and (i > 0 or x.requires_grad):
+                batch.add(cw, B, h, w, 1)
+            enc.append(cw)
+            h, w = h // 2, w // 2
+        for blk in list(self.decoder) + [self.final_layer]:
+            cw = ops.ConvWeights(blk[0].weight, self.compute_dtype, 2)
+            h, w = h * 2, w * 2            # the ConvTranspose output is the high-resolution side
+            batch.add(cw, B, h, w, 1)
+            if bwd:
+                batch.add(cw, B, h, w, 0)
+            dec.append(cw)
+        batch.launch()
+        return enc, dec
+
+    def encode(self, x: Tensor, _cws=None) -> EncoderOutput:
         self._check_input(x)
         mu, log_var, pre = engine.EncodeFn.apply(
-            self._enc_specs(), self.compute_dtype, self.training, self._grad_sink, x,
+            self._enc_specs(), self.compute_dtype, self.training, self._grad_sink, _cws, x,
             self.fc_mu.weight, self.fc_mu.bias, self.fc_var.weight, self.fc_var.bias,
             *self._block_params(self.encoder),
         )
         return EncoderOutput(mu=mu, log_var=log_var, pre_latents=pre)
 
-    def _decode_both(self, z: Tensor):
+    def _decode_both(self, z: Tensor, _cws=None):
         if not z.is_cuda:
             raise RuntimeError("torch_vae_b200.VanillaVAE runs on CUDA only (no CPU fallback)")
         if z.dim() != 2 or z.shape[1] != self.latent_dim:
@@ -179,7 +206,7 @@ class VanillaVAE(nn.Module):
         blocks = list(self.decoder) + [self.final_layer]
         last = self.final_layer[3]
         return engine.DecodeFn.apply(
-            self._dec_specs(), self._feat, self.compute_dtype, self.training, self._grad_sink, z,
+            self._dec_specs(), self._feat, self.compute_dtype, self.training, self._grad_sink, _cws, z,
             self.decoder_input.weight, self.decoder_input.bias, last.weight, last.bias,
             *self._block_params(blocks),
         )
@@ -193,9 +220,11 @@ class VanillaVAE(nn.Module):
         return engine.ReparamFn.apply(mu, log_var, eps, self._rng_seed, None if eps is not None else self._rng_offset)
 
     def forward(self, x: Tensor, eps: Optional[Tensor] = None) -> ModelOutput:
-        encoding = self.encode(x)
+        self._check_input(x)
+        enc_cws, dec_cws = self._prepack(x)
+        encoding = self.encode(x, enc_cws)
         z = self.reparameterize(encoding["mu"], encoding["log_var"], eps)
-        probs, logits = self._decode_both(z)
+        probs, logits = self._decode_both(z, dec_cws)
         return ModelOutput(output=probs, input=x, encoded=encoding, latents=z, logits=logits)
 
     def loss(self, output: ModelOutput) -> LossOutput:

@@ -585,12 +585,13 @@ def umma_tma_eligible(B: int, Hi: int, Wi: int, Ci: int, Co: int, stride: int, m
     return bool(_L().vae_umma_tma_eligible(B, Hi, Wi, Ci, Co, stride, mode))
 
 
-def umma_tma_pack_weight(w: torch.Tensor, stride: int, mode: int) -> Optional[torch.Tensor]:
+def umma_tma_pack_weight(w: torch.Tensor, stride: int, mode: int, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     Co, Ci = w.shape[0], w.shape[1]
-    n = int(_L().vae_umma_tma_packed_elems(Ci, Co, stride, mode))
-    if n == 0:
-        return None
-    out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        n = int(_L().vae_umma_tma_packed_elems(Ci, Co, stride, mode))
+        if n == 0:
+            return None
+        out = torch.empty(n, dtype=torch.bfloat16, device=w.device)
     rc = _L().vae_umma_tma_pack_weight(_f32(w, "conv weight"), _p(out), Ci, Co, stride, mode, _stream())
     _lib.check(rc, "vae_umma_tma_pack_weight")
     return out
@@ -621,9 +622,10 @@ def set_umma_rw(enable: bool) -> bool:
     return bool(_L().vae_set_umma_rw(1 if enable else 0))
 
 
-def umma_rw_pack_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
+def umma_rw_pack_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     Co, Ci = w.shape[0], w.shape[1]
-    out = torch.empty(9 * Ci * Co, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty(9 * Ci * Co, dtype=torch.bfloat16, device=w.device)
     rc = _L().vae_umma_rw_pack_weight(_f32(w, "conv weight"), _p(out), Ci, Co, mode, _stream())
     _lib.check(rc, "vae_umma_rw_pack_weight")
     return out
@@ -654,7 +656,7 @@ class ConvWeights:
     images; everything else gets the CUDA-core K-major packs.  Layouts are built
     lazily, once per forward (the optimizer changes the master copy every step)."""
 
-    __slots__ = ("w", "dtype", "stride", "Co", "Ci", "_simt", "_umma", "_rw")
+    __slots__ = ("w", "dtype", "stride", "Co", "Ci", "_simt", "_umma", "_rw", "_batch")
 
     def __init__(self, w: torch.Tensor, dtype: torch.dtype, stride: int):
         self.w, self.dtype, self.stride = w, dtype, stride
@@ -662,6 +664,7 @@ class ConvWeights:
         self._simt = None
         self._umma = {}
         self._rw = {}
+        self._batch = None  # PackBatch whose side-stream launches fill the images held here
 
     def simt(self):
         if self._simt is None:
@@ -671,6 +674,8 @@ class ConvWeights:
     def rw(self, mode: int):
         if mode not in self._rw:
             self._rw[mode] = umma_rw_pack_weight(self.w, mode)
+        elif self._batch is not None:
+            self._batch.wait()
         return self._rw[mode]
 
     def umma(self, mode: int, tma: bool = False):
@@ -680,7 +685,81 @@ class ConvWeights:
         if key not in self._umma:
             pack = umma_tma_pack_weight if tma else umma_pack_weight
             self._umma[key] = pack(self.w, self.stride, mode)
+        elif self._batch is not None:
+            self._batch.wait()
         return self._umma[key]
+
+    def kind(self, B: int, Hi: int, Wi: int, mode: int) -> str:
+        """Which tcgen05 kernel serves this layer at activation extent [B, Hi, Wi] (the high-resolution
+        side): 'rw' (resident weights), 'tma' (streamed weights) or 'other'."""
+        if self.dtype != torch.bfloat16 or not umma_available():
+            return "other"
+        if umma_rw_eligible(B, Hi, Wi, self.Ci, self.Co, self.stride, mode):
+            return "rw"
+        if umma_tma_eligible(B, Hi, Wi, self.Ci, self.Co, self.stride, mode):
+            return "tma"
+        return "other"
+
+
+_AUX_STREAMS = {}
+
+
+def aux_stream(device) -> "torch.cuda.Stream":
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _AUX_STREAMS:
+        _AUX_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _AUX_STREAMS[idx]
+
+
+class PackBatch:
+    """All weight images of one step, packed on a side stream while the first (CUDA-core) layer runs.
+
+    The images depend only on the fp32 master weights, so their ~15 small launches need not sit on the
+    critical path between the layers.  Buffers are allocated on the caller's stream (they are freed
+    there), the side stream is forked from it (the optimizer step of the previous iteration precedes the
+    fork) and joined by ``wait()`` at the first use -- a fork/join pattern CUDA-graph capture accepts."""
+
+    def __init__(self):
+        self._jobs = []
+        self._event = None
+
+    def add(self, cw: ConvWeights, B: int, Hi: int, Wi: int, mode: int) -> None:
+        kind = cw.kind(B, Hi, Wi, mode)
+        if kind == "rw" and mode not in cw._rw:
+            out = torch.empty(9 * cw.Ci * cw.Co, dtype=torch.bfloat16, device=cw.w.device)
+            cw._rw[mode] = out
+            self._jobs.append(lambda: umma_rw_pack_weight(cw.w, mode, out=out))
+        elif kind == "tma" and (mode, True) not in cw._umma:
+            n = int(_L().vae_umma_tma_packed_elems(cw.Ci, cw.Co, cw.stride, mode))
+            if n == 0:
+                return
+            out = torch.empty(n, dtype=torch.bfloat16, device=cw.w.device)
+            cw._umma[(mode, True)] = out
+            self._jobs.append(lambda: umma_tma_pack_weight(cw.w, cw.stride, mode, out=out))
+        else:
+            return
+        cw._batch = self
+
+    def launch(self) -> None:
+        if not self._jobs:
+            return
+        dev = torch.cuda.current_device()
+        main = torch.cuda.current_stream(dev)
+        aux = aux_stream(dev)
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            for job in self._jobs:
+                job()
+            self._event = torch.cuda.Event()
+            self._event.record(aux)
+        self._jobs = []
+
+    def wait(self) -> None:
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            self._event = None
 
 
 def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None):
