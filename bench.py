@@ -459,6 +459,8 @@ def b200_arm(a):
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     e2e_state = {"i": 0}
+    e2e_loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_done = [torch.cuda.Event() for _ in range(2)]
 
     def prefetch(k):
         with torch.cuda.stream(copy_stream):
@@ -478,9 +480,14 @@ def b200_arm(a):
         xd = train_tf(dev_rolls[k], out=static_x if graph is not None else None)
         freed[k].record(cur)
         losses = run_step(xd)
-        losses_host[0:1].copy_(losses["loss"].detach().reshape(1), non_blocking=True)
-        cur.synchronize()  # the caller reads the loss every step (train.py:672)
-        return float(losses_host[0])
+        e2e_loss_host[k:k + 1].copy_(losses["loss"].detach().reshape(1), non_blocking=True)
+        loss_done[k].record(cur)
+        # The caller reads a loss every step (train.py:672), one step behind: step i's launches are queued
+        # before step i-1's loss is awaited, so the GPU never idles through a host round trip.
+        if e2e_state["i"] == 1:
+            return None
+        loss_done[k ^ 1].synchronize()
+        return float(e2e_loss_host[k ^ 1])
 
     for _ in range(3):
         e2e_step()
@@ -500,7 +507,7 @@ def b200_arm(a):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rolls_host.numel() * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / a.steps,
-                    "input": "uint8 rolls in pinned host memory -> H2D (prefetched one batch ahead) -> device RollTransform -> step -> loss D2H"},
+                    "input": "uint8 rolls in pinned host memory -> H2D (prefetched one batch ahead) -> device RollTransform -> step -> loss D2H (read every step, one step behind)"},
             "gpu_launches": launches_per_step * a.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,

@@ -593,6 +593,35 @@ __global__ void roll_transform_kernel(const uint8_t* __restrict__ rolls, float* 
   const uint8_t* src = rolls + (long long)b * Hs * Ws;
   float* dst = out + (long long)b * H * W;
   const int n = H * W;
+  if ((W & 7) == 0) {
+    // a thread owns 8 consecutive time steps of one pitch row: 8 byte loads, two 16-byte stores
+    const int wv = W >> 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * wv; i += gridDim.x * blockDim.x) {
+      const int h = i / wv, w0 = (i - h * wv) << 3;
+      const int hs = h + shift;  // pitch transpose inside the cropped window, zero fill
+      float v[8];
+      if (hs >= 0 && hs < H) {
+        const uint8_t* row = src + (long long)(oy + hs) * Ws + (ox + w0);
+        uint8_t raw[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) raw[k] = __ldg(row + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (float)raw[k] * (1.0f / 255.0f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (thr >= 0.0f) v[k] = v[k] > thr ? 1.0f : 0.0f;
+        v[k] = (v[k] - mean) * inv_std;
+      }
+      float4* o = reinterpret_cast<float4*>(dst + (long long)h * W + w0);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    return;
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int h = i / W, w = i % W;
     int hs = h + shift;  // pitch transpose inside the cropped window, zero fill
