@@ -346,13 +346,16 @@ struct BwdSmem {
   uint32_t* tmem_ptr;
 };
 
-constexpr size_t kBwdSmemBytes = 1024 + kFtSlots * kRowBytes + kA1Bufs * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
-                                 2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 8) + 16;
+constexpr size_t bwd_smem_bytes(int slots) {
+  return 1024 + (size_t)slots * kRowBytes + kA1Bufs * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
+         2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 8) + 16;
+}
+constexpr size_t kBwdSmemBytes = bwd_smem_bytes(kFtSlots);
 
-__device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
+__device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem, int slots) {   // barrier arrays stay sized for kFtSlots
   BwdSmem s;
   s.ring = smem;
-  s.a1 = s.ring + kFtSlots * kRowBytes;
+  s.a1 = s.ring + slots * kRowBytes;
   s.b1 = s.a1 + kA1Bufs * kRowBytes + 8192;
   s.dlsm = reinterpret_cast<float*>(s.b1 + 2048);
   s.cst = s.dlsm + 4 * 130;
@@ -370,17 +373,19 @@ __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem) {
 }
 
 // PASS: 1 = reduce (BN sums + weight / bias gradient of the final conv), 2 = apply (dy)
-template <int PASS>
-__global__ void __launch_bounds__(kFtThreads, 2)
+// SLOTS y rows in the ring, CTAS resident CTAs per SM (pass 2 is bound by issue latency, not by bytes in
+// flight: three CTAs with four slots each keep the same 12 rows per SM in flight with 50 % more warps)
+template <int PASS, int SLOTS, int CTAS>
+__global__ void __launch_bounds__(kFtThreads, CTAS)
 final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  BwdSmem S = carve_bwd(smem);
+  BwdSmem S = carve_bwd(smem, SLOTS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = P.H, RB = P.RB;
   if (warp == 9) {
     if (lane == 0) {
-      for (int s = 0; s < kFtSlots; ++s) {
+      for (int s = 0; s < SLOTS; ++s) {
         mbar_init(&S.full_bar[s], 1);
         mbar_init(&S.empty_bar[s], PASS == 1 ? 1 : kFtWorkers);  // pass 1: freed by the MMA commit; pass 2: by the workers
         mbar_init(&S.a2ready_bar[s], kFtWorkers);
@@ -443,19 +448,19 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       // global memory with one TMA tensor store (coalesced by the copy engine) and only afterwards
       // recycles the slot for a new load
       auto store_row = [&](uint32_t m) {
-        const uint32_t slot = m % kFtSlots;
-        mbar_wait(&S.a2ready_bar[slot], (m / kFtSlots) & 1u);
+        const uint32_t slot = m % SLOTS;
+        mbar_wait(&S.a2ready_bar[slot], (m / SLOTS) & 1u);
         tma_store_4d(&P.tmap_dy, S.ring + slot * kRowBytes, 0, 0, S.coord[2 * slot], S.coord[2 * slot + 1]);
         bulk_commit_group();
       };
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
         const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
         for (int i = 0; i < RB; ++i, ++n) {
-          const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u;
+          const uint32_t slot = n % SLOTS, ph = (n / SLOTS) & 1u;
           if (PASS == 1) {
             mbar_wait(&S.empty_bar[slot], ph ^ 1u);
-          } else if (n >= kFtSlots) {
-            store_row(n - kFtSlots);
+          } else if (n >= SLOTS) {
+            store_row(n - SLOTS);
             bulk_wait_group_read0();  // the store has finished reading the slot
           }
           if (PASS == 2) {
@@ -467,7 +472,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         }
       }
       if (PASS == 2) {
-        for (uint32_t m = n > kFtSlots ? n - kFtSlots : 0; m < n; ++m) store_row(m);
+        for (uint32_t m = n > SLOTS ? n - SLOTS : 0; m < n; ++m) store_row(m);
         bulk_wait_group0();
       }
     }
@@ -495,7 +500,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     for (uint32_t n = 0; n < total; ++n) {
       if (n + 1 < total) issue_da(n + 1);   // the next row's da runs under this row's elementwise math
       if (PASS == 1) {
-        const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, ab = n % kA1Bufs;
+        const uint32_t slot = n % SLOTS, ph = (n / SLOTS) & 1u, ab = n % kA1Bufs;
         mbar_wait(&S.a2ready_bar[slot], ph);
         tc_fence_after();
         if (elect_one()) {
@@ -557,7 +562,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         // row's ring slot.  With three tiles the wait is for work issued two rows ago, off the critical path.
         if (PASS == 1 && nn >= (uint32_t)kA1Bufs) {
           const uint32_t m = nn - kA1Bufs;
-          mbar_wait(&S.empty_bar[m % kFtSlots], (m / kFtSlots) & 1u);
+          mbar_wait(&S.empty_bar[m % SLOTS], (m / SLOTS) & 1u);
         }
         float w[16];
 #pragma unroll
@@ -588,7 +593,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
           fetch3(h0 + i + 3, pf);
           stage_a1(n + 1);
         }
-        const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u, buf = n & 1u, bph = (n >> 1) & 1u;
+        const uint32_t slot = n % SLOTS, ph = (n / SLOTS) & 1u, buf = n & 1u, bph = (n >> 1) & 1u;
         mbar_wait(&S.full_bar[slot], ph);
         mbar_wait(&S.d1full_bar[buf], bph);
         tc_fence_after();
@@ -972,16 +977,19 @@ extern "C" int vae_final_conv_fwd_tc(const void* y, const float* mean, const flo
 }
 
 static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
+  // pass 2: <4 slots, 3 CTAs per SM> measured 254 us against 297 us for <6 slots, 2 CTAs> on the B = 512 tensor
+  constexpr int kP2Slots = 4, kP2Ctas = 3;
   static bool attr1 = false, attr2 = false;
   if (pass == 1 && !attr1) {
-    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<1, kFtSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
     attr1 = true;
   }
   if (pass == 2 && !attr2) {
-    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<2, kP2Slots, kP2Ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bwd_smem_bytes(kP2Slots)));
     attr2 = true;
   }
-  int grid = 2 * sm_count();
+  int grid = (pass == 2 ? kP2Ctas : 2) * sm_count();
   if (grid > P.total_bands) grid = P.total_bands;
   if (pass == 1 && g_final_gemm_reduce) {
     static bool attr3 = false;
@@ -992,8 +1000,8 @@ static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
     final_bwd_reduce_gemm_kernel<<<grid, kFtThreads, kP1SmemBytes, st>>>(P);
     return check_launch("final_bwd_reduce_gemm");
   }
-  if (pass == 1) final_bwd_tc_kernel<1><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
-  else final_bwd_tc_kernel<2><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
+  if (pass == 1) final_bwd_tc_kernel<1, kFtSlots, 2><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
+  else final_bwd_tc_kernel<2, kP2Slots, kP2Ctas><<<grid, kFtThreads, bwd_smem_bytes(kP2Slots), st>>>(P);
   return check_launch(pass == 1 ? "final_bwd_reduce_tc" : "final_bwd_apply_tc");
 }
 
