@@ -551,8 +551,8 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       // the look-ahead row stays RAW (bf16 bits) until it enters the window one iteration later: a
       // conversion next to the load would make the thread wait for the load at once (ncu: 15 % of all
       // stall samples of the kernel sat on that conversion)
-      auto fetch3_raw = [&](int h, uint32_t* v) {
-        v[0] = v[1] = v[2] = 0u;
+      auto fetch3_raw = [&](int h, unsigned short* v) {
+        v[0] = v[1] = v[2] = 0;
         if (h >= 0 && h < H) {
           const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
           if (p > 0) v[0] = __ldg(row + p - 1);
@@ -561,7 +561,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
         }
       };
       float r0[3], r1[3], r2[3];
-      uint32_t pf[3];
+      unsigned short pf[3];   // 16-bit type: widening (and with it any use of the load) happens at the shift below
       if (half == 0) {
         fetch3(h0 - 1, r0);
         fetch3(h0, r1);
@@ -601,7 +601,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
           for (int k = 0; k < 3; ++k) {
             r0[k] = r1[k];
             r1[k] = r2[k];
-            r2[k] = __uint_as_float(pf[k] << 16);
+            r2[k] = __uint_as_float((uint32_t)pf[k] << 16);
           }
           fetch3_raw(h0 + i + 3, pf);
           stage_a1(n + 1);
@@ -816,8 +816,8 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
       // the look-ahead row stays RAW (bf16 bits) until it enters the window one iteration later: a
       // conversion next to the load would make the thread wait for the load at once (ncu: 15 % of all
       // stall samples of the kernel sat on that conversion)
-      auto fetch3_raw = [&](int h, uint32_t* v) {
-        v[0] = v[1] = v[2] = 0u;
+      auto fetch3_raw = [&](int h, unsigned short* v) {
+        v[0] = v[1] = v[2] = 0;
         if (h >= 0 && h < H) {
           const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
           if (p > 0) v[0] = __ldg(row + p - 1);
@@ -826,7 +826,7 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
         }
       };
       float r0[3], r1[3], r2[3];
-      uint32_t pf[3];
+      unsigned short pf[3];   // 16-bit type: widening (and with it any use of the load) happens at the shift below
       if (half == 0) {
         fetch3(h0 - 1, r0);
         fetch3(h0, r1);
@@ -863,7 +863,7 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
           for (int k = 0; k < 3; ++k) {
             r0[k] = r1[k];
             r1[k] = r2[k];
-            r2[k] = __uint_as_float(pf[k] << 16);
+            r2[k] = __uint_as_float((uint32_t)pf[k] << 16);
           }
           fetch3_raw(h0 + i + 3, pf);
           stage_a1(n + 1);
