@@ -85,6 +85,8 @@ class GradientBuckets:
             self.buckets.append(flat)
             self.pending.append(len(grp))
         self._count = list(self.pending)
+        self._staged = [([], []) for _ in self.buckets]
+        self._nccl_avg = self.is_cuda and dist.get_backend(process_group) == "nccl"
         self._works: List[Optional[object]] = [None] * len(self.buckets)
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.is_cuda else None
         self.bytes_per_step = 4 * sum(b.numel() for b in self.buckets)
@@ -99,6 +101,7 @@ class GradientBuckets:
         """Call before backward of every step."""
         self._count = list(self.pending)
         self._works = [None] * len(self.buckets)
+        self._staged = [([], []) for _ in self.buckets]
 
     def push(self, p, grad: torch.Tensor) -> None:
         """Gradient of ``p`` is ready (called from engine.py backward schedules)."""
@@ -106,13 +109,18 @@ class GradientBuckets:
         if ent is None:
             return
         bi = ent[0]
-        self.view(p).copy_(grad.reshape(p.shape))
+        dst, src = self._staged[bi]
+        dst.append(self.view(p))
+        src.append(grad.reshape(p.shape))
         self._count[bi] -= 1
         if self._count[bi] == 0:
             self._launch(bi)
 
     def _launch(self, bi: int) -> None:
         flat = self.buckets[bi]
+        dst, src = self._staged[bi]
+        torch._foreach_copy_(dst, src)  # the bucket's gradients in one multi-tensor launch, not one copy each
+        self._staged[bi] = ([], [])
         op = dist.ReduceOp.SUM
         if self.is_cuda:
             ready = torch.cuda.Event()
@@ -120,7 +128,10 @@ class GradientBuckets:
             self.comm_stream.wait_event(ready)
             with torch.cuda.stream(self.comm_stream):
                 if self.average and self.world > 1:
-                    flat.mul_(1.0 / self.world)  # pre-scale: sum of pre-scaled == mean
+                    if self._nccl_avg:
+                        op = dist.ReduceOp.AVG  # averaged inside the collective: no pre-scale launch
+                    else:
+                        flat.mul_(1.0 / self.world)  # pre-scale: sum of pre-scaled == mean
                 self._works[bi] = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
         else:
             if self.average and self.world > 1:
