@@ -79,9 +79,11 @@ extern "C" int vae_adamw_step(const vae_adamw_tensor* tensors, int count, double
       T.step[i] = e.step; T.n[i] = (int)e.n; T.lr[i] = e.lr; T.wd[i] = e.wd;
       if (e.n > max_n) max_n = e.n;
     }
-    int bx = (int)((max_n + 256 * 8 - 1) / (256 * 8));
+    // four elements per thread of the largest tensor: the loop is a chain of dependent loads, so few
+    // iterations per thread matter more than few blocks (blocks past a small tensor's end exit at once)
+    int bx = (int)((max_n + 256 * 4 - 1) / (256 * 4));
     if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
+    if (bx > 512) bx = 512;
     adamw_kernel<<<dim3(bx, c), 256, 0, st>>>(T, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
                                                (float)eps);
     int rc = check_launch("adamw");
