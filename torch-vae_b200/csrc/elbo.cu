@@ -136,9 +136,10 @@ elbo_bwd_kernel(const T* __restrict__ logits, const float* __restrict__ target,
 // 1 for logit > 17.3 and log(0) = -inf is clamped to -100 in both).  The fp32 instantiation keeps
 // the exact functions of the two-kernel path (1e-5 parity).
 // ---------------------------------------------------------------------------------------------
-template <bool FAST>
-__device__ __forceinline__ void elbo_point(float v, float t, int input_is_prob, float gn, float& bce, float& d) {
-  if (FAST && !input_is_prob) {
+template <bool FAST, bool PROB>
+__device__ __forceinline__ void elbo_point(float v, float t, float gn, float& bce, float& d) {
+  constexpr int input_is_prob = PROB ? 1 : 0;
+  if (FAST && !PROB) {
     const float e = __expf(-v);
     const float p = __frcp_rn(1.0f + e);
     const float om = 1.0f - p;
@@ -155,12 +156,12 @@ __device__ __forceinline__ void elbo_point(float v, float t, int input_is_prob, 
   }
 }
 
-template <typename T, bool FAST>
+template <typename T, bool FAST, bool PROB>   // PROB: `logits` holds probabilities (compile-time: no per-element branch)
 __global__ void __launch_bounds__(256)
 elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target, const float* __restrict__ mu,
                   const float* __restrict__ logvar, float* __restrict__ losses, double* __restrict__ scratch,
                   T* __restrict__ dlogits, float* __restrict__ dmu, float* __restrict__ dlogvar, long long n_elem,
-                  int B, int L, float kld_weight, int input_is_prob) {
+                  int B, int L, float kld_weight) {
   __shared__ double red[2][8];
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -183,7 +184,7 @@ elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float b_, d_;
-      elbo_point<FAST>(lg0.v[k], tg0.v[k], input_is_prob, gn, b_, d_);
+      elbo_point<FAST, PROB>(lg0.v[k], tg0.v[k], gn, b_, d_);
       part += b_;
       lg0.v[k] = d_;
     }
@@ -192,7 +193,7 @@ elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float b_, d_;
-        elbo_point<FAST>(lg1.v[k], tg1.v[k], input_is_prob, gn, b_, d_);
+        elbo_point<FAST, PROB>(lg1.v[k], tg1.v[k], gn, b_, d_);
         part += b_;
         lg1.v[k] = d_;
       }
@@ -202,7 +203,7 @@ elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target
   }
   for (long long i = n_vec * 8 + tid; i < n_elem; i += nthreads) {
     float b_, d_;
-    elbo_point<FAST>(to_f(logits[i]), target[i], input_is_prob, gn, b_, d_);
+    elbo_point<FAST, PROB>(to_f(logits[i]), target[i], gn, b_, d_);
     bce += b_;
     dlogits[i] = from_f<T>(d_);
   }
@@ -340,14 +341,17 @@ extern "C" int vae_elbo_fused(const void* logits, const float* target, const flo
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const int grid = (int)blocks;
-  if (dtype == VAE_BF16)
-    elbo_fused_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)logits, target, mu, logvar, losses, scratch,
-                                                        (bf16*)dlogits, dmu, dlogvar, n_elem, B, L, kld_weight,
-                                                        input_is_prob);
-  else
-    elbo_fused_kernel<float, false><<<grid, 256, 0, st>>>((const float*)logits, target, mu, logvar, losses, scratch,
-                                                          (float*)dlogits, dmu, dlogvar, n_elem, B, L, kld_weight,
-                                                          input_is_prob);
+#define VAE_ELBO_GO(T, FAST, PROB)                                                                               \
+  elbo_fused_kernel<T, FAST, PROB><<<grid, 256, 0, st>>>((const T*)logits, target, mu, logvar, losses, scratch,   \
+                                                         (T*)dlogits, dmu, dlogvar, n_elem, B, L, kld_weight)
+  if (dtype == VAE_BF16) {
+    if (input_is_prob) VAE_ELBO_GO(bf16, true, true);
+    else VAE_ELBO_GO(bf16, true, false);
+  } else {
+    if (input_is_prob) VAE_ELBO_GO(float, false, true);
+    else VAE_ELBO_GO(float, false, false);
+  }
+#undef VAE_ELBO_GO
   return check_launch("elbo_fused");
 }
 
