@@ -252,8 +252,9 @@ def test_one_pass_elbo_equals_forward_plus_backward(tv, dtype, shape):
     B, L, H, W = shape
     logits = rnd(B, 1, H, W, seed=1, scale=3.0)
     logits[0, 0, 0, :4] = torch.tensor([25.0, -25.0, 110.0, -110.0])
+    logits[0, 0, 0, 4:8] = torch.tensor([88.0, -88.0, 95.0, -95.0])  # subnormal sigmoid: the MUFU path must step aside
     x = (torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(2)) < 0.3).float()
-    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 0.0, 1.0])
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0])
     mu, lv = rnd(B, L, seed=3), rnd(B, L, seed=4) * 0.5
     ld, xd, md, vd = dev(logits).to(dtype), dev(x), dev(mu), dev(lv)
     one = torch.tensor(1.0, device="cuda")

@@ -130,20 +130,41 @@ elbo_bwd_kernel(const T* __restrict__ logits, const float* __restrict__ target,
 // logits are read.  Bytes per element: logits + target in, dlogits out (3*H*W*sizeof
 // with an fp32 target: 2 + 4 + 2 B in bf16).  The gradients are written for an upstream grad of 1;
 // elbo_scale_grads_kernel rescales them in place only when the actual grad differs.
-// FAST (bf16 path, tolerance 2e-2): MUFU-based exp / log / reciprocal -- four special-function
+// FAST (bf16 path, tolerance 2e-2): bare MUFU exp2 / log2 / reciprocal -- four special-function
 // ops per element instead of ~60 instructions of exact libm code, which made the exact kernel
 // issue-bound at 1.7 TB/s.  The clamps and the fp32 saturation points are the same (p rounds to
-// 1 for logit > 17.3 and log(0) = -inf is clamped to -100 in both).  The fp32 instantiation keeps
-// the exact functions of the two-kernel path (1e-5 parity).
+// 1 for logit > 17.3 and log(0) = -inf is clamped to -100 in both); vectors holding a |logit| > 80
+// (subnormal intermediates) take the exact code.  The fp32 instantiation keeps the exact functions
+// of the two-kernel path (1e-5 parity).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// FAST: bare MUFU ops, no range fix-ups.  Valid for |logit| <= 80, where no intermediate is subnormal;
+// elbo_vec8 routes anything larger to the exact code, so the saturation (p == 1 for logit > 17.3,
+// log(0) -> -100) and the clamp behave as in the reference everywhere.
 template <bool FAST, bool PROB>
 __device__ __forceinline__ void elbo_point(float v, float t, float gn, float& bce, float& d) {
   constexpr int input_is_prob = PROB ? 1 : 0;
   if (FAST && !PROB) {
-    const float e = __expf(-v);
-    const float p = __frcp_rn(1.0f + e);
+    const float e = mufu_ex2(v * -1.4426950408889634f);
+    const float p = mufu_rcp(1.0f + e);
     const float om = 1.0f - p;
-    const float l1 = fmaxf(__logf(om), -100.0f), l0 = fmaxf(__logf(p), -100.0f);
+    const float l1 = fmaxf(mufu_lg2(om) * 0.6931471805599453f, -100.0f);
+    const float l0 = fmaxf(mufu_lg2(p) * 0.6931471805599453f, -100.0f);
     bce = (t - 1.0f) * l1 - t * l0;
     const float pq = p * om, dd = gn * (p - t);
     d = pq >= 1e-12f ? dd : dd * pq * 1e12f;
@@ -154,6 +175,38 @@ __device__ __forceinline__ void elbo_point(float v, float t, float gn, float& bc
     const float dd = gn * (p - t) / fmaxf(pq, 1e-12f);
     d = input_is_prob ? dd : dd * pq;
   }
+}
+
+// eight elements in place (v: logits in, dlogits out); returns their BCE sum.  MUFU path unless one of
+// them is out of its range.
+template <bool FAST, bool PROB>
+__device__ __forceinline__ float elbo_vec8(float* v, const float* t, float gn) {
+  float part = 0.0f;
+  bool fast = false;
+  if (FAST && !PROB) {
+    float m = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(v[k]));
+    fast = m <= 80.0f;
+  }
+  if (fast) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float b_, d_;
+      elbo_point<true, false>(v[k], t[k], gn, b_, d_);
+      part += b_;
+      v[k] = d_;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float b_, d_;
+      elbo_point<false, PROB>(v[k], t[k], gn, b_, d_);
+      part += b_;
+      v[k] = d_;
+    }
+  }
+  return part;
 }
 
 template <typename T, bool FAST, bool PROB>   // PROB: `logits` holds probabilities (compile-time: no per-element branch)
@@ -180,30 +233,17 @@ elbo_fused_kernel(const T* __restrict__ logits, const float* __restrict__ target
       lg1.load(logits + i1 * 8);
       tg1.load(target + i1 * 8);
     }
-    float part = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float b_, d_;
-      elbo_point<FAST, PROB>(lg0.v[k], tg0.v[k], gn, b_, d_);
-      part += b_;
-      lg0.v[k] = d_;
-    }
+    float part = elbo_vec8<FAST, PROB>(lg0.v, tg0.v, gn);
     lg0.store(dlogits + i * 8);
     if (two) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float b_, d_;
-        elbo_point<FAST, PROB>(lg1.v[k], tg1.v[k], gn, b_, d_);
-        part += b_;
-        lg1.v[k] = d_;
-      }
+      part += elbo_vec8<FAST, PROB>(lg1.v, tg1.v, gn);
       lg1.store(dlogits + i1 * 8);
     }
     bce += part;
   }
   for (long long i = n_vec * 8 + tid; i < n_elem; i += nthreads) {
     float b_, d_;
-    elbo_point<FAST, PROB>(to_f(logits[i]), target[i], gn, b_, d_);
+    elbo_point<false, PROB>(to_f(logits[i]), target[i], gn, b_, d_);
     bce += b_;
     dlogits[i] = from_f<T>(d_);
   }
