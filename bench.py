@@ -29,11 +29,21 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HIDDEN = [32, 64, 128, 256]
-LATENT = 10
 METRIC = "vae_train_samples_per_sec"
 UNIT = "samples/s"
-FLOPS_PER_SAMPLE_TRAIN = {(128, 128): 0.9419e9}  # BASELINE.md §2 (FlopCounterMode on the reference)
+# BASELINE.json configs -> workloads.  "train" (configs[1]/[2]) is the one `metric` is quoted on and the
+# default; "wide_long" is configs[3]; "sample" is configs[4] (decode-only, its own metric name).
+WORKLOADS = {
+    "train": {"hidden": [32, 64, 128, 256], "latent": 10, "height": 128, "width": 128, "batch": 512,
+              "flops_train": 0.9419e9, "flops_decode": 0.1985e9},
+    "wide_long": {"hidden": [64, 128, 256, 512], "latent": 256, "height": 128, "width": 1024, "batch": 64,
+                  "flops_train": 30.728e9, "flops_decode": None},
+    "sample": {"hidden": [32, 64, 128, 256], "latent": 10, "height": 128, "width": 128, "batch": 4096,
+               "flops_train": 0.9419e9, "flops_decode": 0.1985e9},
+}
+HIDDEN = WORKLOADS["train"]["hidden"]
+LATENT = WORKLOADS["train"]["latent"]
+FLOPS_PER_SAMPLE_TRAIN = {}  # filled by apply_workload (FlopCounterMode on the reference)
 
 
 def parse():
@@ -42,16 +52,42 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="batch per GPU")
-    ap.add_argument("--height", type=int, default=128)
-    ap.add_argument("--width", type=int, default=128)
+    ap.add_argument("--workload", default="train", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="batch per GPU (default: the workload's)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW instead of the fused kernel")
     ap.add_argument("--cpu-batch", type=int, default=64)
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager (reference class on cuda) leg")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel CUDA-event breakdown here")
-    return ap.parse_args()
+    return apply_workload(ap.parse_args())
+
+
+def apply_workload(a):
+    global HIDDEN, LATENT
+    w = WORKLOADS[a.workload]
+    HIDDEN, LATENT = list(w["hidden"]), w["latent"]
+    a.batch = a.batch or w["batch"]
+    a.height = a.height or w["height"]
+    a.width = a.width or w["width"]
+    if (a.height, a.width) == (w["height"], w["width"]):
+        FLOPS_PER_SAMPLE_TRAIN[(a.height, a.width)] = w["flops_train"]
+    return a
+
+
+def activation_bytes(H, W, hidden, elem=2):
+    """Bytes per sample of every layer output the step keeps (bf16 NHWC), forward + as many gradients."""
+    n, h, w = 0, H, W
+    for c in hidden:
+        h, w = h // 2, w // 2
+        n += c * h * w
+    for c in list(reversed(hidden))[1:] + [hidden[0]]:
+        h, w = h * 2, w * 2
+        n += c * h * w
+    return 2 * (n * 2 + H * W) * elem
 
 
 def workload_name(a):
@@ -164,9 +200,9 @@ def algorithmic_cost(name, tag):
     if name == "vae_final_bwd_apply":  # reads y and dlogits, writes dy
         B, H, W, C, _, d = t[:6]
         return (B * H * W * (2 * C + 1) * _sz(d), 2 * B * H * W * 9 * C)
-    if name == "vae_bn_finalize_apply_lrelu":
+    if name == "vae_bn_finalize_apply_lrelu":  # integer args: n_pix, C, count, training, dtype
         n, C = t[:2]
-        d = t[5] if len(t) > 5 else 1
+        d = t[4] if len(t) > 4 else 1
         return (2 * n * C * _sz(d), 3 * n * C)
     if name in ("vae_skinny_reduce", "vae_skinny_wgrad", "vae_skinny_expand"):
         M, N, K = t[:3]
@@ -230,17 +266,79 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------
+# per-kernel CUDA-event breakdown and the roofline object of the dominant kernel
+# ----------------------------------------------------------------------------
+def kernel_breakdown(ops, step_fn, profile_json=None, n_prof=3):
+    """Every C-ABI launch of `n_prof` eager steps bracketed with CUDA events on the launching stream.
+    -> (rows sorted by time [(key, launches, ms)], kernel ms per step, launches per step, n_prof)."""
+    for _ in range(2):
+        step_fn()
+    torch.cuda.synchronize()
+    tl = ops.Timeline()
+    ops.set_timeline(tl)
+    l0 = ops.LAUNCHES
+    for _ in range(n_prof):
+        step_fn()
+    torch.cuda.synchronize()
+    launches_per_step = (ops.LAUNCHES - l0) // n_prof
+    ops.set_timeline(None)
+    summ = tl.summary()
+    rows = sorted(((k, n, ms) for k, (n, ms) in summ.items()), key=lambda r: -r[2])
+    total_kernel_ms = sum(r[2] for r in rows) / n_prof
+    if profile_json:
+        with open(profile_json, "w") as f:
+            json.dump({"per_step_kernel_ms": total_kernel_ms, "launches_per_step": launches_per_step,
+                       "kernels": [{"name": k[0], "args": list(k[1]), "launches_per_step": n / n_prof,
+                                    "ms_per_step": ms / n_prof, "share": ms / n_prof / total_kernel_ms,
+                                    "alg_bytes": algorithmic_cost(*k)[0], "alg_flops": algorithmic_cost(*k)[1]} for k, n, ms in rows]}, f, indent=1)
+    return rows, total_kernel_ms, launches_per_step, n_prof
+
+
+def roofline_of(ops, top_key, step_fn, reps, share):
+    tl2 = ops.Timeline(only=top_key)
+    ops.set_timeline(tl2)
+    for _ in range(reps):
+        step_fn()
+    torch.cuda.synchronize()
+    ops.set_timeline(None)
+    n_top, ms_top = tl2.summary()[top_key]
+    top_bytes, top_flops = algorithmic_cost(*top_key)
+    peaks = load_peaks()
+    avg_s = ms_top / n_top / 1e3
+    hbm_bound = top_bytes / (peaks["hbm_gbs"] * 1e9) >= top_flops / (peaks["bf16_tflops_sustained"] * 1e12)
+    if hbm_bound:
+        achieved, peak, unit = top_bytes / avg_s / 1e9, peaks["hbm_gbs"], "GB/s"
+    else:
+        achieved, peak, unit = top_flops / avg_s / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
+    return {"bound": "hbm" if hbm_bound else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "traffic": measured_traffic(*top_key), "kernel": top_key[0], "kernel_args": list(top_key[1]),
+            "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": top_bytes, "alg_flops_per_launch": top_flops,
+            "share_of_step_kernel_time": share,
+            "peak_source": peaks["source"] + (" (sustained bf16 figure: the kernel is timed inside a long step)" if not hbm_bound else "")}
+
+
+# ----------------------------------------------------------------------------
 # CPU arms
 # ----------------------------------------------------------------------------
 def cpu_reference_run(a, steps, warmup, batch):
-    """The reference's CPU train step (oracle port of train.py:635-656) on all host cores."""
+    """The reference's CPU train step (train.py:635-656) on all host cores: the UNMODIFIED reference class
+    from baseline/_ref (kind "reference") when it is installed, else the oracle port (kind "port")."""
+    from oracle import reference_driver as rd
     from oracle import vae_oracle as vo
 
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    params = vo.xavier_params(1, LATENT, a.height, a.width, HIDDEN, seed=0)
-    trainer = vo.CpuTrainStep(params, batch)
     x, _ = vo.synthetic_batch(batch, a.height, a.width, LATENT)
+    if rd.available():
+        trainer = rd.ReferenceTrainStep(a.height, a.width, HIDDEN, LATENT, batch, device="cpu")
+        kind = "reference"
+        what = ("midi_autoencoder.models.VanillaVAE from baseline/_ref driven as train.py:635-656"
+                + ("" if (a.height, a.width) == (32, 32) else " (literals models.py:33,166 generalised, SURVEY 8c)"))
+    else:
+        params = vo.xavier_params(1, LATENT, a.height, a.width, HIDDEN, seed=0)
+        trainer = vo.CpuTrainStep(params, batch)
+        kind = "port"
+        what = "oracle/vae_oracle.CpuTrainStep = reference train.py:635-656 with ATen CPU ops"
     for _ in range(warmup):
         trainer(x)
     times = []
@@ -249,10 +347,101 @@ def cpu_reference_run(a, steps, warmup, batch):
         trainer(x)
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": batch * steps / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of batch {batch} fp32 1x{a.height}x{a.width} (median {statistics.median(times)*1e3:.0f} ms/step), "
-                      "oracle/vae_oracle.CpuTrainStep = reference train.py:635-656 with ATen CPU ops",
+    return {"value": batch * steps / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{steps} steps of batch {batch} fp32 1x{a.height}x{a.width} (median {statistics.median(times)*1e3:.0f} ms/step), {what}",
             "ms_per_step": 1e3 * total / steps}
+
+
+def cpu_sample_run(a, steps, warmup, batch):
+    """Reference `sample()` (models.py:250-263) on the host cores, eval mode, no_grad."""
+    from oracle import reference_driver as rd
+    from oracle import vae_oracle as vo
+
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    if rd.available():
+        torch.manual_seed(0)
+        model = rd.build_model(a.height, a.width, HIDDEN, LATENT).eval()
+        fn = lambda: model.sample(batch, "cpu")
+        kind, what = "reference", "midi_autoencoder.models.VanillaVAE.sample from baseline/_ref (eval, no_grad)"
+    else:
+        params = vo.xavier_params(1, LATENT, a.height, a.width, HIDDEN, seed=0)
+        fn = lambda: vo.decode_only(params, torch.randn(batch, LATENT), a.height, a.width)
+        kind, what = "port", "oracle/vae_oracle.decode_only"
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} calls of sample({batch}) fp32 1x{a.height}x{a.width} (median {statistics.median(times)*1e3:.0f} ms), {what}",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def gpu_eager_run(a, dev, batch, steps=10, warmup=3):
+    """SURVEY.md section 2b / BASELINE configs[1] "vs reference torch eager": the UNMODIFIED reference module
+    on the SAME GPU through cuDNN / cuBLAS, fp32 (TF32 convolutions: torch's default) and bf16 autocast, timed
+    with CUDA events.  A second stated baseline beside cpu_baseline; None when baseline/_ref is absent."""
+    from oracle import reference_driver as rd
+    from oracle import vae_oracle as vo
+
+    if not rd.available():
+        return None
+    out = {"kind": "reference", "what": "midi_autoencoder.models.VanillaVAE from baseline/_ref on cuda (ATen eager: cuDNN/cuBLAS), "
+                                        "train.py:635-656 with torch.optim.AdamW over encoder+decoder", "batch": batch, "steps": steps}
+    x = vo.synthetic_batch(batch, a.height, a.width, LATENT)[0].to(dev)
+    for name, autocast in (("fp32_tf32conv", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            trainer = rd.ReferenceTrainStep(a.height, a.width, HIDDEN, LATENT, batch, device=dev, autocast=autocast)
+            for _ in range(warmup):
+                trainer(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                trainer(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms}
+            del trainer
+        except Exception as e:  # report, do not hide (e.g. out of memory at the wide config)
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        torch.cuda.empty_cache()
+    return out
+
+
+def gpu_eager_sample_run(a, dev, batch, steps=10, warmup=3):
+    from oracle import reference_driver as rd
+
+    if not rd.available():
+        return None
+    torch.manual_seed(0)
+    model = rd.build_model(a.height, a.width, HIDDEN, LATENT).to(dev).eval()
+    out = {"kind": "reference", "what": "midi_autoencoder.models.VanillaVAE.sample from baseline/_ref on cuda (eval, no_grad; "
+                                        "z drawn on the host as models.py:258 does)", "batch": batch, "steps": steps}
+    for name, autocast in (("fp32_tf32conv", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=autocast or torch.float32, enabled=autocast is not None):
+                for _ in range(warmup):
+                    model.sample(batch, dev)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    model.sample(batch, dev)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms}
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        torch.cuda.empty_cache()
+    return out
 
 
 def reference_arm(a):
@@ -260,14 +449,24 @@ def reference_arm(a):
     if rank != 0:
         return
     steps, warmup = max(1, min(a.steps, 30)), max(1, min(a.warmup, 5))
-    r = cpu_reference_run(a, steps, warmup, a.cpu_batch)
+    if a.workload == "sample":
+        r = cpu_sample_run(a, max(1, min(a.steps, 10)), 1, min(a.batch, 256))
+        metric, unit = "vae_sample_images_per_sec", "images/s"
+        note = f"CPU arm runs a bounded sample: sample({min(a.batch, 256)}) per step on {r['cores']} host cores"
+    else:
+        cpu_batch = a.cpu_batch if a.workload == "train" else min(a.cpu_batch, 8)
+        if a.workload != "train":
+            steps, warmup = min(steps, 5), 1
+        r = cpu_reference_run(a, steps, warmup, cpu_batch)
+        metric, unit = METRIC, UNIT
+        note = f"CPU arm runs a bounded sample: batch {cpu_batch} per step on {r['cores']} host cores"
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "note": f"CPU arm runs a bounded sample: batch {a.cpu_batch} per step on {r['cores']} host cores"},
+        "config": {"workload": workload_name(a), "note": note},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -306,8 +505,12 @@ def b200_arm(a):
               {"params": model.decoder.parameters(), "lr": lr, "name": "decoder"}]  # train.py:210-228
     if a.torch_adamw:
         opt = torch.optim.AdamW(groups, lr=lr, weight_decay=0.0, capturable=not a.no_graph)
+        sched = None
     else:
         opt = tv.FusedAdamW(groups, lr=lr, weight_decay=0.0)
+        # train.py:232-238: OneCycleLR over the groups' lrs, stepped per batch (:659); here advanced on the
+        # device so that the captured step follows it.  1000 epochs x 100 steps: the schedule never runs out.
+        sched = tv.optim.FusedOneCycleLR(opt, [g["lr"] for g in opt.param_groups], epochs=1000, steps_per_epoch=100)
     buckets = None
     if world > 1:
         buckets = GradientBuckets(model)
@@ -328,31 +531,13 @@ def b200_arm(a):
         if buckets is not None:
             buckets.finish()
         opt.step()  # :656
+        if sched is not None:
+            sched.step()  # :659
         return losses
 
     # -- per-kernel breakdown (eager, untimed): find the dominant kernel -----
-    for _ in range(2):
-        train_step(x_dev)
-    torch.cuda.synchronize()
-    tl = ops.Timeline()
-    ops.set_timeline(tl)
-    n_prof = 3
-    l0 = ops.LAUNCHES
-    for _ in range(n_prof):
-        train_step(x_dev)
-    torch.cuda.synchronize()
-    launches_per_step = (ops.LAUNCHES - l0) // n_prof
-    ops.set_timeline(None)
-    summ = tl.summary()
-    rows = sorted(((k, n, ms) for k, (n, ms) in summ.items()), key=lambda r: -r[2])
-    total_kernel_ms = sum(r[2] for r in rows) / n_prof
+    rows, total_kernel_ms, launches_per_step, n_prof = kernel_breakdown(ops, lambda: train_step(x_dev), a.profile_json if rank == 0 else None)
     top_key = rows[0][0]
-    if a.profile_json and rank == 0:
-        with open(a.profile_json, "w") as f:
-            json.dump({"per_step_kernel_ms": total_kernel_ms, "launches_per_step": launches_per_step,
-                       "kernels": [{"name": k[0], "args": list(k[1]), "launches_per_step": n / n_prof,
-                                    "ms_per_step": ms / n_prof, "share": ms / n_prof / total_kernel_ms,
-                                    "alg_bytes": algorithmic_cost(*k)[0], "alg_flops": algorithmic_cost(*k)[1]} for k, n, ms in rows]}, f, indent=1)
 
     # -- optional CUDA-graph capture of the whole step -------------------------
     use_graph = not a.no_graph  # NCCL all-reduces on the side stream are captured with the step
@@ -423,25 +608,8 @@ def b200_arm(a):
     value = B * world * a.steps / (ms_total / 1e3)
 
     # -- dominant kernel, bracketed live (eager so the events land on the launch stream)
-    tl2 = ops.Timeline(only=top_key)
-    ops.set_timeline(tl2)
-    for _ in range(max(3, min(a.steps, 10))):
-        train_step(x_dev)
-    torch.cuda.synchronize()
-    ops.set_timeline(None)
-    n_top, ms_top = tl2.summary()[top_key]
-    top_bytes, top_flops = algorithmic_cost(*top_key)
-    peaks = load_peaks()
-    avg_s = ms_top / n_top / 1e3
-    hbm_bound = top_bytes / (peaks["hbm_gbs"] * 1e9) >= top_flops / (peaks["bf16_tflops_sustained"] * 1e12)
-    if hbm_bound:
-        achieved, peak, unit = top_bytes / avg_s / 1e9, peaks["hbm_gbs"], "GB/s"
-    else:
-        achieved, peak, unit = top_flops / avg_s / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
-    roofline = {"bound": "hbm" if hbm_bound else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": measured_traffic(*top_key), "kernel": top_key[0], "kernel_args": list(top_key[1]),
-                "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": top_bytes, "alg_flops_per_launch": top_flops,
-                "share_of_step_kernel_time": rows[0][2] / n_prof / total_kernel_ms, "peak_source": peaks["source"]}
+    roofline = roofline_of(ops, top_key, lambda: train_step(x_dev), max(3, min(a.steps, 10)),
+                           rows[0][2] / n_prof / total_kernel_ms)
 
     # -- end to end through the public API with HOST buffers (e2e) ---------------
     # What a training loop around the drop-in does per batch (train.py:620-674): the batch sits in
@@ -502,9 +670,9 @@ def b200_arm(a):
             "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "height": H, "width": W, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world}", "cuda_graph": bool(graph is not None),
-                       "optimizer": ("torch.optim.AdamW" if a.torch_adamw else "FusedAdamW (one launch, torch.optim.AdamW state layout)")
-                                    + " over encoder+decoder groups (train.py:210-228), inside the timed step",
-                       "l2": f"per-step working set {(4.13e6*3*B)/1e6:.0f} MB of activations >> 126 MB L2 (inputs larger than L2)"},
+                       "optimizer": ("torch.optim.AdamW" if a.torch_adamw else "FusedAdamW + FusedOneCycleLR (device-resident lr/beta1, torch.optim.AdamW state layout)")
+                                    + " over encoder+decoder groups (train.py:210-238), optimizer.step and scheduler.step inside the timed step",
+                       "l2": f"per-step activation working set {activation_bytes(H, W, HIDDEN) * B / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rolls_host.numel() * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / a.steps,
@@ -514,8 +682,17 @@ def b200_arm(a):
             "roofline": roofline,
             "step_tflops": FLOPS_PER_SAMPLE_TRAIN.get((H, W), 0) * value / 1e12 if (H, W) in FLOPS_PER_SAMPLE_TRAIN else None,
         }
+        if world == 1 and not a.no_eager_baseline:
+            del graph
+            torch.cuda.empty_cache()
+            eager = gpu_eager_run(a, dev, B)
+            if eager is not None:
+                line["gpu_eager_baseline"] = eager
         if world == 1 and not a.no_cpu_baseline:
-            r = cpu_reference_run(a, 10, 2, a.cpu_batch)
+            if a.workload == "train":
+                r = cpu_reference_run(a, 10, 2, a.cpu_batch)
+            else:
+                r = cpu_reference_run(a, 3, 1, min(a.cpu_batch, 8))
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -528,10 +705,150 @@ def b200_arm(a):
         os._exit(0)
 
 
+def b200_sample_arm(a):
+    """BASELINE.json configs[4]: decoder-only sampling, z ~ N(0, I) -> piano-rolls (models.py:250-263),
+    batch 4096 on one B200, eval mode, no_grad.  `value`: z from the device Philox stream, images stay in
+    HBM.  `e2e`: the reference's own call shape -- z drawn on the HOST with torch.randn (models.py:258),
+    copied to the device, decoded, and the images copied back to pinned host memory."""
+    import torch_vae_b200 as tv
+    from torch_vae_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; torch_vae_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tv.load_library()
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    B, H, W = a.batch, a.height, a.width
+    torch.manual_seed(0)
+    model = tv.VanillaVAE(1, LATENT, (H, W), hidden_dims=list(HIDDEN), compute_dtype=dtype).to(dev).eval()
+    model.manual_seed(0, rank)
+
+    def sample_step():
+        with torch.no_grad():
+            return model.sample(B, dev, device_rng=True)
+
+    rows, total_kernel_ms, launches_per_step, n_prof = kernel_breakdown(ops, sample_step, a.profile_json if rank == 0 else None)
+    top_key = rows[0][0]
+
+    graph, static_out = None, None
+    if not a.no_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    sample_step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = sample_step()
+            torch.cuda.synchronize()
+        except Exception as e:
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed, running eagerly: {e}", file=sys.stderr)
+            graph = None
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return static_out
+        return sample_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for _ in range(max(3, a.warmup)):
+        run_step()
+    if rank == 0:
+        t_wait = time.time()
+        while not clocks.samples and time.time() - t_wait < 2.0:
+            time.sleep(0.01)
+    t0 = time.time()
+    ms_total = timed(run_step, a.steps)
+    t1 = time.time()
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    value = B * world * a.steps / (ms_total / 1e3)
+    roofline = roofline_of(ops, top_key, sample_step, max(3, min(a.steps, 10)), rows[0][2] / n_prof / total_kernel_ms)
+
+    # e2e: host z -> H2D -> decode -> D2H of the images
+    img_host = torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory()
+    z_host = torch.empty((B, LATENT), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        torch.randn((B, LATENT), out=z_host)  # models.py:258
+        with torch.no_grad():
+            img = model.decode(z_host.to(dev, non_blocking=True))
+        img_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller owns the images when the call returns
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    if rank == 0:
+        line = {
+            "metric": "vae_sample_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": "decoder-only sampling (BASELINE configs[4]): " + workload_name(a), "height": H, "width": W,
+                       "batch_per_gpu": B, "parallelism": f"replicas x{world}", "cuda_graph": graph is not None,
+                       "l2": f"{B * H * W * 32 * 2 / 1e6:.0f} MB full-resolution activation per step >> 126 MB L2"},
+            "clocks": clk,
+            "e2e": {"value": B * world * a.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": z_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": img_host.numel() * 4 * world, "ms_per_step": ms_e2e / a.steps,
+                    "input": "z = torch.randn on the host (models.py:258) -> H2D -> decode -> fp32 images D2H into pinned memory"},
+            "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
+            "roofline": roofline,
+            "step_tflops": WORKLOADS[a.workload]["flops_decode"] * value / 1e12 if (H, W) == (128, 128) else None,
+        }
+        if world == 1 and not a.no_eager_baseline:
+            del graph
+            torch.cuda.empty_cache()
+            eager = gpu_eager_sample_run(a, dev, B)
+            if eager is not None:
+                line["gpu_eager_baseline"] = eager
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_sample_run(a, 3, 1, min(B, 256))
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         reference_arm(a)
+    elif a.workload == "sample":
+        b200_sample_arm(a)
     else:
         b200_arm(a)
 

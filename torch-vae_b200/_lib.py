@@ -62,6 +62,8 @@ PROTOTYPES = {
     "vae_final_bwd_apply_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f,
                                _i, _vp],
     "vae_adamw_step": [_vp, _i, C.c_double, C.c_double, C.c_double, _vp],
+    "vae_adamw_step_dev": [_vp, _vp, _i, _vp, _i, C.c_double, _vp],
+    "vae_onecycle_step": [_vp, _vp, _vp, _i, _ll, C.c_double, _i, _i, _vp],
     "vae_heads_supported": [_i, _i],
     "vae_skinny_reduce": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_skinny_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],

@@ -1,19 +1,32 @@
 #!/usr/bin/env bash
-# Build libvae_b200.so (the C-ABI library) for sm_100a, in-tree.
+# Build libvae_b200.so (the C-ABI library) for sm_100a, in-tree.  Incremental: a source is recompiled
+# when it, a header next to it, or the public header is newer than its object (FORCE=1 rebuilds all).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="${HERE}/../libvae_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
-       --expt-relaxed-constexpr -Xptxas -v)
+       --expt-relaxed-constexpr -Xptxas -v -Wno-deprecated-gpu-targets)
 mkdir -p "${HERE}/obj"
-pids=()
-for f in runtime adamw elementwise elbo conv_simt conv_edge final_block final_block_tc heads gemm_simt conv_umma conv_umma_tma conv_umma_rw conv_umma_wgrad conv_wgrad_tma; do
-  "${NVCC}" "${FLAGS[@]}" -c "${HERE}/${f}.cu" -o "${HERE}/obj/${f}.o" > "${HERE}/obj/${f}.log" 2>&1 &
-  pids+=($!)
+newest_hdr=0
+for h in "${HERE}"/*.cuh "${HERE}/../../include/vae_b200.h" "${HERE}/build.sh"; do
+  t=$(stat -c %Y "$h"); [ "$t" -gt "$newest_hdr" ] && newest_hdr=$t
+done
+pids=(); names=()
+for src in "${HERE}"/*.cu; do
+  f="$(basename "${src}" .cu)"
+  obj="${HERE}/obj/${f}.o"
+  if [ "${FORCE:-0}" = "1" ] || [ ! -f "$obj" ] || [ "$(stat -c %Y "$src")" -gt "$(stat -c %Y "$obj")" ] || [ "$newest_hdr" -gt "$(stat -c %Y "$obj")" ]; then
+    "${NVCC}" "${FLAGS[@]}" -c "${src}" -o "${obj}" > "${HERE}/obj/${f}.log" 2>&1 &
+    pids+=($!); names+=("$f")
+  fi
 done
 fail=0
-for p in "${pids[@]}"; do wait "$p" || fail=1; done
-if [ "$fail" -ne 0 ]; then cat "${HERE}"/obj/*.log | grep -E "error|Error" -A3 | head -80; exit 1; fi
+for i in "${!pids[@]}"; do
+  if ! wait "${pids[$i]}"; then fail=1; echo "== ${names[$i]}.cu failed"; grep -E "error|Error" -A3 "${HERE}/obj/${names[$i]}.log" | head -40; rm -f "${HERE}/obj/${names[$i]}.o"; fi
+done
+[ "$fail" -ne 0 ] && exit 1
+# objects whose source was deleted must not be linked
+for obj in "${HERE}"/obj/*.o; do [ -f "${HERE}/$(basename "$obj" .o).cu" ] || rm -f "$obj"; done
 "${NVCC}" -shared -o "${OUT}" "${HERE}"/obj/*.o -lcudart
-echo "built ${OUT}"
+echo "built ${OUT} (${#pids[@]} recompiled: ${names[*]:-none})"

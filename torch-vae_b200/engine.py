@@ -69,6 +69,16 @@ def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     return vec, ops.bn_apply_lrelu(y, vec, beta)
 
 
+def _dst(sink, p):
+    """Where a parameter gradient is written: straight into its all-reduce bucket slice when a
+    gradient sink (parallel.GradientBuckets) is attached, else a fresh tensor (None)."""
+    return sink.view(p) if sink is not None else None
+
+
+def _dst3(sink, params):
+    return tuple(sink.view(p).view(-1) for p in params) if sink is not None else None
+
+
 class EncodeFn(torch.autograd.Function):
     """encoder convs -> flatten -> fc_mu / fc_var  (models.py:107-145)."""
 
@@ -121,15 +131,16 @@ class EncodeFn(torch.autograd.Function):
         F_ = pre.shape[1]
         if ops.heads_supported(F_, L):
             d_pre = ops.skinny_expand(dmu, w_mu, dlv, w_var, None, F_, 1, F_, pre.dtype)
-            g_w_mu, _ = ops.skinny_wgrad(dmu, pre, (L, F_), F_, 1, False)
-            g_w_var, _ = ops.skinny_wgrad(dlv, pre, (L, F_), F_, 1, False)
+            g_w_mu, _ = ops.skinny_wgrad(dmu, pre, (L, F_), F_, 1, False, out=_dst(sink, w_mu))
+            g_w_var, _ = ops.skinny_wgrad(dlv, pre, (L, F_), F_, 1, False, out=_dst(sink, w_var))
         else:
             d_pre = ops.linear_bwd_input(dmu, w_mu, out_dtype=pre.dtype)
             ops.linear_bwd_input(dlv, w_var, out=d_pre, accumulate=True)
-            g_w_mu, g_w_var = ops.linear_bwd_weight(dmu, pre), ops.linear_bwd_weight(dlv, pre)
+            g_w_mu = ops.linear_bwd_weight(dmu, pre, out=_dst(sink, w_mu))
+            g_w_var = ops.linear_bwd_weight(dlv, pre, out=_dst(sink, w_var))
         if dpre is not None:
             d_pre = d_pre + dpre.to(d_pre.dtype)
-        g_b_mu, g_b_var = ops.colsum(dmu), ops.colsum(dlv)
+        g_b_mu, g_b_var = ops.colsum(dmu, out=_dst(sink, b_mu)), ops.colsum(dlv, out=_dst(sink, b_var))
         if sink is not None:
             for p_, g_ in ((w_mu, g_w_mu), (b_mu, g_b_mu), (w_var, g_w_var), (b_var, g_b_var)):
                 sink.push(p_, g_)
@@ -141,8 +152,10 @@ class EncodeFn(torch.autograd.Function):
             sp = specs[i]
             h_in, y, vec, cw, Hi, Wi = saved[i]
             gamma, beta = conv_params[4 * i + 2], conv_params[4 * i + 3]
-            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
-            conv_grads[4 * i] = ops.conv_weight_grad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi)
+            w_i, b_i = conv_params[4 * i], conv_params[4 * i + 1]
+            dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training,
+                                                             outs=_dst3(sink, (gamma, beta, b_i)))
+            conv_grads[4 * i] = ops.conv_weight_grad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi, out=_dst(sink, w_i))
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
             conv_grads[4 * i + 3] = dbeta
@@ -154,6 +167,10 @@ class EncodeFn(torch.autograd.Function):
             elif ctx.x_needs_grad:
                 dx = ops.nhwc_to_nchw(ops.conv_data_grad(dy, cw), torch.float32).view(B, sp.ci, Hi, Wi)
         ctx.saved = None
+        if sink is not None:
+            # the sink owns the parameter gradients (it exposes them as p.grad after the all-reduce); handing
+            # them to autograd as well would let AccumulateGrad add into a bucket that is being reduced
+            return (None, None, None, None, None, dx, None, None, None, None, *([None] * len(conv_grads)))
         return (None, None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
 
 
@@ -252,7 +269,10 @@ class DecodeFn(torch.autograd.Function):
             # Conv2d(C->1) backward + LeakyReLU + BatchNorm backward in two passes over y
             _, y, vec, _ = saved[-1]
             gamma, beta = conv_params[4 * (n_blk - 1) + 2], conv_params[4 * (n_blk - 1) + 3]
-            fused = ops.final_block_backward(dlog, y, vec, gamma, beta, w_last, ctx.training)
+            b_conv = conv_params[4 * (n_blk - 1) + 1]
+            fused = ops.final_block_backward(dlog, y, vec, gamma, beta, w_last, ctx.training,
+                                             outs=_dst3(sink, (gamma, beta, b_conv)),
+                                             last_outs=(sink.view(w_last), sink.view(b_last)) if sink is not None else None)
             g_w_last, g_b_last = fused[4], fused[5]
             d_act = None
         else:
@@ -260,8 +280,8 @@ class DecodeFn(torch.autograd.Function):
             # final Conv2d(C -> 1): bias grad is a plain sum, done as two column sums
             n = dlog.numel()
             cols = 256 if n % 256 == 0 else 1
-            g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1))
-            g_w_last = ops.conv_weight_grad(act_last, dlog, 1, c_last, 1, H, W)
+            g_b_last = ops.colsum(ops.colsum(dlog.view(n // cols, cols)).view(cols, 1), out=_dst(sink, b_last))
+            g_w_last = ops.conv_weight_grad(act_last, dlog, 1, c_last, 1, H, W, out=_dst(sink, w_last))
             d_act = ops.conv_data_grad(dlog, cw3)
         if sink is not None:
             sink.push(w_last, g_w_last)
@@ -273,10 +293,11 @@ class DecodeFn(torch.autograd.Function):
             if fused_last and i == n_blk - 1:
                 dy, dgamma, dbeta, dbias = fused[:4]
             else:
-                dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training)
+                dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training,
+                                                                 outs=_dst3(sink, (gamma, beta, conv_params[4 * i + 1])))
             Hi, Wi = y.shape[1], y.shape[2]
             # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
-            conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi)
+            conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi, out=_dst(sink, conv_params[4 * i]))
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
             conv_grads[4 * i + 3] = dbeta
@@ -288,10 +309,10 @@ class DecodeFn(torch.autograd.Function):
         L_, F_ = z.shape[1], w_in.shape[0]
         skinny = ops.heads_supported(F_, L_)
         if skinny:
-            g_w_in, g_b_in = ops.skinny_wgrad(z, d_d, (F_, L_), 1, L_, True)
+            g_w_in, g_b_in = ops.skinny_wgrad(z, d_d, (F_, L_), 1, L_, True, out=_dst(sink, w_in), colsum_out=_dst(sink, b_in))
         else:
-            g_w_in = ops.linear_bwd_weight(d_d, z)
-            g_b_in = ops.colsum(d_d)
+            g_w_in = ops.linear_bwd_weight(d_d, z, out=_dst(sink, w_in))
+            g_b_in = ops.colsum(d_d, out=_dst(sink, b_in))
         if sink is not None:
             sink.push(w_in, g_w_in)
             sink.push(b_in, g_b_in)
@@ -303,6 +324,8 @@ class DecodeFn(torch.autograd.Function):
             dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32)
         ctx.saved = None
         ctx.last = None
+        if sink is not None:  # see EncodeFn.backward: the sink owns the parameter gradients
+            return (None, None, None, None, None, None, dz, None, None, None, None, *([None] * len(conv_grads)))
         return (None, None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
 
 

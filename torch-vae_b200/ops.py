@@ -109,6 +109,11 @@ def _p(t: Optional[torch.Tensor]):
         raise RuntimeError("torch_vae_b200 kernels need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("torch_vae_b200 kernels need contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream (one process per GPU, torchrun model):
+        # a tensor of another device would be dereferenced by the wrong GPU
+        raise RuntimeError(f"torch_vae_b200: tensor lives on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device() first")
     return t.data_ptr()
 
 
@@ -164,10 +169,10 @@ def conv_dgrad(dy, wt, bias, stride: int, stats=None):
     return dx
 
 
-def conv_wgrad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int):
+def conv_wgrad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int, out=None):
     """-> dw [Co,Ci,3,3] fp32 (reference OIHW layout)."""
     B = dy.shape[0]
-    dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+    dw = out if out is not None else torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
     rc = _L().vae_conv_wgrad(_p(x), _p(dy), _p(dw), B, Hi, Wi, Ci, Co, stride, code(x), code(dy), _stream())
     _lib.check(rc, "vae_conv_wgrad")
     return dw
@@ -214,8 +219,19 @@ def bn_apply_lrelu(y, vec, beta, slope: float = LRELU_SLOPE):
     return act
 
 
-def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = LRELU_SLOPE):
-    """-> (dy, dgamma, dbeta, dbias)."""
+def _small_outs(outs, C, device):
+    """(dgamma, dbeta, dbias) destinations: caller-provided fp32 [C] tensors (gradient-bucket views) or fresh ones."""
+    if outs is not None:
+        for t in outs:
+            if t.dtype != torch.float32 or t.numel() != C:
+                raise RuntimeError("gradient destination must be float32 with one element per channel")
+        return outs
+    small = torch.empty((3, C), dtype=torch.float32, device=device)
+    return small[0], small[1], small[2]
+
+
+def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = LRELU_SLOPE, outs=None):
+    """-> (dy, dgamma, dbeta, dbias); ``outs`` = optional (dgamma, dbeta, dbias) destinations."""
     C = y.shape[-1]
     n_pix = y.numel() // C
     lib = _L()
@@ -226,14 +242,14 @@ def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = 
     )
     _lib.check(rc, "vae_bn_lrelu_bwd_reduce")
     dy = torch.empty_like(y)
-    small = torch.empty((3, C), dtype=torch.float32, device=y.device)
+    dgamma, dbeta, dbias = _small_outs(outs, C, y.device)
     rc = lib.vae_bn_lrelu_bwd_apply(
         _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
-        _f32(gamma, "bn weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
-        small[2].data_ptr(), n_pix, C, slope, 1 if training else 0, code(y), _stream(),
+        _f32(gamma, "bn weight"), _p(dstats), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), n_pix, C, slope,
+        1 if training else 0, code(y), _stream(),
     )
     _lib.check(rc, "vae_bn_lrelu_bwd_apply")
-    return dy, small[0], small[1], small[2]
+    return dy, dgamma, dbeta, dbias
 
 
 # ------------------------------------------------- fused output block (models.py:76-82)
@@ -271,13 +287,15 @@ def final_conv_fwd(y, vec, beta, w_last, b_last, slope: float = LRELU_SLOPE):
     return logits, probs
 
 
-def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, slope: float = LRELU_SLOPE):
+def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, slope: float = LRELU_SLOPE,
+                         outs=None, last_outs=None):
     """-> (dy, dgamma, dbeta, dbias, dw_last, db_last): backward of Conv2d(C->1) + LeakyReLU +
-    BatchNorm in two passes over y (reduce, apply)."""
+    BatchNorm in two passes over y (reduce, apply).  ``outs`` = optional (dgamma, dbeta, dbias)
+    destinations, ``last_outs`` = optional (dw_last [1,C,3,3], db_last [1]) destinations."""
     B, H, W, C = y.shape
     lib = _L()
     dstats = torch.empty(2 * C + 1, dtype=torch.float64, device=y.device)
-    dw_last = torch.empty((1, C, 3, 3), dtype=torch.float32, device=y.device)
+    dw_last = last_outs[0] if last_outs is not None else torch.empty((1, C, 3, 3), dtype=torch.float32, device=y.device)
     mean, scale, rstd = vec[2].data_ptr(), vec[0].data_ptr(), vec[3].data_ptr()
     tc = final_tc_supported(y)
     if tc:
@@ -292,22 +310,22 @@ def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, s
         )
     _lib.check(rc, "vae_final_bwd_reduce")
     dy = torch.empty_like(y)
-    small = torch.empty((3, C), dtype=torch.float32, device=y.device)
-    db_last = torch.empty(1, dtype=torch.float32, device=y.device)
+    dgamma, dbeta, dbias = _small_outs(outs, C, y.device)
+    db_last = last_outs[1] if last_outs is not None else torch.empty(1, dtype=torch.float32, device=y.device)
     if tc:
         rc = lib.vae_final_bwd_apply_tc(
             _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
-            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
-            small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, _stream(),
+            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), _p(dgamma), _p(dbeta), _p(dbias),
+            _p(db_last), B, H, W, C, slope, 1 if training else 0, _stream(),
         )
     else:
         rc = lib.vae_final_bwd_apply(
             _p(dlogits), _p(y), mean, scale, _f32(beta, "bn bias"), rstd, _f32(gamma, "bn weight"),
-            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), small[0].data_ptr(), small[1].data_ptr(),
-            small[2].data_ptr(), _p(db_last), B, H, W, C, slope, 1 if training else 0, code(y), _stream(),
+            _f32(w_last, "final conv weight"), _p(dstats), _p(dy), _p(dgamma), _p(dbeta), _p(dbias),
+            _p(db_last), B, H, W, C, slope, 1 if training else 0, code(y), _stream(),
         )
     _lib.check(rc, "vae_final_bwd_apply")
-    return dy, small[0], small[1], small[2], dw_last, db_last
+    return dy, dgamma, dbeta, dbias, dw_last, db_last
 
 
 # ---------------------------------------------------------------- layout glue
@@ -356,13 +374,22 @@ def skinny_reduce(A, W, bias, wsn: int, wsk: int, N: int):
     return out
 
 
-def skinny_wgrad(D, A, g_shape, gsn: int, gsk: int, want_colsum: bool):
-    """G(n,k) = sum_m D[m,n] A[m,k] laid out as G.flat[n*gsn + k*gsk]; colsum[k] = sum_m A[m,k]."""
+def skinny_wgrad(D, A, g_shape, gsn: int, gsk: int, want_colsum: bool, out=None, colsum_out=None):
+    """G(n,k) = sum_m D[m,n] A[m,k] laid out as G.flat[n*gsn + k*gsk]; colsum[k] = sum_m A[m,k].
+    ``out`` / ``colsum_out``: optional destinations (gradient-bucket views); they are zeroed here."""
     M, K = A.shape
     N = D.shape[1]
-    buf = torch.zeros(N * K + (K if want_colsum else 0), dtype=torch.float32, device=A.device)
-    G = buf[: N * K].view(g_shape)
-    cs = buf[N * K:] if want_colsum else None
+    if out is not None:
+        G = out.view(g_shape)
+        G.zero_()
+        cs = None
+        if want_colsum:
+            cs = colsum_out if colsum_out is not None else torch.empty(K, dtype=torch.float32, device=A.device)
+            cs.zero_()
+    else:
+        buf = torch.zeros(N * K + (K if want_colsum else 0), dtype=torch.float32, device=A.device)
+        G = buf[: N * K].view(g_shape)
+        cs = buf[N * K:] if want_colsum else None
     rc = _L().vae_skinny_wgrad(_f32(D, "latent gradient"), _p(A), G.data_ptr(), cs.data_ptr() if want_colsum else None,
                                M, N, K, gsn, gsk, code(A), _stream())
     _lib.check(rc, "vae_skinny_wgrad")
@@ -396,17 +423,18 @@ def linear_bwd_input(dout, w, out=None, out_dtype=torch.float32, accumulate=Fals
     return gemm(dout, w, out, Bn, K, N, (N, 1), (K, 1), (K, 1), accumulate=accumulate)
 
 
-def linear_bwd_weight(dout, x):
+def linear_bwd_weight(dout, x, out=None):
     """dout[B,N]^T @ x[B,K] -> dw[N,K] fp32."""
     Bn, N = dout.shape
     K = x.shape[1]
-    dw = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty((N, K), dtype=torch.float32, device=x.device)
     return gemm(dout, x, dw, N, K, Bn, (1, N), (K, 1), (K, 1))
 
 
-def colsum(A):
+def colsum(A, out=None):
     M, N = A.shape
-    out = torch.empty(N, dtype=torch.float32, device=A.device)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=A.device)
     rc = _L().vae_colsum(_p(A), _p(out), M, N, code(A), _stream())
     _lib.check(rc, "vae_colsum")
     return out
@@ -793,21 +821,24 @@ def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
     return conv_dgrad(dy, cw.simt()[1], bias, cw.stride, stats)
 
 
-def conv_weight_grad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int):
+def conv_weight_grad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int, out=None):
     """dW [Co,Ci,3,3] fp32: tcgen05 kernel for bf16 tensor-core shaped layers, the
-    CUDA-core kernels otherwise (fp32 path, single-channel edge layers)."""
+    CUDA-core kernels otherwise (fp32 path, single-channel edge layers).  ``out``: optional
+    destination in the reference's OIHW layout (a gradient-bucket view)."""
+    if out is not None and (out.dtype != torch.float32 or out.numel() != Co * Ci * 9):
+        raise RuntimeError("conv_weight_grad: destination must be float32 [Co, Ci, 3, 3]")
     if x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and umma_available() and \
             _L().vae_wgrad_tma_eligible(dy.shape[0], Hi, Wi, Ci, Co, stride):
         B = dy.shape[0]
-        dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+        dw = out if out is not None else torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
         ws = torch.empty(9 * Co * Ci, dtype=torch.float32, device=dy.device)
         rc = _L().vae_conv_wgrad_tma(_p(x), _p(dy), _p(dw), _p(ws), B, Hi, Wi, Ci, Co, stride, _stream())
         _lib.check(rc, "vae_conv_wgrad_tma")
         return dw
     if x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and _L().vae_umma_wgrad_supported(Ci, Co):
         B = dy.shape[0]
-        dw = torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
+        dw = out if out is not None else torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
         rc = _L().vae_conv_wgrad_umma(_p(x), _p(dy), _p(dw), B, Hi, Wi, Ci, Co, stride, _stream())
         _lib.check(rc, "vae_conv_wgrad_umma")
         return dw
-    return conv_wgrad(x, dy, stride, Ci, Co, Hi, Wi)
+    return conv_wgrad(x, dy, stride, Ci, Co, Hi, Wi, out=out)

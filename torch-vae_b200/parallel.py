@@ -21,6 +21,13 @@ arrives its all-reduce is enqueued on a side stream (ordered after the producing
 kernels by an event), so NVLink traffic runs under the remaining backward
 kernels.  ``finish()`` joins the side stream and points every ``p.grad`` at its
 reduced bucket view.  The path shards with no other data-path collective.
+
+Ownership: while a sink is attached the backward schedules write each gradient
+straight into its bucket slice (no gather copy) and return ``None`` to autograd
+for the parameters, so ``AccumulateGrad`` never touches a bucket that is being
+reduced.  Consequently gradient ACCUMULATION over several backward passes is not
+supported with a sink: every backward overwrites the buckets (``begin()`` may be
+preceded by ``zero_grad`` with either ``set_to_none`` setting).
 """
 
 from __future__ import annotations
@@ -109,9 +116,11 @@ class GradientBuckets:
         if ent is None:
             return
         bi = ent[0]
-        dst, src = self._staged[bi]
-        dst.append(self.view(p))
-        src.append(grad.reshape(p.shape))
+        view = self.view(p)
+        if grad.data_ptr() != view.data_ptr():  # kernels normally write straight into the bucket slice (engine._dst)
+            dst, src = self._staged[bi]
+            dst.append(view)
+            src.append(grad.reshape(p.shape))
         self._count[bi] -= 1
         if self._count[bi] == 0:
             self._launch(bi)
@@ -119,7 +128,8 @@ class GradientBuckets:
     def _launch(self, bi: int) -> None:
         flat = self.buckets[bi]
         dst, src = self._staged[bi]
-        torch._foreach_copy_(dst, src)  # the bucket's gradients in one multi-tensor launch, not one copy each
+        if dst:  # gradients that were produced elsewhere: one multi-tensor copy, not one copy each
+            torch._foreach_copy_(dst, src)
         self._staged[bi] = ([], [])
         op = dist.ReduceOp.SUM
         if self.is_cuda:
