@@ -376,9 +376,9 @@ class CpuTrainStep:
             lr=lr, weight_decay=0.0,
         )
 
-    def __call__(self, x: Tensor):
+    def __call__(self, x: Tensor, eps: Optional[Tensor] = None):
         mu, log_var, pre, feat_shape = encode(self.P, self.Bf, x, True)
-        z = reparameterize(mu, log_var, torch.randn_like(mu))
+        z = reparameterize(mu, log_var, torch.randn_like(mu) if eps is None else eps)
         output = torch.sigmoid(decode_logits(self.P, self.Bf, z, feat_shape, True))
         for p in self.P.values():
             p.grad = None

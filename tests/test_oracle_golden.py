@@ -90,3 +90,37 @@ def test_fp64_oracle_close_to_fp32():
         # accumulated in the same module's weight gradient.
         floor = vo.grad_floor(r64["grads"], k)
         assert vo.rel_err(r32["grads"][k], r64["grads"][k], floor=floor) < 1e-4, k
+
+
+def test_philox_restatement_against_random123_known_answers():
+    """oracle/roll_transform_oracle.philox4x32_10 against the Random123 kat_vectors for philox4x32-10."""
+    from oracle import roll_transform_oracle as ro
+
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, want in kat:
+        assert ro.philox4x32_10(ctr, key) == want
+
+
+def test_roll_transform_oracle_semantics():
+    import numpy as np
+
+    from oracle import roll_transform_oracle as ro
+
+    rng = np.random.default_rng(0)
+    rolls = (rng.random((3, 128, 160)) < 0.1).astype(np.uint8) * 255
+    out, prm = ro.roll_transform(rolls, 128, 128, False, 0, -1.0, 0.5, 1.0, 0, 0)
+    assert prm == [(0, 16, 0)] * 3
+    assert np.array_equal(out[:, 0], rolls[:, :, 16:144].astype(np.float32) / np.float32(255) - np.float32(0.5))
+    out, prm = ro.roll_transform(rolls, 128, 128, True, 5, 0.5, 0.0, 1.0, 9, 4)
+    for b, (top, left, shift) in enumerate(prm):
+        assert top == 0 and 0 <= left <= 32 and -5 <= shift <= 5
+        win = (rolls[b, :, left:left + 128] > 127).astype(np.float32)
+        for h in range(128):
+            src = h + shift
+            want = win[src] if 0 <= src < 128 else np.zeros(128, np.float32)
+            assert np.array_equal(out[b, 0, h], want)

@@ -346,3 +346,33 @@ def test_shape_errors_are_runtime_errors(tv):
         model(torch.zeros(2, 1, 32, 32))  # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         model.decode(torch.zeros(2, 11, device="cuda"))
+
+
+# ---------------------------------------------------------------------------
+# property test: random shapes inside the kernels' constraints
+# ---------------------------------------------------------------------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(B=st.integers(1, 5), hm=st.integers(1, 3), wm=st.integers(1, 4),
+       widths=st.sampled_from([[8, 16, 32, 64], [32, 64, 128, 256], [16, 16, 48, 24], [4, 8, 8, 16]]),
+       L=st.integers(1, 12), kldw=st.sampled_from([1.0, 0.00025]))
+def test_property_random_shapes_fp32(tv, B, hm, wm, widths, L, kldw):
+    """(B, H, W, widths, latent) drawn by hypothesis; H, W multiples of 16 (four stride-2 layers)."""
+    H, W = 16 * hm, 16 * wm
+    params = vo.closed_form_params(vo.param_shapes(1, L, H, W, list(widths)))
+    x, eps = vo.closed_form_inputs(B, H, W, L)
+    r64 = vo.step(params, x, eps, kld_weight=kldw, dtype=torch.float64)
+    model = build(tv, H, W, widths, L, kldw, torch.float32, params)
+    out, losses, grads, bufs = run_cuda(model, x, eps)
+    assert vo.rel_err(losses["loss"], r64["loss"]) <= 1e-5
+    assert vo.rel_err(out["output"], r64["output"].reshape(out["output"].shape)) <= 1e-5
+    assert vo.rel_err(out["encoded"]["mu"], r64["mu"]) <= 1e-5
+    # gradients: tiny batches make BatchNorm backward ill conditioned, so the bound scales with the reference's own noise
+    r32 = vo.step(params, x, eps, kld_weight=kldw)
+    for k, g in grads.items():
+        floor = vo.grad_floor(r64["grads"], k)
+        noise = vo.rel_err(r32["grads"][k], r64["grads"][k], floor)
+        assert vo.rel_err(g, r64["grads"][k], floor) <= max(1e-4, 8 * noise), (k, B, H, W, widths, L)

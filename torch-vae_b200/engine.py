@@ -69,6 +69,17 @@ def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     return vec, ops.bn_apply_lrelu(y, vec, beta)
 
 
+# Teacher-forcing hook for the parity tests: when a list is installed here, every backward hop appends
+# (name, {tensor name: tensor}) with exactly the tensors its kernels consumed and produced, so that a test can
+# redo that hop in exact arithmetic on IDENTICAL inputs (tests/test_bf16_rigor_gpu.py).  None in production.
+TRACE = None
+
+
+def _trace(name, **tensors):
+    if TRACE is not None:
+        TRACE.append((name, tensors))
+
+
 def _dst(sink, p):
     """Where a parameter gradient is written: straight into its all-reduce bucket slice when a
     gradient sink (parallel.GradientBuckets) is attached, else a fresh tensor (None)."""
@@ -141,6 +152,8 @@ class EncodeFn(torch.autograd.Function):
         if dpre is not None:
             d_pre = d_pre + dpre.to(d_pre.dtype)
         g_b_mu, g_b_var = ops.colsum(dmu, out=_dst(sink, b_mu)), ops.colsum(dlv, out=_dst(sink, b_var))
+        _trace("heads", dmu=dmu, dlv=dlv, pre=pre, w_mu=w_mu, w_var=w_var, d_pre=d_pre, g_w_mu=g_w_mu, g_w_var=g_w_var,
+               g_b_mu=g_b_mu, g_b_var=g_b_var)
         if sink is not None:
             for p_, g_ in ((w_mu, g_w_mu), (b_mu, g_b_mu), (w_var, g_w_var), (b_var, g_b_var)):
                 sink.push(p_, g_)
@@ -162,10 +175,14 @@ class EncodeFn(torch.autograd.Function):
             if sink is not None:
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
+            d_in = d_act
             if i > 0:
                 d_act = ops.conv_data_grad(dy, cw)
             elif ctx.x_needs_grad:
                 dx = ops.nhwc_to_nchw(ops.conv_data_grad(dy, cw), torch.float32).view(B, sp.ci, Hi, Wi)
+            _trace(f"encoder.{i}", transposed=False, d_act=d_in, y=y, vec=vec, gamma=gamma, h_in=h_in, w=conv_params[4 * i],
+                   dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act if i > 0 else None,
+                   training=ctx.training)
         ctx.saved = None
         if sink is not None:
             # the sink owns the parameter gradients (it exposes them as p.grad after the all-reduce); handing
@@ -193,6 +210,7 @@ class ReparamFn(torch.autograd.Function):
     def backward(ctx, dz):
         eps, log_var = ctx.saved_tensors
         dmu, dlv = ops.reparam_bwd(dz.contiguous(), eps, log_var)
+        _trace("reparam", dz=dz, eps=eps, log_var=log_var, dmu=dmu, dlv=dlv)
         return dmu, dlv, None, None, None
 
 
@@ -275,6 +293,8 @@ class DecodeFn(torch.autograd.Function):
                                              last_outs=(sink.view(w_last), sink.view(b_last)) if sink is not None else None)
             g_w_last, g_b_last = fused[4], fused[5]
             d_act = None
+            _trace("final", dlog=dlog, y=y, vec=vec, gamma=gamma, w_last=w_last, dy=fused[0], dgamma=fused[1], dbeta=fused[2],
+                   g_w_last=g_w_last, g_b_last=g_b_last, training=ctx.training)
         else:
             c_last = act_last.shape[-1]
             # final Conv2d(C -> 1): bias grad is a plain sum, done as two column sums
@@ -304,7 +324,11 @@ class DecodeFn(torch.autograd.Function):
             if sink is not None:
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
+            d_in = d_act
             d_act = ops.conv_forward(dy, cw, None)  # gradient w.r.t. the ConvT input
+            _trace(f"decoder.{i}", transposed=True, d_act=d_in, y=y, vec=vec, gamma=gamma, h_in=h_in, w=conv_params[4 * i],
+                   dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act, training=ctx.training,
+                   fused_bn=bool(fused_last and i == n_blk - 1))
         d_d = ops.nhwc_to_nchw(d_act)  # [B, F] C-major, matching decoder_input's output
         L_, F_ = z.shape[1], w_in.shape[0]
         skinny = ops.heads_supported(F_, L_)
@@ -322,6 +346,7 @@ class DecodeFn(torch.autograd.Function):
             dz = ops.skinny_reduce(d_d, w_in, None, 1, L_, L_)
         else:
             dz = ops.linear_bwd_input(d_d, w_in, out_dtype=torch.float32)
+        _trace("decoder_input", d_d=d_d, z=z, w_in=w_in, g_w_in=g_w_in, g_b_in=g_b_in, dz=dz)
         ctx.saved = None
         ctx.last = None
         if sink is not None:  # see EncodeFn.backward: the sink owns the parameter gradients
@@ -366,4 +391,8 @@ class ElboFn(torch.autograd.Function):
         else:  # a second backward through a retained graph, or latents that were not fp32
             pred, target, mu, log_var = ctx.saved_tensors
             dpred, dmu, dlv = ops.elbo_bwd(pred, target, mu, log_var, g, ctx.kld_weight, ctx.input_is_prob)
+        if TRACE is not None:
+            pred, target, mu, log_var = ctx.saved_tensors
+            _trace("elbo", pred=pred, target=target, mu=mu, log_var=log_var, dpred=dpred, dmu=dmu, dlv=dlv,
+                   kld_weight=ctx.kld_weight, input_is_prob=ctx.input_is_prob)
         return dpred, None, dmu, dlv, None, None
