@@ -276,14 +276,14 @@ int vae_adamw_step(const vae_adamw_tensor* tensors /* host array */, int count, 
                    double eps, vae_stream_t stream);
 
 /* The same step with the hyper-parameters in DEVICE memory, so that a captured CUDA graph follows a
- * per-batch schedule: hyper[4*g .. 4*g+3] = {lr, beta1, beta2, weight_decay} (fp32) of parameter group g,
+ * per-batch schedule: hyper[8*g .. 8*g+5] = {lr, beta1, beta2, weight_decay, 1-beta1, 1-beta2} (fp32, rows of 8) of group g,
  * group_of[i] (host array) = group of tensor i; the lr / wd fields of the records are ignored.
  * replaces: optimizer.step() (train.py:656) under the per-batch scheduler of train.py:232-238,659 */
 int vae_adamw_step_dev(const vae_adamw_tensor* tensors /* host array */, const int* group_of /* host array */,
                        int count, const float* hyper, int n_groups, double eps, vae_stream_t stream);
 
 /* One scheduler.step() of torch.optim.lr_scheduler.OneCycleLR (two phases) on the device:
- * counter[0] (int64 = last_epoch) += 1, then hyper[4*g] = lr and, with cycle_momentum, hyper[4*g+1] = beta1.
+ * counter[0] (int64 = last_epoch) += 1, then hyper[8*g] = lr and, with cycle_momentum, hyper[8*g+1] = beta1, hyper[8*g+4] = 1 - beta1.
  * per_group (host array) = n_groups (<= 8) records {initial_lr, max_lr, min_lr, base_momentum, max_momentum}
  * of doubles; anneal 0 = cos, 1 = linear.  Past total_steps (where torch raises) the schedule is clamped.
  * replaces: scheduler.step() (train.py:659) of the OneCycleLR built at train.py:232-238 */

@@ -356,11 +356,12 @@ from hypothesis import strategies as st  # noqa: E402
 
 
 @settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
-@given(B=st.integers(1, 5), hm=st.integers(1, 3), wm=st.integers(1, 4),
+@given(B=st.integers(2, 5), hm=st.integers(1, 3), wm=st.integers(1, 4),
        widths=st.sampled_from([[8, 16, 32, 64], [32, 64, 128, 256], [16, 16, 48, 24], [4, 8, 8, 16]]),
        L=st.integers(1, 12), kldw=st.sampled_from([1.0, 0.00025]))
 def test_property_random_shapes_fp32(tv, B, hm, wm, widths, L, kldw):
-    """(B, H, W, widths, latent) drawn by hypothesis; H, W multiples of 16 (four stride-2 layers)."""
+    """(B, H, W, widths, latent) drawn by hypothesis; H, W multiples of 16 (four stride-2 layers); B >= 2 because
+    train-mode BatchNorm rejects a single value per channel (16x16 input, B = 1) in the reference too."""
     H, W = 16 * hm, 16 * wm
     params = vo.closed_form_params(vo.param_shapes(1, L, H, W, list(widths)))
     x, eps = vo.closed_form_inputs(B, H, W, L)

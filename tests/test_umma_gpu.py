@@ -194,6 +194,7 @@ TMA_CASES = [
     (2, 16, 512, 64, 32, 2),    # wide rolls: Wj = 256, tiles of 128 pixels inside a row
     (3, 16, 16, 32, 32, 1),     # stride 1
     (64, 64, 64, 32, 64, 2),    # many tiles per CTA
+    (4, 16, 128, 256, 512, 2),  # wide model: 512 output channels = two 256-channel launches (UMMA N <= 256)
 ]
 
 

@@ -57,8 +57,11 @@ __global__ void adamw_bump_steps_kernel(const __grid_constant__ AdamTable T, int
 }
 
 // Same update with the hyper-parameters read from DEVICE memory: hyper[group] = {lr, beta1, beta2,
-// weight_decay}.  A captured CUDA graph then follows a per-batch schedule (OneCycleLR cycles lr and
+// weight_decay, 1 - beta1, 1 - beta2, -, -} (the complements are formed in double precision by whoever
+// writes the table, as torch forms `1 - beta` from Python floats).  A captured CUDA graph then follows a per-batch schedule (OneCycleLR cycles lr and
 // beta1, train.py:232-238,659) instead of replaying the values of capture time.
+constexpr int kAdamHyperStride = 8;
+
 struct AdamGroupTable {
   int grp[kAdamMaxTensors];
 };
@@ -68,9 +71,9 @@ adamw_dev_kernel(const __grid_constant__ AdamTable T, const __grid_constant__ Ad
                  const float* __restrict__ hyper, float eps) {
   const int t = blockIdx.y;
   const int n = T.n[t];
-  const float* h = hyper + 4 * G.grp[t];
+  const float* h = hyper + kAdamHyperStride * G.grp[t];
   const float lr = h[0], beta1 = h[1], beta2 = h[2], wd = h[3];
-  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  const float omb1 = h[4], omb2 = h[5];
   const float step = T.step[t][0] + 1.0f;
   const float bc1 = 1.0f - powf(beta1, step);
   const float bc2 = 1.0f - powf(beta2, step);
@@ -120,8 +123,11 @@ __global__ void onecycle_kernel(float* hyper, long long* counter, const __grid_c
       lr = ann(T.max_lr[g], T.min_lr[g], pct);
       mom = ann(T.base_m[g], T.max_m[g], pct);
     }
-    hyper[4 * g] = (float)lr;
-    if (cycle_momentum) hyper[4 * g + 1] = (float)mom;
+    hyper[kAdamHyperStride * g] = (float)lr;
+    if (cycle_momentum) {
+      hyper[kAdamHyperStride * g + 1] = (float)mom;
+      hyper[kAdamHyperStride * g + 4] = (float)(1.0 - mom);
+    }
   }
   __syncthreads();
   if (g == 0) counter[0] = step;
@@ -166,8 +172,8 @@ extern "C" int vae_adamw_step(const vae_adamw_tensor* tensors, int count, double
   return VAE_OK;
 }
 
-/* vae_adamw_step with the hyper-parameters in DEVICE memory: hyper[4*g .. 4*g+3] = {lr, beta1, beta2,
- * weight_decay} of parameter group g (fp32), group_of[i] (host) = group of tensor i.  The lr / wd fields of
+/* vae_adamw_step with the hyper-parameters in DEVICE memory: hyper[8*g .. 8*g+5] = {lr, beta1, beta2,
+ * weight_decay, 1 - beta1, 1 - beta2} of parameter group g (fp32, rows of 8), group_of[i] (host) = group of tensor i.  The lr / wd fields of
  * the tensor records are ignored.  CUDA-graph replays follow whatever vae_onecycle_step (or a host copy)
  * last wrote into `hyper`.
  * replaces: optimizer.step() (train.py:656) under a per-batch scheduler (train.py:232-238,659) */
@@ -203,7 +209,7 @@ extern "C" int vae_adamw_step_dev(const vae_adamw_tensor* tensors, const int* gr
 }
 
 /* One scheduler.step() of torch.optim.lr_scheduler.OneCycleLR (two-phase) on the device: counter[0] (int64,
- * = last_epoch) += 1, then hyper[4*g] = lr and, with cycle_momentum, hyper[4*g+1] = beta1 for g < n_groups (<= 8).
+ * = last_epoch) += 1, then hyper[8*g] = lr and, with cycle_momentum, hyper[8*g+1] = beta1, hyper[8*g+4] = 1 - beta1 for g < n_groups (<= 8).
  * per_group (host) = n_groups records {initial_lr, max_lr, min_lr, base_momentum, max_momentum} as doubles.
  * replaces: scheduler.step() (train.py:659) of the OneCycleLR built at train.py:232-238 */
 extern "C" int vae_onecycle_step(float* hyper, long long* counter, const double* per_group, int n_groups,

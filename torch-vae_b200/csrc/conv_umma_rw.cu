@@ -35,6 +35,14 @@ struct RwParams {
   const float* bias;
   bf16* out;
   double* stats;
+  // Fused BatchNorm-backward prologue of the NEXT hop (optional): the produced tensor is the gradient
+  // w.r.t. act = lrelu(bn(y)) of the layer below.  With bn_y set the epilogue reads y at the pixel it
+  // writes, multiplies by LeakyReLU'(u) and accumulates  stats[c] = sum du,  stats[N + c] = sum du * xhat
+  // (the two reductions BatchNorm backward needs) instead of the forward statistics: the tensor written
+  // is du, and the separate reduce pass over (d_act, y) disappears.
+  const bf16* bn_y;
+  const float4* bn_vec;   // [N] {mean, scale, beta, rstd}
+  float slope;
 };
 
 template <int MODE, int KC, int N>
@@ -56,7 +64,7 @@ struct RwCfg {
   static constexpr int ROWB = MODE == 1 ? 128 : N * 2;   // contiguous global bytes a thread produces per output row
   static constexpr int EPI_PITCH = ROWB + 16;
   static constexpr int EPI = 8 * 32 * EPI_PITCH;
-  static constexpr int TAIL = 8 * 24 + 16 + 4 * (2 * 64 + 64) + EPI;
+  static constexpr int TAIL = 8 * 24 + 16 + 4 * (2 * 64 + 64) + 64 * 16 + EPI;
   static size_t smem_bytes(int stages) { return 1024 + (size_t)stages * STAGE + WBYTES + TAIL; }
 };
 
@@ -93,11 +101,14 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(full_bar + 24);  // barrier block padded to 192 B
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][64]
   float* s_bias = s_stats + 128;                            // [64]
-  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_bias + 64);  // [8 epilogue warps][32 rows][EPI_PITCH]
+  float4* s_bn = reinterpret_cast<float4*>(s_bias + 64);     // [64] {mean, scale, beta, rstd} (fused BN backward)
+  uint8_t* s_epi = reinterpret_cast<uint8_t*>(s_bn + 64);    // [8 epilogue warps][32 rows][EPI_PITCH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 128; i += kRwThreads) s_stats[i] = 0.0f;
   for (int i = threadIdx.x; i < 64; i += kRwThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
+  if (P.bn_y != nullptr)
+    for (int i = threadIdx.x; i < N; i += kRwThreads) s_bn[i] = P.bn_vec[i];
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kRwMaxStages; ++s) {
@@ -246,10 +257,24 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
         else
           dst = P.out + (((long long)b * P.Hout + 2 * jh) * P.Wout + 2 * jw) * N;
       }
+      constexpr int NCHUNK = Cfg::ACC_COLS / 32;
+      // fused BN backward: this thread's y values (same element offsets as the row it writes), requested
+      // BEFORE the wait for the accumulator so that the loads fly while the MMAs of the tile run
+      uint4 yraw[NCHUNK][4];
+      if (P.bn_y != nullptr) {
+        const long long eoff = dst != nullptr ? (long long)(dst - P.out) : 0;
+#pragma unroll
+        for (int ci = 0; ci < NCHUNK; ++ci) {
+          // MODE 0: chunk ci = channels 32ci..; MODE 1: chunk ci = output pixel (2jh + (ci>>1), 2jw + (ci&1)), N = 32
+          const long long o = MODE == 0 ? eoff + ci * 32 : eoff + (long long)(ci >> 1) * P.Wout * N + (ci & 1) * N;
+          const uint4* src = reinterpret_cast<const uint4*>(P.bn_y + o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) yraw[ci][q] = __ldg(src + q);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
-      constexpr int NCHUNK = Cfg::ACC_COLS / 32;
 #pragma unroll
       for (int ci = 0; ci < NCHUNK; ++ci) {
         float v[32];
@@ -268,6 +293,27 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           v[i + 1] = valid ? v[i + 1] + b4.y : 0.0f;
           v[i + 2] = valid ? v[i + 2] + b4.z : 0.0f;
           v[i + 3] = valid ? v[i + 3] + b4.w : 0.0f;
+        }
+        float second[32];   // what the second statistic sums: y^2 (forward) or du * xhat (fused BN backward)
+        if (P.bn_y != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w4[4] = {yraw[ci][q].x, yraw[ci][q].y, yraw[ci][q].z, yraw[ci][q].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int i = q * 8 + k;
+              const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
+              const float4 c4 = s_bn[cbase + i];            // mean, scale, beta, rstd
+              const float t = yv - c4.x;
+              const float u = fmaf(t, c4.y, c4.z);          // same expression as the forward apply (bn_affine)
+              const float du = u > 0.0f ? v[i] : v[i] * P.slope;
+              v[i] = du;
+              second[i] = du * (t * c4.w);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
         }
         {
           // A thread's accumulator row is ROWB contiguous bytes of the output (MODE 0: its pixel's N channels;
@@ -305,16 +351,13 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               run1[i] += v[i];
-              run2[i] = fmaf(v[i], v[i], run2[i]);
+              run2[i] += second[i];
             }
           } else {
-            float sq[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
             warp_transpose_reduce32(v, lane);
-            warp_transpose_reduce32(sq, lane);
+            warp_transpose_reduce32(second, lane);
             atomicAdd(&s_stats[cbase + lane], v[0]);
-            atomicAdd(&s_stats[64 + cbase + lane], sq[0]);
+            atomicAdd(&s_stats[64 + cbase + lane], second[0]);
           }
         }
       }
@@ -379,7 +422,7 @@ static bool rw_plan(RwPlan& p, int B, int Hi, int Wi, int Ci, int Co, int stride
 
 template <int MODE, int KC, int N>
 static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const float* bias, void* out, double* stats,
-                     int B, cudaStream_t st) {
+                     int B, cudaStream_t st, const void* bn_y = nullptr, const float* bn_vec = nullptr, float slope = 0.0f) {
   using Cfg = RwCfg<MODE, KC, N>;
   RwParams P{};
   cuuint64_t gdim[4] = {(cuuint64_t)KC, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)B};
@@ -400,6 +443,7 @@ static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const fl
   VAE_REQUIRE(stages >= 2, "conv_umma_rw: shared memory budget");
   P.stages = stages;
   P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  P.bn_y = (const bf16*)bn_y; P.bn_vec = reinterpret_cast<const float4*>(bn_vec); P.slope = slope;
   auto kern = umma_rw_conv_kernel<MODE, KC, N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -444,17 +488,36 @@ extern "C" int vae_umma_rw_pack_weight(const float* w_oihw, void* out, int Ci, i
  * vae_umma_rw_pack_weight.
  * replaces: aten::convolution (models.py:45, 66-68, 77) and the data-gradient half of
  * aten::convolution_backward (train.py:650) on the narrow layers */
-extern "C" int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
-                                int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+static int rw_dispatch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi,
+                       int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* bn_vec,
+                       float slope) {
   VAE_REQUIRE(in && wpk && out && (mode == 0 || mode == 1), "conv_umma_rw: bad argument");
   RwPlan pl{};
   VAE_REQUIRE(rw_plan(pl, B, Hi, Wi, Ci, Co, stride, mode), "conv_umma_rw: shape not served by this kernel");
   cudaStream_t st = as_stream(stream);
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * pl.n, st));
-  if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st);
-  if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st);
-  if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st);
-  if (mode == 1 && pl.kc == 64) return rw_launch<1, 64, 32>(pl, in, wpk, bias, out, stats, B, st);
+  if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
+  if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
+  if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
+  if (mode == 1 && pl.kc == 64) return rw_launch<1, 64, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
   set_error("conv_umma_rw: no instantiation");
   return VAE_ERR_UNSUPPORTED;
+}
+
+extern "C" int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
+                                int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+  return rw_dispatch(in, wpk, bias, out, stats, B, Hi, Wi, Ci, Co, stride, mode, stream, nullptr, nullptr, 0.0f);
+}
+
+/* vae_conv_umma_rw producing the gradient w.r.t. an activation act = lrelu(bn(y)) (models.py:45-47,66-70) with the
+ * first half of that BatchNorm's backward fused into the epilogue: `y` is the stored pre-normalisation tensor of
+ * the layer below (same shape as `out`), bn_vec = [channels][4] fp32 {mean, gamma*rstd, beta, rstd}.  `out`
+ * receives du = d_act * LeakyReLU'(u) and dstats[0..C) = sum du, dstats[C..2C) = sum du * xhat (fp64), i.e. what
+ * vae_bn_lrelu_bwd_reduce computes in a separate pass over (d_act, y).
+ * replaces: the LeakyReLU / native_batch_norm_backward reductions of train.py:650 for the layer below */
+extern "C" int vae_conv_umma_rw_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* bn_vec,
+                                      double* dstats, float slope, int B, int Hi, int Wi, int Ci, int Co, int stride,
+                                      int mode, vae_stream_t stream) {
+  VAE_REQUIRE(y && bn_vec && dstats, "conv_umma_rw_bnbwd: bad argument");
+  return rw_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, bn_vec, slope);
 }

@@ -55,7 +55,9 @@ struct TmaConvParams {
   const bf16* wpk;
   const float* bias;
   bf16* out;
-  double* stats;
+  int ldo;             // channels per pixel of the produced tensor (> N when the launch writes a channel slice)
+  double* stats;       // [N] sums of this launch's channels
+  double* stats2;      // [N] sums of squares
   long long* trace;  // optional [6][512] clock64 samples of CTA 0 (tuning aid)
 };
 
@@ -276,7 +278,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
         const uint32_t jw = mu % (uint32_t)g.Wj, t2 = mu / (uint32_t)g.Wj;
         const uint32_t jh = t2 % (uint32_t)g.Hj, b = t2 / (uint32_t)g.Hj;
         const int oh = (int)jh * g.out_mul + tt.ph, ow = (int)jw * g.out_mul + tt.pw;
-        dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * g.Nout;
+        dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * P.ldo;
       }
       mbar_wait(&tfull_bar[acc], acc_ph);
       if (ew == 0) VAE_TTRACE(4, it);
@@ -345,7 +347,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
       for (int i = threadIdx.x - 64; i < N; i += 256) {
         atomicAdd(&P.stats[i], (double)s_stats[i]);
-        atomicAdd(&P.stats[N + i], (double)s_stats[256 + i]);
+        atomicAdd(&P.stats2[i], (double)s_stats[256 + i]);
       }
     }
   }
@@ -404,6 +406,11 @@ static bool tma_plan(TmaConvParams& P, const GatherGeom& g) {
   return true;
 }
 
+// A forward conv with more than 256 output channels runs as Co / 256 launches, each producing a 256-channel
+// slice of the output (the UMMA N extent and the TMEM double buffer end at 256 columns); the packed weight
+// images of the slices follow one another.  OIHW weights of a slice are contiguous (co is outermost).
+static int tma_nsplit(int Co, int mode) { return (mode == 0 && Co > 256 && Co % 256 == 0) ? Co / 256 : 1; }
+
 static long long tma_packed_elems(const TmaConvParams& P) {
   long long n = 0;
   for (int p = 0; p < P.g.nphase; ++p) n += (long long)P.nkb[p] * (P.b_stage_bytes / 2);
@@ -424,25 +431,28 @@ extern "C" int vae_set_umma_tma(int enable) {
  * the spatial extents decompose into whole output rows per 128-pixel tile. */
 extern "C" int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode) {
   if (B <= 0 || Hi <= 0 || Wi <= 0 || (stride != 1 && stride != 2) || Hi % stride || Wi % stride) return 0;
-  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
+  const int co = Co / tma_nsplit(Co, mode);
+  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, co, stride) : geom_dgrad(B, Hi, Wi, Ci, co, stride);
   TmaConvParams P{};
   return tma_plan(P, g) ? 1 : 0;
 }
 
 extern "C" long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode) {
-  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, Co, stride)
-                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, Co, stride);
+  const int ns = tma_nsplit(Co, mode), co = Co / ns;
+  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, co, stride)
+                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, co, stride);
   TmaConvParams P{};
   if (!tma_plan(P, g)) return 0;
-  return tma_packed_elems(P);
+  return ns * tma_packed_elems(P);
 }
 
 extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, int Co, int stride, int mode,
                                         vae_stream_t stream) {
   VAE_REQUIRE(w_oihw && out && (mode == 0 || mode == 1) && (stride == 1 || stride == 2),
               "umma_tma_pack_weight: bad argument");
-  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, Co, stride)
-                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, Co, stride);
+  const int ns = tma_nsplit(Co, mode), co = Co / ns;
+  GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, co, stride)
+                           : geom_dgrad(1, 128 * stride, 128 * stride, Ci, co, stride);
   TmaConvParams P{};
   VAE_REQUIRE(tma_plan(P, g), "umma_tma_pack_weight: shape not served by the TMA path");
   long long n_max = 0;  // one element per thread: the OIHW reads are scattered, parallelism hides them
@@ -451,8 +461,14 @@ extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, 
     if (n > n_max) n_max = n;
   }
   dim3 grid((unsigned)((n_max + 255) / 256), g.nphase);
-  pack_tma_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_oihw, (bf16*)out, P, Co, Ci, mode);
-  return check_launch("pack_tma_weight");
+  const long long per = tma_packed_elems(P);
+  for (int s = 0; s < ns; ++s) {
+    pack_tma_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w_oihw + (long long)s * co * Ci * 9, (bf16*)out + s * per, P,
+                                                                 co, Ci, mode);
+    int rc = check_launch("pack_tma_weight");
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 /* Conv forward (mode 0) / data gradient == ConvTranspose forward (mode 1) with the A
@@ -463,9 +479,11 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
   VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
                   (mode == 0 || mode == 1),
               "conv_umma_tma: bad argument");
-  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, Co, stride) : geom_dgrad(B, Hi, Wi, Ci, Co, stride);
+  const int ns = tma_nsplit(Co, mode), co = Co / ns;
+  GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, co, stride) : geom_dgrad(B, Hi, Wi, Ci, co, stride);
   TmaConvParams P{};
   VAE_REQUIRE(tma_plan(P, g), "conv_umma_tma: shape not served by the TMA path");
+  const int n_total = g.Nout * ns;   // channels per pixel of the produced tensor
   EncodeTiledFn encode = get_encode_fn();
   VAE_REQUIRE(encode != nullptr, "conv_umma_tma: cuTensorMapEncodeTiled is not available in this driver");
   // NHWC tensor, innermost dimension first
@@ -481,8 +499,8 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VAE_REQUIRE(cr == CUDA_SUCCESS, "conv_umma_tma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
-  P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
+  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n_total, st));
+  P.ldo = n_total;
   P.trace = umma_trace_ptr();
   size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64;
   static bool attr_set = false;
@@ -492,6 +510,16 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
   }
   int grid = sm_count();
   if (grid > P.total_tiles) grid = P.total_tiles;
-  umma_tma_conv_kernel<<<grid, kTThreads, smem, st>>>(P);
-  return check_launch("umma_tma_conv");
+  const long long per = tma_packed_elems(P);
+  for (int s = 0; s < ns; ++s) {
+    P.wpk = (const bf16*)wpk + s * per;
+    P.bias = bias ? bias + s * g.Nout : nullptr;
+    P.out = (bf16*)out + s * g.Nout;
+    P.stats = stats ? stats + s * g.Nout : nullptr;
+    P.stats2 = stats ? stats + n_total + s * g.Nout : nullptr;
+    umma_tma_conv_kernel<<<grid, kTThreads, smem, st>>>(P);
+    int rc = check_launch("umma_tma_conv");
+    if (rc != 0) return rc;
+  }
+  return 0;
 }

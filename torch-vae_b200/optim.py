@@ -41,7 +41,7 @@ class FusedAdamW(torch.optim.AdamW):
         kw.pop("fused", None)
         kw["capturable"] = True  # step counters live on the device
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, **kw)
-        self._hyper = None          # device [n_groups, 4] fp32: lr, beta1, beta2, weight_decay
+        self._hyper = None          # device [n_groups, 8] fp32: lr, beta1, beta2, weight_decay, 1-beta1, 1-beta2, -, -
         self._hyper_host = None     # the host values last uploaded
         self._device_schedule = False  # True once a FusedOneCycleLR owns lr / beta1 on the device
 
@@ -81,13 +81,17 @@ class FusedAdamW(torch.optim.AdamW):
         for group in self.param_groups:
             lr = group["lr"]
             lr = float(lr) if not isinstance(lr, torch.Tensor) else float(lr.item())
-            rows.append((lr, float(group["betas"][0]), float(group["betas"][1]), float(group["weight_decay"])))
+            b1, b2 = float(group["betas"][0]), float(group["betas"][1])
+            rows.append((lr, b1, b2, float(group["weight_decay"]), 1.0 - b1, 1.0 - b2, 0.0, 0.0))
         return rows
 
     def hyper_table(self, device) -> torch.Tensor:
         """The device table the kernel reads; created on first use."""
-        if self._hyper is None or self._hyper.device != torch.device(device) or self._hyper.shape[0] != len(self.param_groups):
-            self._hyper = torch.zeros((len(self.param_groups), 4), dtype=torch.float32, device=device)
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device(device.type, torch.cuda.current_device())
+        if self._hyper is None or self._hyper.device != device or self._hyper.shape[0] != len(self.param_groups):
+            self._hyper = torch.zeros((len(self.param_groups), 8), dtype=torch.float32, device=device)
             self._hyper_host = None
         return self._hyper
 
