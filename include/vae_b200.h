@@ -139,6 +139,21 @@ int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* o
                      int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
                      vae_stream_t stream);
 
+/* The same two kernels producing the gradient w.r.t. an activation act = lrelu(bn(y)) of the layer below
+ * (models.py:45-47,66-70) with the first half of that BatchNorm's backward fused into the epilogue: `y` is the
+ * stored pre-normalisation tensor of the layer below (same shape as `out`), mean / scale (= gamma*rstd) / beta / rstd its
+ * [channels] fp32 vectors.  `out` receives du = d_act * LeakyReLU'(u) and dstats[0..C) = sum du,
+ * dstats[C..2C) = sum du * xhat (fp64) -- what vae_bn_lrelu_bwd_reduce computes in a separate pass over
+ * (d_act, y); follow with vae_bn_lrelu_bwd_apply(training | 2).
+ * replaces: aten::convolution_backward (data gradient) + aten::leaky_relu_backward + the reductions of
+ * aten::native_batch_norm_backward (train.py:650) */
+int vae_conv_umma_rw_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* mean,
+                           const float* scale, const float* beta, const float* rstd, double* dstats, float slope,
+                           int B, int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream);
+int vae_conv_umma_tma_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* mean,
+                            const float* scale, const float* beta, const float* rstd, double* dstats, float slope,
+                            int B, int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream);
+
 /* TMA-fed weight gradient (conv_wgrad_tma.cu): operands staged MN-major straight from NHWC
  * boxes; ws is a caller-provided fp32 workspace of 9*Co*Ci elements; dw overwritten.
  * replaces: the weight-gradient half of aten::convolution_backward (train.py:650) */
@@ -188,7 +203,9 @@ int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const float* scale,
 
 /* Pass 2: dy = gamma*rstd*(du - dbeta/M - xhat*dgamma/M) (training) or
  * dy = du*scale (eval); writes dgamma[C], dbeta[C] and dbias[C] = sum dy (the
- * gradient of the conv bias that feeds this BatchNorm).
+ * gradient of the conv bias that feeds this BatchNorm).  `training`: bit 0 = train-mode
+ * statistics, bit 1 = `dact` already holds du (written by vae_conv_umma_*_bnbwd, whose
+ * epilogue also produced dstats, so pass 1 is skipped).
  * replaces: aten::native_batch_norm_backward */
 int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
                            const float* beta, const float* mean, const float* rstd,

@@ -271,3 +271,52 @@ def test_umma_rw_conv(ops, case):
     out2 = ops.conv_umma_rw(inp.cuda().bfloat16(), wpk, None, None, Ci, Co, s, mode)  # no bias / stats
     ref2 = ref - b.double().view(1, -1, 1, 1)
     assert rel_err(nchw(out2.float().cpu()), ref2) < TOL
+
+
+# ---------------------------------------------------------------------------
+# fused BatchNorm-backward epilogue (vae_conv_umma_{rw,tma}_bnbwd): out = du, dstats = {sum du, sum du * xhat}
+# ---------------------------------------------------------------------------
+BNB_CASES = [
+    # kind, B, H, W (high-res side of the equivalent conv), Ci, Co, mode
+    ("rw", 3, 32, 32, 32, 32, 0),
+    ("rw", 2, 16, 64, 32, 64, 0),
+    ("rw", 2, 32, 32, 32, 32, 1),
+    ("rw", 3, 16, 32, 32, 64, 1),
+    ("rw", 16, 128, 128, 32, 32, 0),   # many tiles per CTA, both epilogue sets
+    ("tma", 5, 32, 32, 64, 128, 0),
+    ("tma", 5, 32, 32, 64, 128, 1),
+    ("tma", 6, 16, 16, 128, 256, 0),
+    ("tma", 6, 16, 16, 128, 256, 1),
+]
+
+
+@pytest.mark.parametrize("case", BNB_CASES, ids=[f"{c[0]}-m{c[6]}-{c[4]}x{c[5]}-B{c[1]}" for c in BNB_CASES])
+def test_conv_with_fused_bn_backward_epilogue(ops, case):
+    kind, B, H, W, Ci, Co, mode = case
+    s = 2
+    w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * (Ci if mode == 0 else Co)))
+    if mode == 0:
+        x = rnd(B, Ci, H, W, seed=1)
+        d_act = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), None, stride=s, padding=1)
+        inp, C = nhwc(x), Co
+    else:
+        x = rnd(B, Co, H // s, W // s, seed=1)
+        d_act = F.conv_transpose2d(x.bfloat16().double(), w.bfloat16().double(), None, stride=s, padding=1, output_padding=1)
+        inp, C = nhwc(x), Ci
+    y = rnd(*d_act.shape, seed=7).bfloat16()
+    mean, rstd = rnd(C, seed=8, scale=0.3), rnd(C, seed=9).abs() + 0.5
+    gamma, beta = rnd(C, seed=10) + 1.5, rnd(C, seed=11, scale=0.2)
+    scale = gamma * rstd
+    vec = torch.stack([scale, beta - mean * scale, mean, rstd]).cuda().contiguous()
+    cw = ops.ConvWeights(w.cuda(), torch.bfloat16, s)
+    wpk = (cw.rw(mode) if kind == "rw" else cw.umma(mode, tma=True))
+    du, dstats = ops.conv_umma_bnbwd(kind, inp.cuda().bfloat16(), wpk, nhwc(y).cuda(), vec, beta.cuda(), Ci, Co, s, mode)
+    torch.cuda.synchronize()
+    y64 = y.double()
+    t = y64 - mean.double().view(1, -1, 1, 1)
+    u = t * scale.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1)
+    want = torch.where(u > 0, d_act, d_act * 0.01)
+    xhat = t * rstd.double().view(1, -1, 1, 1)
+    assert rel_err(nchw(du.float().cpu()), want) < TOL
+    assert rel_err(dstats.cpu()[:C], want.sum(dim=(0, 2, 3))) < 2e-3
+    assert rel_err(dstats.cpu()[C:], (want * xhat).sum(dim=(0, 2, 3))) < 2e-3

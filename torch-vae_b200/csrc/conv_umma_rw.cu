@@ -41,7 +41,7 @@ struct RwParams {
   // (the two reductions BatchNorm backward needs) instead of the forward statistics: the tensor written
   // is du, and the separate reduce pass over (d_act, y) disappears.
   const bf16* bn_y;
-  const float4* bn_vec;   // [N] {mean, scale, beta, rstd}
+  const float *bn_mean, *bn_scale, *bn_beta, *bn_rstd;   // [N] each (scale = gamma * rstd)
   float slope;
 };
 
@@ -84,7 +84,7 @@ __global__ void pack_rw_weight_kernel(const float* __restrict__ w, bf16* __restr
   }
 }
 
-template <int MODE, int KC, int N>
+template <int MODE, int KC, int N, bool BNB>
 __global__ void __launch_bounds__(kRwThreads, 1)
 umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   using Cfg = RwCfg<MODE, KC, N>;
@@ -107,8 +107,8 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 128; i += kRwThreads) s_stats[i] = 0.0f;
   for (int i = threadIdx.x; i < 64; i += kRwThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
-  if (P.bn_y != nullptr)
-    for (int i = threadIdx.x; i < N; i += kRwThreads) s_bn[i] = P.bn_vec[i];
+  if constexpr (BNB)
+    for (int i = threadIdx.x; i < N; i += kRwThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kRwMaxStages; ++s) {
@@ -239,9 +239,10 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
     const int ew = warp & 3;           // TMEM lane group = warp % 4
     const int eset = (warp - 2) >> 2;  // warps 2-5: even tiles, 6-9: odd tiles
     const int r = ew * 32 + lane;
-    float run1[32], run2[32];
+    const uint32_t s_bn_a = smem_u32(s_bn);
+    float run1[BNB ? 1 : 32], run2[BNB ? 1 : 32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
+    for (int i = 0; i < (BNB ? 1 : 32); ++i) run1[i] = run2[i] = 0.0f;
     for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -260,8 +261,8 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
       constexpr int NCHUNK = Cfg::ACC_COLS / 32;
       // fused BN backward: this thread's y values (same element offsets as the row it writes), requested
       // BEFORE the wait for the accumulator so that the loads fly while the MMAs of the tile run
-      uint4 yraw[NCHUNK][4];
-      if (P.bn_y != nullptr) {
+      uint4 yraw[BNB ? NCHUNK : 1][4];
+      if constexpr (BNB) {
         const long long eoff = dst != nullptr ? (long long)(dst - P.out) : 0;
 #pragma unroll
         for (int ci = 0; ci < NCHUNK; ++ci) {
@@ -269,7 +270,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           const long long o = MODE == 0 ? eoff + ci * 32 : eoff + (long long)(ci >> 1) * P.Wout * N + (ci & 1) * N;
           const uint4* src = reinterpret_cast<const uint4*>(P.bn_y + o);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) yraw[ci][q] = __ldg(src + q);
+          for (int q = 0; q < 4; ++q) yraw[ci][q] = ldg_nc_v4_pinned(src + q);
         }
       }
       mbar_wait(&tfull_bar[acc], acc_ph);
@@ -295,7 +296,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           v[i + 3] = valid ? v[i + 3] + b4.w : 0.0f;
         }
         float second[32];   // what the second statistic sums: y^2 (forward) or du * xhat (fused BN backward)
-        if (P.bn_y != nullptr) {
+        if constexpr (BNB) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t w4[4] = {yraw[ci][q].x, yraw[ci][q].y, yraw[ci][q].z, yraw[ci][q].w};
@@ -303,7 +304,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
             for (int k = 0; k < 8; ++k) {
               const int i = q * 8 + k;
               const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
-              const float4 c4 = s_bn[cbase + i];            // mean, scale, beta, rstd
+              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta, rstd
               const float t = yv - c4.x;
               const float u = fmaf(t, c4.y, c4.z);          // same expression as the forward apply (bn_affine)
               const float du = u > 0.0f ? v[i] : v[i] * P.slope;
@@ -347,7 +348,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           }
         }
         if (P.stats != nullptr) {
-          if (N <= 32) {
+          if constexpr (N <= 32 && !BNB) {   // BNB: the y prefetch needs the registers of the running sums
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               run1[i] += v[i];
@@ -363,7 +364,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
       }
     }
     if (P.stats != nullptr) {
-      if (N <= 32) {
+      if constexpr (N <= 32 && !BNB) {   // BNB: the y prefetch needs the registers of the running sums
         warp_transpose_reduce32(run1, lane);
         warp_transpose_reduce32(run2, lane);
         if (lane < N) {
@@ -422,7 +423,7 @@ static bool rw_plan(RwPlan& p, int B, int Hi, int Wi, int Ci, int Co, int stride
 
 template <int MODE, int KC, int N>
 static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const float* bias, void* out, double* stats,
-                     int B, cudaStream_t st, const void* bn_y = nullptr, const float* bn_vec = nullptr, float slope = 0.0f) {
+                     int B, cudaStream_t st, const void* bn_y = nullptr, const float* const* bn_vec = nullptr, float slope = 0.0f) {
   using Cfg = RwCfg<MODE, KC, N>;
   RwParams P{};
   cuuint64_t gdim[4] = {(cuuint64_t)KC, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)B};
@@ -443,12 +444,13 @@ static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const fl
   VAE_REQUIRE(stages >= 2, "conv_umma_rw: shared memory budget");
   P.stages = stages;
   P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
-  P.bn_y = (const bf16*)bn_y; P.bn_vec = reinterpret_cast<const float4*>(bn_vec); P.slope = slope;
-  auto kern = umma_rw_conv_kernel<MODE, KC, N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  P.bn_y = (const bf16*)bn_y; P.slope = slope;
+  if (bn_y != nullptr) { P.bn_mean = bn_vec[0]; P.bn_scale = bn_vec[1]; P.bn_beta = bn_vec[2]; P.bn_rstd = bn_vec[3]; }
+  auto kern = bn_y != nullptr ? umma_rw_conv_kernel<MODE, KC, N, true> : umma_rw_conv_kernel<MODE, KC, N, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bn_y != nullptr]) {
     VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[bn_y != nullptr] = true;
   }
   int grid = sm_count();
   if (grid > P.total_tiles) grid = P.total_tiles;
@@ -489,7 +491,7 @@ extern "C" int vae_umma_rw_pack_weight(const float* w_oihw, void* out, int Ci, i
  * replaces: aten::convolution (models.py:45, 66-68, 77) and the data-gradient half of
  * aten::convolution_backward (train.py:650) on the narrow layers */
 static int rw_dispatch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi,
-                       int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* bn_vec,
+                       int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* const* bn_vec,
                        float slope) {
   VAE_REQUIRE(in && wpk && out && (mode == 0 || mode == 1), "conv_umma_rw: bad argument");
   RwPlan pl{};
@@ -511,13 +513,15 @@ extern "C" int vae_conv_umma_rw(const void* in, const void* wpk, const float* bi
 
 /* vae_conv_umma_rw producing the gradient w.r.t. an activation act = lrelu(bn(y)) (models.py:45-47,66-70) with the
  * first half of that BatchNorm's backward fused into the epilogue: `y` is the stored pre-normalisation tensor of
- * the layer below (same shape as `out`), bn_vec = [channels][4] fp32 {mean, gamma*rstd, beta, rstd}.  `out`
+ * the layer below (same shape as `out`), mean / scale (= gamma*rstd) / beta / rstd = the layer's [channels] fp32 vectors.  `out`
  * receives du = d_act * LeakyReLU'(u) and dstats[0..C) = sum du, dstats[C..2C) = sum du * xhat (fp64), i.e. what
  * vae_bn_lrelu_bwd_reduce computes in a separate pass over (d_act, y).
  * replaces: the LeakyReLU / native_batch_norm_backward reductions of train.py:650 for the layer below */
-extern "C" int vae_conv_umma_rw_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* bn_vec,
-                                      double* dstats, float slope, int B, int Hi, int Wi, int Ci, int Co, int stride,
-                                      int mode, vae_stream_t stream) {
-  VAE_REQUIRE(y && bn_vec && dstats, "conv_umma_rw_bnbwd: bad argument");
-  return rw_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, bn_vec, slope);
+extern "C" int vae_conv_umma_rw_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* mean,
+                                      const float* scale, const float* beta, const float* rstd, double* dstats,
+                                      float slope, int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
+                                      vae_stream_t stream) {
+  VAE_REQUIRE(y && mean && scale && beta && rstd && dstats, "conv_umma_rw_bnbwd: bad argument");
+  const float* vec[4] = {mean, scale, beta, rstd};
+  return rw_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, vec, slope);
 }

@@ -58,6 +58,11 @@ struct TmaConvParams {
   int ldo;             // channels per pixel of the produced tensor (> N when the launch writes a channel slice)
   double* stats;       // [N] sums of this launch's channels
   double* stats2;      // [N] sums of squares
+  // fused BatchNorm-backward prologue of the next hop (see conv_umma_rw.cu): with bn_y set the epilogue writes
+  // du = acc * LeakyReLU'(u(y)) and the statistics become sum du / sum du * xhat
+  const bf16* bn_y;
+  const float *bn_mean, *bn_scale, *bn_beta, *bn_rstd;   // [N] each (scale = gamma * rstd)
+  float slope;
   long long* trace;  // optional [6][512] clock64 samples of CTA 0 (tuning aid)
 };
 
@@ -100,6 +105,7 @@ __global__ void pack_tma_weight_kernel(const float* __restrict__ w, bf16* __rest
       P.trace[(role) * 512 + (idx)] = clock64();                                          \
   } while (0)
 
+template <bool BNB>
 __global__ void __launch_bounds__(kTThreads, 1)
 umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -114,6 +120,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);  // [2][256]
   float* s_bias = s_stats + 512;                            // [256]
   uint32_t* s_taps = reinterpret_cast<uint32_t*>(s_bias + 256);  // [4 phases][dw pack, dh pack, sub-tiles, -]
+  float4* s_bn = reinterpret_cast<float4*>(s_taps + 16);         // [256] {mean, scale, beta, rstd} (BNB only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const GatherGeom& g = P.g;
@@ -122,6 +129,8 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
 
   for (int i = threadIdx.x; i < 512; i += kTThreads) s_stats[i] = 0.0f;
   for (int i = threadIdx.x; i < 256; i += kTThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
+  if constexpr (BNB)
+    for (int i = threadIdx.x; i < N; i += kTThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kTStagesMax; ++s) {
@@ -261,9 +270,11 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const int ew = warp & 3;           // TMEM lane group = warp % 4
     const int eset = (warp - 2) >> 2;  // warps 2-5 serve accumulator 0 (even tiles), 6-9 accumulator 1
     const int r = ew * 32 + lane;
-    float run1[32], run2[32];
+    const uint32_t s_bn_a = smem_u32(s_bn);
+    constexpr int RUN = BNB ? 1 : 32;   // BNB: the y prefetch needs the registers of the running sums
+    float run1[RUN], run2[RUN];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.0f;
+    for (int i = 0; i < RUN; ++i) run1[i] = run2[i] = 0.0f;
     for (int it = eset, tile = blockIdx.x + eset * gridDim.x; tile < P.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int phase = tile / P.tiles_per_phase;
       const int mt = tile - phase * P.tiles_per_phase;
@@ -280,11 +291,25 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
         const int oh = (int)jh * g.out_mul + tt.ph, ow = (int)jw * g.out_mul + tt.pw;
         dst = P.out + (((long long)b * g.Hout + oh) * g.Wout + ow) * P.ldo;
       }
+      // fused BN backward: y of this thread's pixel, 32 channels at a time, requested one chunk ahead
+      uint4 ycur[4], ynext[4];
+      const bf16* ysrc = nullptr;
+      if constexpr (BNB) {
+        ysrc = P.bn_y + (dst != nullptr ? (long long)(dst - P.out) : 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ycur[q] = ldg_nc_v4_pinned(reinterpret_cast<const uint4*>(ysrc) + q);
+      }
       mbar_wait(&tfull_bar[acc], acc_ph);
       if (ew == 0) VAE_TTRACE(4, it);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
       for (int c0 = 0; c0 < N; c0 += 32) {
+        if constexpr (BNB) {
+          if (c0 + 32 < N) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ynext[q] = ldg_nc_v4_pinned(reinterpret_cast<const uint4*>(ysrc + c0 + 32) + q);
+          }
+        }
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -302,6 +327,29 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
           v[i + 2] = (valid && i + 2 < ncol) ? v[i + 2] + b4.z : 0.0f;
           v[i + 3] = (valid && i + 3 < ncol) ? v[i + 3] + b4.w : 0.0f;
         }
+        float second[32];   // second statistic: y^2 (forward) or du * xhat (fused BN backward)
+        if constexpr (BNB) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w4[4] = {ycur[q].x, ycur[q].y, ycur[q].z, ycur[q].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int i = q * 8 + k;
+              const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
+              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 16));   // mean, scale, beta, rstd
+              const float t = yv - c4.x;
+              const float u = fmaf(t, c4.y, c4.z);           // same expression as the forward apply (bn_affine)
+              const float du = u > 0.0f ? v[i] : v[i] * P.slope;
+              v[i] = du;
+              second[i] = du * (t * c4.w);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) ycur[q] = ynext[q];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
+        }
         if (valid) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
@@ -315,32 +363,33 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
           }
         }
         if (P.stats != nullptr) {
-          if (N <= 32) {
+          if (!BNB && N <= 32) {
+            if constexpr (!BNB) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              run1[i] += v[i];
-              run2[i] = fmaf(v[i], v[i], run2[i]);
+              for (int i = 0; i < 32; ++i) {
+                run1[i] += v[i];
+                run2[i] += second[i];
+              }
             }
           } else {
-            float sq[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
             warp_transpose_reduce32(v, lane);
-            warp_transpose_reduce32(sq, lane);
+            warp_transpose_reduce32(second, lane);
             if (lane < ncol) {
               atomicAdd(&s_stats[c0 + lane], v[0]);
-              atomicAdd(&s_stats[256 + c0 + lane], sq[0]);
+              atomicAdd(&s_stats[256 + c0 + lane], second[0]);
             }
           }
         }
       }
     }
-    if (P.stats != nullptr && N <= 32) {
-      warp_transpose_reduce32(run1, lane);
-      warp_transpose_reduce32(run2, lane);
-      if (lane < N) {
-        atomicAdd(&s_stats[lane], run1[0]);
-        atomicAdd(&s_stats[256 + lane], run2[0]);
+    if constexpr (!BNB) {
+      if (P.stats != nullptr && N <= 32) {
+        warp_transpose_reduce32(run1, lane);
+        warp_transpose_reduce32(run2, lane);
+        if (lane < N) {
+          atomicAdd(&s_stats[lane], run1[0]);
+          atomicAdd(&s_stats[256 + lane], run2[0]);
+        }
       }
     }
     if (P.stats != nullptr) {
@@ -474,8 +523,9 @@ extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, 
 /* Conv forward (mode 0) / data gradient == ConvTranspose forward (mode 1) with the A
  * operand staged by tiled TMA loads.  Same contract as vae_conv_umma (no prologue);
  * wpk from vae_umma_tma_pack_weight. */
-extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
-                                 int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+static int tma_dispatch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi,
+                        int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* const* bn_vec,
+                        float slope) {
   VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
                   (mode == 0 || mode == 1),
               "conv_umma_tma: bad argument");
@@ -502,12 +552,15 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n_total, st));
   P.ldo = n_total;
   P.trace = umma_trace_ptr();
-  size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VAE_CUDA(cudaFuncSetAttribute(umma_tma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64 +
+                (bn_y != nullptr ? 256 * 16 : 0);
+  auto kern = bn_y != nullptr ? umma_tma_conv_kernel<true> : umma_tma_conv_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bn_y != nullptr]) {
+    VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[bn_y != nullptr] = true;
   }
+  P.bn_y = nullptr; P.slope = slope;
   int grid = sm_count();
   if (grid > P.total_tiles) grid = P.total_tiles;
   const long long per = tma_packed_elems(P);
@@ -517,9 +570,31 @@ extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* b
     P.out = (bf16*)out + s * g.Nout;
     P.stats = stats ? stats + s * g.Nout : nullptr;
     P.stats2 = stats ? stats + n_total + s * g.Nout : nullptr;
-    umma_tma_conv_kernel<<<grid, kTThreads, smem, st>>>(P);
+    if (bn_y != nullptr) {
+      P.bn_y = (const bf16*)bn_y + s * g.Nout;
+      P.bn_mean = bn_vec[0] + s * g.Nout; P.bn_scale = bn_vec[1] + s * g.Nout;
+      P.bn_beta = bn_vec[2] + s * g.Nout; P.bn_rstd = bn_vec[3] + s * g.Nout;
+    }
+    kern<<<grid, kTThreads, smem, st>>>(P);
     int rc = check_launch("umma_tma_conv");
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+extern "C" int vae_conv_umma_tma(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B,
+                                 int Hi, int Wi, int Ci, int Co, int stride, int mode, vae_stream_t stream) {
+  return tma_dispatch(in, wpk, bias, out, stats, B, Hi, Wi, Ci, Co, stride, mode, stream, nullptr, nullptr, 0.0f);
+}
+
+/* vae_conv_umma_tma with the first half of the BatchNorm backward of the layer below fused into the epilogue;
+ * same contract as vae_conv_umma_rw_bnbwd (out = du, dstats = {sum du, sum du * xhat}).
+ * replaces: the LeakyReLU / native_batch_norm_backward reductions of train.py:650 for the layer below */
+extern "C" int vae_conv_umma_tma_bnbwd(const void* in, const void* wpk, void* out, const void* y, const float* mean,
+                                       const float* scale, const float* beta, const float* rstd, double* dstats,
+                                       float slope, int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
+                                       vae_stream_t stream) {
+  VAE_REQUIRE(y && mean && scale && beta && rstd && dstats, "conv_umma_tma_bnbwd: bad argument");
+  const float* vec[4] = {mean, scale, beta, rstd};
+  return tma_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, vec, slope);
 }

@@ -338,8 +338,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const double* __restrict__ dstats,
                     T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    float* __restrict__ dbias, long long n_pix, int C, float slope, int training) {
+                    float* __restrict__ dbias, long long n_pix, int C, float slope, int flags) {
   extern __shared__ float red[];  // [lanes][G][V]
+  const int training = flags & 1;
+  const bool is_du = (flags & 2) != 0;   // `dact` already holds du (a conv epilogue applied LeakyReLU')
   const int G = C / V;
   const int lanes = blockDim.x / G;
   const int g = threadIdx.x % G, lane = threadIdx.x / G;
@@ -389,7 +391,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
 #pragma unroll
           for (int k = 0; k < V; ++k) {
             float uu = bn_affine(yv[k], mu[k], sc[k], sh[k]);
-            float du = uu > 0.0f ? dv[k] : dv[k] * slope;
+            float du = (is_du || uu > 0.0f) ? dv[k] : dv[k] * slope;
             float xh = (yv[k] - mu[k]) * rs[k];
             float r = a[k] * (du - c1[k] - xh * c2[k]);
             o.v[k] = r;

@@ -20,6 +20,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// 16-byte read-only global load that stays where it is written: as `asm volatile` it is ordered against the
+// (volatile) mbarrier waits, so a load issued before a wait really flies during the wait (a plain __ldg is sunk
+// by the compiler to its first use, behind the wait)
+__device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4_addr(uint32_t a) {   // LDS.128 by 32-bit shared address (no generic LD)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // shared-memory matrix descriptor with a selectable swizzle (2 = 128B, 4 = 64B)
 __device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;

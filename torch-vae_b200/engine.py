@@ -69,6 +69,24 @@ def _bn_forward(y, stats, gamma, beta, bn, training: bool):
     return vec, ops.bn_apply_lrelu(y, vec, beta)
 
 
+# LeakyReLU' + the two BatchNorm-backward reductions fused into the epilogue of the conv that produces the
+# activation gradient (vae_conv_umma_{rw,tma}_bnbwd).  Correct (tests/test_umma_gpu.py, teacher-forced hops) but
+# measured SLOWER than the separate reduction pass on the B200 (the 8 epilogue warps of the
+# persistent conv kernels are issue / latency bound), so the step does not use it.
+FUSE_BN_BACKWARD = False
+
+
+def _bnbwd(saved_prev, beta_prev):
+    return (saved_prev[1], saved_prev[2], beta_prev) if FUSE_BN_BACKWARD else None
+
+
+def _conv_bnbwd(fn, dy, cw, bnbwd):
+    """fn(dy, cw[, bnbwd]) -> (d_act or du, dstats or None)."""
+    if bnbwd is None:
+        return (fn(dy, cw) if fn is ops.conv_data_grad else fn(dy, cw, None)), None
+    return fn(dy, cw, bnbwd=bnbwd) if fn is ops.conv_data_grad else fn(dy, cw, None, bnbwd=bnbwd)
+
+
 # Teacher-forcing hook for the parity tests: when a list is installed here, every backward hop appends
 # (name, {tensor name: tensor}) with exactly the tensors its kernels consumed and produced, so that a test can
 # redo that hop in exact arithmetic on IDENTICAL inputs (tests/test_bf16_rigor_gpu.py).  None in production.
@@ -161,13 +179,14 @@ class EncodeFn(torch.autograd.Function):
         d_act = ops.nchw_to_nhwc(d_pre, C, h, w)
         conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
         dx = None
+        dstats = None   # set when d_act already holds du: the producing conv fused LeakyReLU' + the BN reductions
         for i in range(len(specs) - 1, -1, -1):
             sp = specs[i]
             h_in, y, vec, cw, Hi, Wi = saved[i]
             gamma, beta = conv_params[4 * i + 2], conv_params[4 * i + 3]
             w_i, b_i = conv_params[4 * i], conv_params[4 * i + 1]
             dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training,
-                                                             outs=_dst3(sink, (gamma, beta, b_i)))
+                                                             outs=_dst3(sink, (gamma, beta, b_i)), dstats=dstats)
             conv_grads[4 * i] = ops.conv_weight_grad(h_in, dy, 2, sp.ci, sp.co, Hi, Wi, out=_dst(sink, w_i))
             conv_grads[4 * i + 1] = dbias
             conv_grads[4 * i + 2] = dgamma
@@ -175,13 +194,15 @@ class EncodeFn(torch.autograd.Function):
             if sink is not None:
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
-            d_in = d_act
+            d_in, d_in_is_du = d_act, dstats is not None
             if i > 0:
-                d_act = ops.conv_data_grad(dy, cw)
+                # gradient w.r.t. the activation of block i-1, with that block's LeakyReLU' and BN reductions fused
+                d_act, dstats = _conv_bnbwd(ops.conv_data_grad, dy, cw, _bnbwd(saved[i - 1], conv_params[4 * i - 1]))
             elif ctx.x_needs_grad:
                 dx = ops.nhwc_to_nchw(ops.conv_data_grad(dy, cw), torch.float32).view(B, sp.ci, Hi, Wi)
-            _trace(f"encoder.{i}", transposed=False, d_act=d_in, y=y, vec=vec, gamma=gamma, h_in=h_in, w=conv_params[4 * i],
-                   dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act if i > 0 else None,
+            _trace(f"encoder.{i}", transposed=False, d_act=d_in, d_act_is_du=d_in_is_du, y=y, vec=vec, gamma=gamma, h_in=h_in,
+                   w=conv_params[4 * i], dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act if i > 0 else None,
+                   d_out_bn=(saved[i - 1][1], saved[i - 1][2]) if i > 0 and dstats is not None else None,
                    training=ctx.training)
         ctx.saved = None
         if sink is not None:
@@ -283,6 +304,7 @@ class DecodeFn(torch.autograd.Function):
         dlog = dlog.view(B, H, W, 1)
         conv_grads: List[Optional[torch.Tensor]] = [None] * len(conv_params)
         n_blk = len(specs)
+        dstats = None   # see EncodeFn.backward
         if fused_last:
             # Conv2d(C->1) backward + LeakyReLU + BatchNorm backward in two passes over y
             _, y, vec, _ = saved[-1]
@@ -314,7 +336,8 @@ class DecodeFn(torch.autograd.Function):
                 dy, dgamma, dbeta, dbias = fused[:4]
             else:
                 dy, dgamma, dbeta, dbias = ops.bn_lrelu_backward(d_act, y, vec, gamma, beta, ctx.training,
-                                                                 outs=_dst3(sink, (gamma, beta, conv_params[4 * i + 1])))
+                                                                 outs=_dst3(sink, (gamma, beta, conv_params[4 * i + 1])),
+                                                                 dstats=dstats)
             Hi, Wi = y.shape[1], y.shape[2]
             # equivalent conv: X = convT output side (dy), Y = convT input (h_in)
             conv_grads[4 * i] = ops.conv_weight_grad(dy, h_in, 2, sp.ci, sp.co, Hi, Wi, out=_dst(sink, conv_params[4 * i]))
@@ -324,11 +347,15 @@ class DecodeFn(torch.autograd.Function):
             if sink is not None:
                 for k in range(4):
                     sink.push(conv_params[4 * i + k], conv_grads[4 * i + k])
-            d_in = d_act
-            d_act = ops.conv_forward(dy, cw, None)  # gradient w.r.t. the ConvT input
-            _trace(f"decoder.{i}", transposed=True, d_act=d_in, y=y, vec=vec, gamma=gamma, h_in=h_in, w=conv_params[4 * i],
-                   dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act, training=ctx.training,
-                   fused_bn=bool(fused_last and i == n_blk - 1))
+            d_in, d_in_is_du = d_act, dstats is not None
+            if i > 0:   # gradient w.r.t. the ConvT input = activation of block i-1: its LeakyReLU' + BN reductions fused
+                d_act, dstats = _conv_bnbwd(ops.conv_forward, dy, cw, _bnbwd(saved[i - 1], conv_params[4 * i - 1]))
+            else:       # decoder_input's output has no BatchNorm
+                d_act, dstats = ops.conv_forward(dy, cw, None), None
+            _trace(f"decoder.{i}", transposed=True, d_act=d_in, d_act_is_du=d_in_is_du, y=y, vec=vec, gamma=gamma, h_in=h_in,
+                   w=conv_params[4 * i], dy=dy, dgamma=dgamma, dbeta=dbeta, dw=conv_grads[4 * i], d_out=d_act,
+                   d_out_bn=(saved[i - 1][1], saved[i - 1][2]) if i > 0 and dstats is not None else None,
+                   training=ctx.training, fused_bn=bool(fused_last and i == n_blk - 1))
         d_d = ops.nhwc_to_nchw(d_act)  # [B, F] C-major, matching decoder_input's output
         L_, F_ = z.shape[1], w_in.shape[0]
         skinny = ops.heads_supported(F_, L_)

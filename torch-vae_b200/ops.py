@@ -230,23 +230,26 @@ def _small_outs(outs, C, device):
     return small[0], small[1], small[2]
 
 
-def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = LRELU_SLOPE, outs=None):
-    """-> (dy, dgamma, dbeta, dbias); ``outs`` = optional (dgamma, dbeta, dbias) destinations."""
+def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = LRELU_SLOPE, outs=None, dstats=None):
+    """-> (dy, dgamma, dbeta, dbias); ``outs`` = optional (dgamma, dbeta, dbias) destinations.  With ``dstats``
+    (from a conv_*(bnbwd=...) call) ``dact`` already holds du and the reduction pass is skipped."""
     C = y.shape[-1]
     n_pix = y.numel() // C
     lib = _L()
-    dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
-    rc = lib.vae_bn_lrelu_bwd_reduce(
-        _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
-        _p(dstats), n_pix, C, slope, code(y), _stream(),
-    )
-    _lib.check(rc, "vae_bn_lrelu_bwd_reduce")
+    is_du = dstats is not None
+    if not is_du:
+        dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+        rc = lib.vae_bn_lrelu_bwd_reduce(
+            _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
+            _p(dstats), n_pix, C, slope, code(y), _stream(),
+        )
+        _lib.check(rc, "vae_bn_lrelu_bwd_reduce")
     dy = torch.empty_like(y)
     dgamma, dbeta, dbias = _small_outs(outs, C, y.device)
     rc = lib.vae_bn_lrelu_bwd_apply(
         _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
         _f32(gamma, "bn weight"), _p(dstats), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), n_pix, C, slope,
-        1 if training else 0, code(y), _stream(),
+        (1 if training else 0) | (2 if is_du else 0), code(y), _stream(),
     )
     _lib.check(rc, "vae_bn_lrelu_bwd_apply")
     return dy, dgamma, dbeta, dbias
@@ -677,6 +680,27 @@ def conv_umma_rw(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int
     return out
 
 
+def conv_umma_bnbwd(kind: str, inp, wpk, y, vec, beta, Ci: int, Co: int, stride: int, mode: int, slope: float = LRELU_SLOPE):
+    """conv_umma_rw / conv_umma_tma producing the gradient w.r.t. act = lrelu(bn(y)) with LeakyReLU' and the two
+    BatchNorm-backward reductions fused into the epilogue -> (du, dstats[2C] fp64).  ``vec`` = the layer's
+    (scale, shift, mean, rstd) rows, ``y`` its stored conv output (shape of the result)."""
+    if inp.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+        raise RuntimeError("conv_umma_bnbwd: bf16 activations only")
+    C = y.shape[-1]
+    du = torch.empty_like(y)
+    dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+    B = inp.shape[0]
+    if mode == 0:
+        Hi, Wi = inp.shape[1], inp.shape[2]
+    else:
+        Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
+    fn = _L().vae_conv_umma_rw_bnbwd if kind == "rw" else _L().vae_conv_umma_tma_bnbwd
+    rc = fn(_p(inp), _p(wpk), _p(du), _p(y), vec[2].data_ptr(), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[3].data_ptr(),
+            _p(dstats), slope, B, Hi, Wi, Ci, Co, stride, mode, _stream())
+    _lib.check(rc, f"vae_conv_umma_{kind}_bnbwd")
+    return du, dstats
+
+
 class ConvWeights:
     """Per-step operand layouts of one 3x3 conv weight (fp32 OIHW master copy).
 
@@ -790,8 +814,20 @@ class PackBatch:
             self._event = None
 
 
-def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None):
-    """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies."""
+def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None, bnbwd=None):
+    """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies.
+
+    ``bnbwd`` = (y, vec, beta) of the BatchNorm block whose activation gradient this call produces (the conv runs
+    as the backward of a ConvTranspose2d): when a tcgen05 kernel serves the layer the result is (du, dstats) with
+    LeakyReLU' and the BatchNorm-backward reductions fused into the epilogue, else (d_act, None)."""
+    if bnbwd is not None:
+        y_, vec_, beta_ = bnbwd
+        if x.dtype == torch.bfloat16 and pro is None and bias is None and umma_available() and y_.dtype == torch.bfloat16:
+            if umma_rw_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+                return conv_umma_bnbwd("rw", x, cw.rw(0), y_, vec_, beta_, cw.Ci, cw.Co, cw.stride, 0)
+            if umma_tma_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+                return conv_umma_bnbwd("tma", x, cw.umma(0, tma=True), y_, vec_, beta_, cw.Ci, cw.Co, cw.stride, 0)
+        return conv_forward(x, cw, bias, stats, Ci, pro), None
     if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == cw.Ci:
         if pro is None and umma_available() and umma_rw_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
             return conv_umma_rw(x, cw.rw(0), bias, stats, cw.Ci, cw.Co, cw.stride, 0)
@@ -805,8 +841,18 @@ def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None,
     return conv_fprop(x, cw.simt()[0], bias, cw.stride, cw.dtype, stats, Ci=Ci if Ci is not None else cw.Ci)
 
 
-def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None):
-    """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward."""
+def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None, bnbwd=None):
+    """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward.
+    ``bnbwd``: see conv_forward."""
+    if bnbwd is not None:
+        y_, vec_, beta_ = bnbwd
+        s_ = cw.stride
+        if dy.dtype == torch.bfloat16 and pro is None and bias is None and umma_available() and y_.dtype == torch.bfloat16:
+            if umma_rw_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+                return conv_umma_bnbwd("rw", dy, cw.rw(1), y_, vec_, beta_, cw.Ci, cw.Co, s_, 1)
+            if umma_tma_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+                return conv_umma_bnbwd("tma", dy, cw.umma(1, tma=True), y_, vec_, beta_, cw.Ci, cw.Co, s_, 1)
+        return conv_data_grad(dy, cw, bias, stats, pro), None
     if dy.dtype == torch.bfloat16:
         s_ = cw.stride
         if pro is None and umma_available() and umma_rw_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
