@@ -686,6 +686,43 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   }
 }
 
+
+// ---- LeakyReLU branch of u = fmaf(y, scale, shift) as a bf16 COMPARISON ----------------------------------
+// y is a stored bf16 value, so the predicate g(y) = [fmaf(y, scale, shift) > 0] (the forward kernel's own
+// expression; one rounding, which preserves the sign) is a step function of y: for scale > 0 there is a
+// largest bf16 value T with g(T) false and g(y) <=> y > T; for scale < 0 the same holds for -y.  T is found
+// from -shift/scale and then corrected by walking the bf16 grid with g itself, so the comparison agrees with
+// the forward's branch for EVERY bf16 input.  One HSET2 per channel pair replaces unpack + FMA + compare.
+__device__ __forceinline__ uint32_t bf16_bits_step(uint32_t b, bool up) {   // neighbour on the bf16 grid (finite range)
+  const bool neg = (b & 0x8000u) != 0;
+  const uint32_t mag = b & 0x7FFFu;
+  if (mag == 0) return up ? 0x0001u : 0x8001u;
+  const bool grow = (up != neg);   // moving away from zero
+  return (uint32_t)((neg ? 0x8000u : 0u) | (grow ? mag + 1 : mag - 1));
+}
+__device__ __forceinline__ float bf16_bits_to_f(uint32_t b) { return __uint_as_float(b << 16); }
+
+// -> {threshold bits (bf16), sign-flip mask (0x8000 when scale < 0)}
+__device__ __forceinline__ void lrelu_threshold(float scale, float shift, uint32_t* thr, uint32_t* sgn) {
+  if (scale == 0.0f || !(scale == scale) || !(shift == shift)) {   // constant branch (NaN parameters: "false")
+    *thr = (shift > 0.0f) ? 0xFF80u : 0x7F80u;   // y > -inf: always; y > +inf: never
+    *sgn = 0u;
+    return;
+  }
+  const float s = fabsf(scale);
+  *sgn = scale < 0.0f ? 0x8000u : 0u;
+  auto g = [&](uint32_t bits) { return fmaf(bf16_bits_to_f(bits), s, shift) > 0.0f; };   // predicate on y' = +-y
+  const uint32_t kMaxPos = 0x7F7Fu, kMaxNeg = 0xFF7Fu;
+  if (g(kMaxNeg)) { *thr = 0xFF80u; return; }    // true on the whole finite range
+  if (!g(kMaxPos)) { *thr = 0x7F80u; return; }   // false on the whole finite range
+  const double t = -(double)shift / (double)s;   // finite here, inside the bf16 range
+  uint32_t T = __float_as_uint((float)t) >> 16;  // truncation: a nearby grid point; corrected below
+  if ((T & 0x7F80u) == 0x7F80u) T = (T & 0x8000u) | 0x7F7Fu;
+  for (int it = 0; it < 300 && g(T); ++it) T = bf16_bits_step(T, false);                        // ensure g(T) false
+  for (int it = 0; it < 300 && T != kMaxPos && !g(bf16_bits_step(T, true)); ++it) T = bf16_bits_step(T, true);
+  *thr = T;
+}
+
 // =============================================================================================
 // backward pass 1, all-GEMM form.  With b = [u > 0] (u = scale*y + shift), q = slope + (1-slope)*b:
 //     du  = q * da,   da[p][c] = sum_w dlwin[p][w] * wf[c][w]        (wf[c][w] = w_last[c][8 - w])
@@ -703,7 +740,7 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 constexpr int kP1Slots = 3;
 constexpr int kP1Ring = kP1Slots * kRowBytes;   // L
 constexpr size_t kP1SmemBytes = 1024 + 3 * kP1Ring + kA1Bufs * kRowBytes + 8192 + 64 * 4 + (3 * 32 * 9 + 16) * 4 +
-                                8 * (3 * kP1Slots + kA1Bufs + 1) + 16;
+                                8 * (3 * kP1Slots + kA1Bufs + 1) + 16 + 32 * 4;
 
 __global__ void __launch_bounds__(kFtThreads, 2)
 final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
@@ -719,6 +756,8 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
   uint64_t* a1ready_bar = opready_bar + kP1Slots;
   uint64_t* done_bar = a1ready_bar + kA1Bufs;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint16_t* thr_s = reinterpret_cast<uint16_t*>(tmem_ptr + 4);   // [32] branch thresholds, [32] sign-flip masks
+  uint16_t* sgn_s = thr_s + 32;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = P.H, RB = P.RB;
@@ -740,8 +779,13 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
     const int tid = threadIdx.x;
     if (tid < 32) {
       const float sc = P.scale[tid];
+      const float sh = fmaf(-P.mean[tid], sc, P.beta[tid]);
       cst[tid] = sc;
-      cst[32 + tid] = fmaf(-P.mean[tid], sc, P.beta[tid]);
+      cst[32 + tid] = sh;
+      uint32_t thr, sgn;
+      lrelu_threshold(sc, sh, &thr, &sgn);
+      thr_s[tid] = (uint16_t)thr;
+      sgn_s[tid] = (uint16_t)sgn;
     }
     for (int i = tid; i < kA1Bufs * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(a1)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 16; i += kFtWorkers) gsm[3 * 32 * 9 + i] = 0.0f;
@@ -794,9 +838,17 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
   } else {
     // =============================== workers ==============================
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const uint32_t y_a = smem_u32(yring), a1_a = smem_u32(a1), cst_a = smem_u32(cst);
+    const uint32_t y_a = smem_u32(yring), a1_a = smem_u32(a1);
     const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
     const uint32_t a1off0 = swz64(p, 0), a1off1 = swz64(p, 1);
+    // this thread's 16 channels (two 16-byte chunks) as 8 bf16x2 words: thresholds and sign-flip masks
+    uint32_t thr2[8], sgn2[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = half * 16 + 2 * w;
+      thr2[w] = (uint32_t)thr_s[c] | ((uint32_t)thr_s[c + 1] << 16);
+      sgn2[w] = (uint32_t)sgn_s[c] | ((uint32_t)sgn_s[c + 1] << 16);
+    }
     float colsum[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) colsum[k] = 0.0f;
@@ -874,19 +926,18 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const uint32_t a = row + (j == 0 ? off0 : off1);
-          const uint32_t cb = cst_a + (uint32_t)((2 * half + j) * 32);
-          float y[8], scv[8], shv[8], bb[8], by[8];
-          unpack8(lds128(a), y);
-          load8f(cb, scv);
-          load8f(cb + 128, shv);
+          const uint4 raw = lds128(a);
+          const uint32_t yw[4] = {raw.x, raw.y, raw.z, raw.w};
+          uint32_t bw[4], byw[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const bool pos = fmaf(y[k], scv[k], shv[k]) > 0.0f;
-            bb[k] = pos ? 1.0f : 0.0f;
-            by[k] = pos ? y[k] : 0.0f;
+          for (int w = 0; w < 4; ++w) {
+            // b = [u > 0] as bf16 1.0 / 0.0 for two channels at once; b * y is exact (y or +-0)
+            const uint32_t yy = yw[w] ^ sgn2[j * 4 + w];
+            asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(bw[w]) : "r"(yy), "r"(thr2[j * 4 + w]));
+            asm("mul.bf16x2 %0, %1, %2;" : "=r"(byw[w]) : "r"(bw[w]), "r"(yw[w]));
           }
-          sts128(a + kP1Ring, pack8(bb));
-          sts128(a + 2 * kP1Ring, pack8(by));
+          sts128(a + kP1Ring, make_uint4(bw[0], bw[1], bw[2], bw[3]));
+          sts128(a + 2 * kP1Ring, make_uint4(byw[0], byw[1], byw[2], byw[3]));
         }
         fence_proxy_async_smem();
         mbar_arrive(&opready_bar[slot]);
