@@ -44,6 +44,38 @@ data_params:
         tv.config.load_config(str(tmp_path / "bad.yaml"))
 
 
+def test_launcher_flags_follow_the_reference_cli(tmp_path):
+    """torch_vae_b200.train: the train.py:770-1063 flag subset of the hot path, the configs/vae.yaml defaults, and
+    the lr rule of train.py:201 (per 128 samples, scaled by the global batch)."""
+    from torch_vae_b200 import train as launcher
+
+    cfg = launcher.get_parser().parse_args([])
+    launcher._apply_yaml(cfg)
+    # reference defaults: train.py:877 (n_features 10), :886 (epochs 5), :894 (lr 0.01), :930 (wd 0), batch 128
+    assert (cfg.n_features, cfg.epochs, cfg.lr_relative, cfg.weight_decay, cfg.batch_size_per_gpu) == (10, 5, 0.01, 0.0, 128)
+    assert cfg.hidden_dims == [32, 64, 128, 256] and cfg.kld_weight == 1.0 and cfg.lr_absolute is None
+    assert cfg.optimizer == "AdamW" and cfg.scheduler == "OneCycle" and cfg.arch == "VanillaVAE"
+    y = tmp_path / "vae.yaml"
+    y.write_text("model_params:\n  latent_dim: 24\n  hidden_dims: [64, 128, 256, 512]\nexp_params:\n  learning_rate: 0.002\n"
+                 "  weight_decay: 0.0001\n  kld_weight: 0.00025\n  manual_seed: 7\ndata_params:\n  train_batch_size: 100\n"
+                 "trainer_params:\n  max_epochs: 100\nlogging_params:\n  log_interval: 25\n")
+    cfg = launcher.get_parser().parse_args(["--config", str(y), "--epochs", "3", "--wd", "0.5"])
+    launcher._apply_yaml(cfg)
+    assert (cfg.n_features, cfg.hidden_dims, cfg.kld_weight, cfg.seed) == (24, [64, 128, 256, 512], 0.00025, 7)
+    assert (cfg.epochs, cfg.weight_decay, cfg.batch_size_per_gpu, cfg.log_interval) == (3, 0.5, 100, 25)   # flags win over YAML
+    assert cfg.lr_absolute == 0.002   # the YAML learning rate is absolute; --lr is relative
+    cfg = launcher.get_parser().parse_args(["--config", str(y), "--lr", "0.02", "--image-size", "128x1024"])
+    launcher._apply_yaml(cfg)
+    assert cfg.lr_absolute is None and cfg.lr_relative == 0.02 and launcher._image_size(cfg.image_size) == (128, 1024)
+    assert launcher._image_size("64") == (64, 64)
+    with pytest.raises(RuntimeError):   # no CUDA device here: the launcher refuses instead of falling back
+        launcher.run(launcher.get_parser().parse_args([]))
+    from torch_vae_b200.trainer import DeviceRollDataset
+
+    with pytest.raises(RuntimeError):
+        DeviceRollDataset(torch.zeros(8, 128, 144, dtype=torch.uint8), None, 4)   # host tensor: the dataset lives in HBM
+
+
 def test_transform_registry_mirrors_reference():
     import torch_vae_b200 as tv
 

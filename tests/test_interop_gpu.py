@@ -239,3 +239,28 @@ def test_fused_onecycle_under_graph_replay_matches_torch(tv):
     assert abs(lrs_ref[-1][0] - lrs_ref[3][0]) > 1e-4  # the schedule really moved
     for a, b in zip(ref_p, got_p):
         assert vo.rel_err(b, a) <= 5e-6
+
+
+def test_launcher_trains_checkpoints_and_resumes(tv, tmp_path):
+    """python -m torch_vae_b200.train: device-resident rolls, graph-replayed step, the safe_save_model file layout
+    (utils.py:311-351 / train.py:445-460) and a resume that continues the counters and the OneCycle schedule."""
+    from torch_vae_b200 import train as launcher
+
+    ck = str(tmp_path / "models" / "checkpoint_latest.pt")
+    argv = ["--image-size", "32", "--batch-size", "16", "--n-rolls", "128", "--epochs", "2", "--checkpoint", ck, "--seed", "3",
+            "--log-interval", "4", "--dtype", "fp32"]
+    r1 = launcher.main(argv[:])
+    assert r1 == 0 and os.path.isfile(ck)
+    data = torch.load(ck, map_location="cpu", weights_only=False)
+    assert {"encoder", "decoder", "optimizer", "scheduler", "config", "epoch", "total_step", "n_samples_seen"} <= set(data)
+    assert data["epoch"] == 2 and data["total_step"] == 16 and data["n_samples_seen"] == 16 * 16
+    if rd.available():   # the reference's resume path (train.py:325-328) finds its keys and shapes
+        ref = rd.build_model(32, 32, [32, 64, 128, 256], 10)
+        ref.encoder.load_state_dict(data["encoder"])
+        ref.decoder.load_state_dict(data["decoder"])
+        torch.optim.AdamW([{"params": ref.encoder.parameters()}, {"params": ref.decoder.parameters()}]).load_state_dict(data["optimizer"])
+    # resume for one more epoch: counters continue
+    cfg = launcher.get_parser().parse_args(argv[:7] + ["3"] + argv[8:])
+    out = launcher.run(cfg)
+    assert out["total_step"] == 24 and out["n_samples_seen"] == 24 * 16
+    assert out["loss"] == out["loss"] and 0.0 < out["loss"] < 10.0   # finite

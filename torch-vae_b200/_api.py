@@ -1,6 +1,6 @@
 """Public surface of the B200-native VanillaVAE training path."""
 
-from . import config, data_transformations, engine, ops, optim, parallel  # noqa: F401
+from . import config, data_transformations, engine, ops, optim, parallel, trainer  # noqa: F401
 from ._lib import LIB_PATH, load as load_library  # noqa: F401
 from .models import VanillaVAE
 from .optim import FusedAdamW
@@ -18,6 +18,7 @@ __all__ = [
     "parallel",
     "config",
     "data_transformations",
+    "trainer",
     "load_library",
     "LIB_PATH",
 ]
