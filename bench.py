@@ -178,6 +178,11 @@ def algorithmic_cost(name, tag):
         B, Hi, Wi, Ci, Co, s = t[:6]
         Ho, Wo = Hi // s, Wi // s
         return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co + 9 * Ci * Co), 2 * B * Ho * Wo * Co * 9 * Ci)
+    if name in ("vae_conv_umma_rw_bnbwd", "vae_conv_umma_tma_bnbwd"):   # + one read of y (shape of the output)
+        B, Hi, Wi, Ci, Co, s, mode = t[:7]
+        Ho, Wo = Hi // s, Wi // s
+        out_elems = B * Ho * Wo * Co if mode == 0 else B * Hi * Wi * Ci
+        return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co + 9 * Ci * Co + out_elems), 2 * B * Ho * Wo * Co * 9 * Ci)
     if name in ("vae_conv_wgrad_umma", "vae_conv_wgrad_tma"):
         B, Hi, Wi, Ci, Co, s = t[:6]
         Ho, Wo = Hi // s, Wi // s
@@ -238,12 +243,13 @@ def algorithmic_cost(name, tag):
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can dominate
 # the B=512 step, from ONE `ncu --set full` capture per kernel (scripts/profile_top.py): the output-block
-# kernels from profiles/r01g_ncu_full_output_block.csv, the conv kernels from profiles/r01e_ncu_full_top_kernels.csv.
+# kernels from profiles/r02i_ncu_full_output_block.csv (final code of round 2), the conv kernels from
+# profiles/r01e_ncu_full_top_kernels.csv.
 # Keyed by (C-ABI entry point, leading integer arguments).
 NCU_TRAFFIC_BYTES = {
-    ("vae_final_conv_fwd_tc", (512, 128, 128, 32)): 559.57e6 + 44.75e6,
-    ("vae_final_bwd_reduce_tc", (512, 128, 128, 32)): 553.83e6 + 8.33e6,
-    ("vae_final_bwd_apply_tc", (512, 128, 128, 32)): 554.86e6 + 495.45e6,
+    ("vae_final_conv_fwd_tc", (512, 128, 128, 32)): 559.65e6 + 46.16e6,
+    ("vae_final_bwd_reduce_tc", (512, 128, 128, 32)): 553.81e6 + 3.85e6,
+    ("vae_final_bwd_apply_tc", (512, 128, 128, 32)): 554.86e6 + 495.68e6,
     ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 1)): 134.33e6 + 477.68e6,
     ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 0)): 536.98e6 + 118.08e6,
     ("vae_conv_wgrad_tma", (512, 128, 128, 32, 32, 2)): 671.55e6 + 6.52e6,
