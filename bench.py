@@ -235,6 +235,12 @@ def algorithmic_cost(name, tag):
     if name in ("vae_nhwc_to_nchw", "vae_nchw_to_nhwc"):
         B, HW, C, ds, dd = t[:5]
         return (B * HW * C * (_sz(ds) + _sz(dd)), 0)
+    if name in ("vae_linear_reduce_tc", "vae_linear_wgrad_tc"):   # M, L, F: fp32 weight / gradient + bf16 activations
+        M, L, F = t[:3]
+        return (4 * L * F + 2 * M * F + 4 * M * L, 2 * M * L * F)
+    if name == "vae_linear_expand_tc":   # M, L, F, layout, dtype of the output
+        M, L, F = t[:3]
+        return (4 * L * F + _sz(t[4] if len(t) > 4 else 1) * M * F + 4 * M * L, 2 * M * L * F)
     if name == "vae_gemm":
         M, N, K = t[:3]
         return (4 * (M * K + K * N + M * N), 2 * M * N * K)

@@ -351,6 +351,28 @@ int vae_gemm(const void* A, const void* Bm, void* C, const float* bias, int M, i
              long long sam, long long sak, long long sbk, long long sbn, long long scm,
              long long scn, int dtA, int dtB, int dtC, int accumulate, vae_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Tensor-core Linear kernels for a WIDE latent (L in {64,128,192,256}, batch M <= 64, F >= 4096 a multiple of 64;
+ * the long / wide configuration has F = 262 144, L = 256): every call streams the fp32 master weight (or writes
+ * the fp32 gradient) once, rounds operands to bf16 while the mma.sync fragments are formed, accumulates in fp32.
+ * Layout codes: 0 = [L][F] (fc_mu / fc_var, models.py:55-56), 1 = [F][L] (decoder_input, models.py:59).
+ * ---------------------------------------------------------------------- */
+int vae_linear_tc_supported(int M, int L, int F);
+/* out[M][L] (fp32, overwritten) = A[M][F] (bf16) . W + bias.
+ * replaces: aten::addmm of fc_mu / fc_var (models.py:137,141; layout 0) and the latent gradient of
+ * decoder_input (train.py:650; layout 1) */
+int vae_linear_reduce_tc(const void* A, const float* W, const float* bias, float* out, int M, int L, int F,
+                         int w_layout, vae_stream_t stream);
+/* out[M][F] (dt_out) = bias[f] + D0[M][L] . W0 (+ D1 . W1), D fp32.
+ * replaces: aten::addmm of decoder_input (models.py:162; layout 1) and the input gradient of fc_mu + fc_var
+ * (train.py:650; layout 0, both heads in one pass) */
+int vae_linear_expand_tc(const float* D0, const float* W0, const float* D1, const float* W1, const float* bias,
+                         void* out, int M, int L, int F, int w_layout, int dt_out, vae_stream_t stream);
+/* G (fp32, overwritten; layout 0: [L][F], 1: [F][L]) = D[M][L]^T . A[M][F], D fp32, A bf16.
+ * replaces: the weight gradients of the three Linear layers (train.py:650) */
+int vae_linear_wgrad_tc(const float* D, const void* A, float* G, int M, int L, int F, int g_layout,
+                        vae_stream_t stream);
+
 /* out[n] = sum_m A[m,n]  (bias gradients).  replaces: aten::sum in addmm backward */
 int vae_colsum(const void* A, float* out, int M, int N, int dtype, vae_stream_t stream);
 

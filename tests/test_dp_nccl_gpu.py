@@ -75,22 +75,29 @@ def _worker(rank, world, port, use_graph, dtype_name, q):
         got = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()}
         # oracle: mean over ranks of the single-rank gradients on each shard (fresh BN buffers do not matter for grads)
         refs = [vo.step(params, sx, se, dtype=torch.float64) for sx, se in shards]
-        r32 = [vo.step(params, sx, se) for sx, se in shards]
+        if dtype_name == "fp32":   # yard-stick: the reference's own fp32 arithmetic; bf16: its bf16-storage emulation
+            yard = [vo.step(params, sx, se) for sx, se in shards]
+        else:
+            from oracle import bf16_emulation as emu
+
+            yard = [emu.step(params, sx, se) for sx, se in shards]
         worst = {}
         for k in got:
             mean64 = sum(r["grads"][k] for r in refs) / world
-            mean32 = sum(r["grads"][k].double() for r in r32) / world
+            mean_y = sum(r["grads"][k].double() for r in yard) / world
             floor = sum(vo.grad_floor(r["grads"], k) for r in refs) / world
             e = vo.rel_err(got[k], mean64, floor)
-            noise = vo.rel_err(mean32, mean64, floor)
-            tol = max(1e-5, 4 * noise) if dtype_name == "fp32" else max(2e-2, 4 * noise)
+            noise = vo.rel_err(mean_y, mean64, floor)
+            tol = max(1e-5, 4 * noise) if dtype_name == "fp32" else max(2e-2, 3 * noise)
             worst[k] = (e, noise, tol)
         bad = {k: v for k, v in worst.items() if v[0] > v[2]}
         if dtype_name == "fp32":
             ok = len(bad) <= 2 and all(v[0] <= 5e-5 for v in bad.values())
-        else:
+        else:   # the rule of tests/test_bf16_rigor_gpu.py (b): 3x the emulation (two parameters up to 5x), medians comparable
             vals = sorted(v[0] for v in worst.values())
-            ok = vals[len(vals) // 2] <= 1e-2
+            yvals = sorted(v[1] for v in worst.values())
+            ok = (len(bad) <= 2 and all(v[0] <= max(2e-2, 5 * v[1]) for v in bad.values())
+                  and vals[len(vals) // 2] <= max(1e-2, 1.5 * yvals[len(yvals) // 2]))
         # every rank must hold the SAME reduced gradient
         flat = torch.cat([p.grad.flatten() for p in model.parameters()])
         lo, hi = flat.clone(), flat.clone()

@@ -494,3 +494,44 @@ def test_fused_adamw_matches_torch(tv):
         assert float(got.state[b]["step"]) == 5.0
     ref2 = torch.optim.AdamW(groups(got_p), lr=1e-3, weight_decay=0.01)
     ref2.load_state_dict(got.state_dict())  # checkpoint compatibility (train.py:445-460)
+
+
+# ---------------------------------------------------------------------------
+# tensor-core Linear kernels for a wide latent (linear_tc.cu): fc_mu / fc_var / decoder_input at L = 64 .. 256
+# ---------------------------------------------------------------------------
+LT_CASES = [(64, 256, 8192), (8, 256, 4096), (33, 64, 4160), (64, 128, 12288), (16, 192, 8192)]
+
+
+@pytest.mark.parametrize("case", LT_CASES, ids=[f"M{m}-L{l}-F{f}" for m, l, f in LT_CASES])
+def test_wide_latent_linear_kernels(tv, case):
+    """Every routed call of ops.linear_* against fp64 matmuls of the bf16-rounded operands (the kernels round the
+    fp32 master weights and the fp32 latent operands to bf16 when they form the tensor-core fragments)."""
+    ops = tv.ops
+    M, L, F_ = case
+    assert ops.linear_tc_supported(M, L, F_)
+    g = torch.Generator().manual_seed(5)
+    bf = lambda t: t.bfloat16().double()
+    pre = (torch.randn(M, F_, generator=g) * 0.5).bfloat16()
+    w_lf = torch.randn(L, F_, generator=g) / math.sqrt(F_)
+    w_fl = torch.randn(F_, L, generator=g) / math.sqrt(L)
+    b_l, b_f = torch.randn(L, generator=g), torch.randn(F_, generator=g)
+    d0, d1 = torch.randn(M, L, generator=g), torch.randn(M, L, generator=g)
+    l0 = ops.LAUNCHES
+    # fc_mu / fc_var forward
+    mu = ops.linear_fwd(pre.cuda(), w_lf.cuda(), b_l.cuda(), torch.float32)
+    assert rel_err(mu.cpu(), pre.double() @ bf(w_lf).t() + b_l.double()) <= 2e-5
+    # decoder_input forward (bf16 output)
+    dec = ops.linear_fwd(d0.cuda(), w_fl.cuda(), b_f.cuda(), torch.bfloat16)
+    assert rel_err(dec.float().cpu(), bf(d0) @ bf(w_fl).t() + b_f.double()) <= 3e-3
+    # input gradient of the two heads, one pass
+    dpre = ops.linear_bwd_input_pair(d0.cuda(), w_lf.cuda(), d1.cuda(), (w_lf * 0.5 + 0.01).cuda(), torch.bfloat16)
+    assert rel_err(dpre.float().cpu(), bf(d0) @ bf(w_lf) + bf(d1) @ bf(w_lf * 0.5 + 0.01)) <= 3e-3
+    # latent gradient of decoder_input
+    dz = ops.linear_bwd_input(pre.cuda(), w_fl.cuda(), out_dtype=torch.float32)
+    assert rel_err(dz.cpu(), pre.double() @ bf(w_fl)) <= 2e-5
+    # weight gradients in both layouts
+    gw = ops.linear_bwd_weight(d0.cuda(), pre.cuda())
+    assert gw.shape == (L, F_) and rel_err(gw.cpu(), bf(d0).t() @ pre.double()) <= 2e-5
+    gw_in = ops.linear_bwd_weight(pre.cuda(), d0.cuda())
+    assert gw_in.shape == (F_, L) and rel_err(gw_in.cpu(), pre.double().t() @ bf(d0)) <= 2e-5
+    assert ops.LAUNCHES - l0 == 6   # one launch each: no packing pass, no second accumulation pass

@@ -57,6 +57,10 @@ PROTOTYPES = {
     "vae_final_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
     "vae_final_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f,
                             _i, _i, _vp],
+    "vae_linear_tc_supported": [_i, _i, _i],
+    "vae_linear_reduce_tc": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "vae_linear_expand_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "vae_linear_wgrad_tc": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "vae_set_final_tc": [_i],
     "vae_final_tc_supported": [_i, _i, _i, _i, _i],
     "vae_final_conv_fwd_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],

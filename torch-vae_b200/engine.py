@@ -163,8 +163,7 @@ class EncodeFn(torch.autograd.Function):
             g_w_mu, _ = ops.skinny_wgrad(dmu, pre, (L, F_), F_, 1, False, out=_dst(sink, w_mu))
             g_w_var, _ = ops.skinny_wgrad(dlv, pre, (L, F_), F_, 1, False, out=_dst(sink, w_var))
         else:
-            d_pre = ops.linear_bwd_input(dmu, w_mu, out_dtype=pre.dtype)
-            ops.linear_bwd_input(dlv, w_var, out=d_pre, accumulate=True)
+            d_pre = ops.linear_bwd_input_pair(dmu, w_mu, dlv, w_var, pre.dtype)
             g_w_mu = ops.linear_bwd_weight(dmu, pre, out=_dst(sink, w_mu))
             g_w_var = ops.linear_bwd_weight(dlv, pre, out=_dst(sink, w_var))
         if dpre is not None:

@@ -66,7 +66,7 @@ class _Proxy:
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
                           "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported", "vae_set_final_tc",
-                          "vae_final_tc_supported"})
+                          "vae_final_tc_supported", "vae_linear_tc_supported"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -409,11 +409,27 @@ def skinny_expand(D0, W0, D1, W1, bias, wsn: int, wsk: int, K: int, out_dtype):
     return out
 
 
+def linear_tc_supported(M: int, L: int, F: int) -> bool:
+    """Tensor-core Linear kernels (linear_tc.cu): batch <= 64, latent 32..256, F features (bf16 activations)."""
+    return bool(_L().vae_linear_tc_supported(M, L, F))
+
+
 def linear_fwd(x, w, b, out_dtype):
     """x[B,K] @ w[N,K]^T + b -> [B,N]   (aten::addmm, models.py:137,141,162)."""
     Bn, K = x.shape
     N = w.shape[0]
     out = torch.empty((Bn, N), dtype=out_dtype, device=x.device)
+    if x.dtype == torch.bfloat16 and out_dtype == torch.float32 and K > N and linear_tc_supported(Bn, N, K):
+        # fc_mu / fc_var: reduction over the features, W[L][F]
+        rc = _L().vae_linear_reduce_tc(_p(x), _f32(w, "weight"), _f32(b, "bias"), _p(out), Bn, N, K, 0, _stream())
+        _lib.check(rc, "vae_linear_reduce_tc")
+        return out
+    if x.dtype == torch.float32 and out_dtype == torch.bfloat16 and N > K and linear_tc_supported(Bn, K, N):
+        # decoder_input: expansion of the latent, W[F][L]
+        rc = _L().vae_linear_expand_tc(_p(x), _f32(w, "weight"), None, None, _f32(b, "bias"), _p(out), Bn, K, N, 1,
+                                       code(out_dtype), _stream())
+        _lib.check(rc, "vae_linear_expand_tc")
+        return out
     return gemm(x, w, out, Bn, N, K, (K, 1), (1, K), (N, 1), bias=b)
 
 
@@ -423,7 +439,27 @@ def linear_bwd_input(dout, w, out=None, out_dtype=torch.float32, accumulate=Fals
     K = w.shape[1]
     if out is None:
         out = torch.empty((Bn, K), dtype=out_dtype, device=dout.device)
+    if not accumulate and dout.dtype == torch.bfloat16 and out.dtype == torch.float32 and N > K and linear_tc_supported(Bn, K, N):
+        # latent gradient of decoder_input: reduction over the features, W[F][L]
+        rc = _L().vae_linear_reduce_tc(_p(dout), _f32(w, "weight"), None, _p(out), Bn, K, N, 1, _stream())
+        _lib.check(rc, "vae_linear_reduce_tc")
+        return out
     return gemm(dout, w, out, Bn, K, N, (N, 1), (K, 1), (K, 1), accumulate=accumulate)
+
+
+def linear_bwd_input_pair(d0, w0, d1, w1, out_dtype):
+    """d0[B,L] @ w0[L,F] + d1[B,L] @ w1[L,F] -> [B,F]: the input gradient of two heads that share their input
+    (fc_mu + fc_var, models.py:137,141), one pass when the tensor-core kernel serves the shape."""
+    Bn, L = d0.shape
+    F_ = w0.shape[1]
+    if d0.dtype == torch.float32 and d1.dtype == torch.float32 and out_dtype == torch.bfloat16 and linear_tc_supported(Bn, L, F_):
+        out = torch.empty((Bn, F_), dtype=out_dtype, device=d0.device)
+        rc = _L().vae_linear_expand_tc(_p(d0), _f32(w0, "weight"), _p(d1), _f32(w1, "weight"), None, _p(out), Bn, L, F_, 0,
+                                       code(out_dtype), _stream())
+        _lib.check(rc, "vae_linear_expand_tc")
+        return out
+    out = linear_bwd_input(d0, w0, out_dtype=out_dtype)
+    return linear_bwd_input(d1, w1, out=out, accumulate=True)
 
 
 def linear_bwd_weight(dout, x, out=None):
@@ -431,6 +467,16 @@ def linear_bwd_weight(dout, x, out=None):
     Bn, N = dout.shape
     K = x.shape[1]
     dw = out if out is not None else torch.empty((N, K), dtype=torch.float32, device=x.device)
+    if dout.dtype == torch.float32 and x.dtype == torch.bfloat16 and K > N and linear_tc_supported(Bn, N, K):
+        # fc_mu / fc_var: G[L][F] = dmu^T . pre
+        rc = _L().vae_linear_wgrad_tc(_p(dout), _p(x), _p(dw), Bn, N, K, 0, _stream())
+        _lib.check(rc, "vae_linear_wgrad_tc")
+        return dw
+    if dout.dtype == torch.bfloat16 and x.dtype == torch.float32 and N > K and linear_tc_supported(Bn, K, N):
+        # decoder_input: G[F][L] = d_d^T . z
+        rc = _L().vae_linear_wgrad_tc(_p(x), _p(dout), _p(dw), Bn, K, N, 1, _stream())
+        _lib.check(rc, "vae_linear_wgrad_tc")
+        return dw
     return gemm(dout, x, dw, N, K, Bn, (1, N), (K, 1), (K, 1))
 
 

@@ -34,6 +34,9 @@ class TrainStep:
         self._static_x = None
         self._static_losses = None
         self._eager_steps = 0
+        # warm-up steps and the capture run on a private (non-default) stream: autograd's AccumulateGrad nodes and
+        # the NCCL / weight-packing side streams must not carry dependencies on default-stream work into the capture
+        self._side = torch.cuda.Stream() if use_graph else None
 
     # train.py:635-659
     def _step(self, x) -> Dict[str, torch.Tensor]:
@@ -52,11 +55,21 @@ class TrainStep:
 
     def _capture(self, x) -> None:
         self._static_x = x.clone()
+        torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
             self._static_losses = self._step(self._static_x)
+        torch.cuda.synchronize()
         self._graph = graph
+
+    def _eager_on_side_stream(self, x):
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            losses = self._step(x)
+        cur.wait_stream(self._side)
+        return losses
 
     def __call__(self, x) -> Dict[str, torch.Tensor]:
         """One optimisation step on the batch ``x`` ([B, 1, H, W] float32, cuda).  The returned loss tensors
@@ -66,7 +79,7 @@ class TrainStep:
         if self._graph is None:
             if self._eager_steps < self.warm_steps:
                 self._eager_steps += 1
-                return self._step(x)
+                return self._eager_on_side_stream(x)
             if not isinstance(self.opt, FusedAdamW) or (self.sched is not None and not isinstance(self.sched, FusedOneCycleLR)):
                 raise RuntimeError("TrainStep: graph replay needs FusedAdamW (+ FusedOneCycleLR): a host-side optimizer or "
                                    "scheduler would be frozen at its capture-time values; pass use_graph=False")
