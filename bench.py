@@ -212,6 +212,9 @@ def algorithmic_cost(name, tag):
     if name in ("vae_skinny_reduce", "vae_skinny_wgrad", "vae_skinny_expand"):
         M, N, K = t[:3]
         return (2 * M * K + 4 * N * K + 4 * M * N, 2 * M * N * K)
+    if name == "vae_skinny_reduce_pair":   # one read of A, two weight matrices, two outputs
+        M, N, K = t[:3]
+        return (2 * M * K + 8 * N * K + 8 * M * N, 4 * M * N * K)
     if name == "vae_bn_apply_lrelu":
         n, C, d = t[:3]
         return (2 * n * C * _sz(d), 3 * n * C)

@@ -319,6 +319,12 @@ int vae_heads_supported(int F, int L);
  * replaces: aten::addmm at models.py:137,141 and dL/dz of decoder_input */
 int vae_skinny_reduce(const void* A, const float* W, const float* bias, float* out, int M, int N,
                       int K, long long wsn, long long wsk, int dtA, vae_stream_t stream);
+/* Two heads that share their input in ONE pass over it (fc_mu and fc_var, models.py:137,141): out0 = A . W0 + bias0,
+ * out1 = A . W1 + bias1, same shapes and strides as vae_skinny_reduce.
+ * replaces: the two aten::addmm of fc_mu / fc_var */
+int vae_skinny_reduce_pair(const void* A, const float* W0, const float* bias0, float* out0, const float* W1,
+                           const float* bias1, float* out1, int M, int N, int K, long long wsn, long long wsk,
+                           int dtA, vae_stream_t stream);
 
 /* G[n*gsn + k*gsk] += sum_m D[m][n]*A[m][k]; colsum[k] += sum_m A[m][k] (may be NULL).
  * G and colsum must be zeroed by the caller.

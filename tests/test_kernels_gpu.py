@@ -454,6 +454,11 @@ def test_skinny_head_gemms(tv, shape, dtype):
     assert rel_err(out, aq @ w_lf.double().t() + b_l.double()) <= 1e-5
     out = ops.skinny_reduce(dev(a.to(dtype)), dev(w_fl), None, 1, L, L)
     assert rel_err(out, aq @ w_fl.double()) <= 1e-5
+    # both heads in one pass over the features (fc_mu and fc_var share their input)
+    w2, b2 = rnd(L, Fd, seed=28, scale=1.0 / math.sqrt(Fd)), rnd(L, seed=29, scale=0.1)
+    o0, o1 = ops.skinny_reduce_pair(dev(a.to(dtype)), dev(w_lf), dev(b_l), dev(w2), dev(b2), Fd, 1, L)
+    assert rel_err(o0, aq @ w_lf.double().t() + b_l.double()) <= 1e-5
+    assert rel_err(o1, aq @ w2.double().t() + b2.double()) <= 1e-5
     # weight gradients in both layouts, with the column sums
     g, cs = ops.skinny_wgrad(dev(d0), dev(a.to(dtype)), (L, Fd), Fd, 1, False)
     assert cs is None and rel_err(g, d0.double().t() @ aq) <= 1e-5

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "vae_onecycle_step": [_vp, _vp, _vp, _i, _ll, C.c_double, _i, _i, _vp],
     "vae_heads_supported": [_i, _i],
     "vae_skinny_reduce": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
+    "vae_skinny_reduce_pair": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_skinny_wgrad": [_vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_skinny_expand": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
     "vae_nhwc_to_nchw": [_vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -61,11 +61,13 @@ struct WChunk {
 // contiguous (no bank conflicts).  `out` is zeroed by the caller (memset node); the slice-0 blocks add
 // the bias.
 // ---------------------------------------------------------------------------------------------
-template <typename TA, int N, int ROWS>
+// NW = 2: two weight matrices / biases / outputs share ONE pass over A (fc_mu and fc_var read the same features)
+template <typename TA, int N, int ROWS, int NW>
 __global__ void __launch_bounds__(256, 2)
 skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
-                     float* __restrict__ out, int M, int K, long long wsn, long long wsk, int ks_len) {
-  extern __shared__ __align__(16) float w_s[];  // [N][2][ks_len / 2]
+                     float* __restrict__ out, const float* __restrict__ W1, const float* __restrict__ bias1,
+                     float* __restrict__ out1, int M, int K, long long wsn, long long wsk, int ks_len) {
+  extern __shared__ __align__(16) float w_s[];  // [NW][N][2][ks_len / 2]
   const int kslices = (K + ks_len - 1) / ks_len;
   const int ks = blockIdx.x % kslices, mb = blockIdx.x / kslices;
   const int k_begin = ks * ks_len, k_len = min(ks_len, K - k_begin);  // multiples of 8
@@ -85,51 +87,66 @@ skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, cons
     }
   };
   load_rows(lane * 8);
-  if (wsk == 1 && (wsn & 3) == 0) {
-    for (int kk = threadIdx.x * 4; kk < k_len; kk += 1024) {
-      const int dst = ((kk >> 2) & 1) * half_len + (kk >> 3) * 4;
-      float4 v[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) v[n] = *reinterpret_cast<const float4*>(W + n * wsn + k_begin + kk);
+  for (int q = 0; q < NW; ++q) {
+    const float* __restrict__ Wq = q == 0 ? W : W1;
+    float* ws = w_s + q * N * ks_len;
+    if (wsk == 1 && (wsn & 3) == 0) {
+      for (int kk = threadIdx.x * 4; kk < k_len; kk += 1024) {
+        const int dst = ((kk >> 2) & 1) * half_len + (kk >> 3) * 4;
+        float4 v[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(&w_s[n * ks_len + dst]) = v[n];
-    }
-  } else {
-    for (int i = threadIdx.x; i < N * k_len; i += 256) {
-      const int kk = i / N, n = i - kk * N;
-      w_s[n * ks_len + ((kk >> 2) & 1) * half_len + (kk >> 3) * 4 + (kk & 3)] = W[n * wsn + (long long)(k_begin + kk) * wsk];
+        for (int n = 0; n < N; ++n) v[n] = *reinterpret_cast<const float4*>(Wq + n * wsn + k_begin + kk);
+#pragma unroll
+        for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(&ws[n * ks_len + dst]) = v[n];
+      }
+    } else {
+      for (int i = threadIdx.x; i < N * k_len; i += 256) {
+        const int kk = i / N, n = i - kk * N;
+        ws[n * ks_len + ((kk >> 2) & 1) * half_len + (kk >> 3) * 4 + (kk & 3)] = Wq[n * wsn + (long long)(k_begin + kk) * wsk];
+      }
     }
   }
   __syncthreads();
   if (m0 >= M) return;
-  float acc[ROWS][N];
+  float acc[NW][ROWS][N];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r)
+  for (int q = 0; q < NW; ++q)
 #pragma unroll
-    for (int n = 0; n < N; ++n) acc[r][n] = 0.0f;
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int n = 0; n < N; ++n) acc[q][r][n] = 0.0f;
   for (int kk = lane * 8; kk < k_len; kk += 256) {
     if (kk != lane * 8) load_rows(kk);
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + (kk >> 1)]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&w_s[n * ks_len + half_len + (kk >> 1)]);
-      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int q = 0; q < NW; ++q)
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r)
+      for (int n = 0; n < N; ++n) {
+        const float* ws = w_s + (q * N + n) * ks_len;
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk >> 1]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[half_len + (kk >> 1)]);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r][n] = fmaf(a[r].v[j], w[j], acc[r][n]);
-    }
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q][r][n] = fmaf(a[r].v[j], w[j], acc[q][r][n]);
+      }
   }
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r)
+  for (int q = 0; q < NW; ++q) {
+    const float* __restrict__ bq = q == 0 ? bias : bias1;
+    float* __restrict__ oq = q == 0 ? out : out1;
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      float v = warp_sum(acc[r][n]);
-      if (lane == ((r * N + n) & 31) && m0 + r < M) {
-        if (ks == 0 && bias != nullptr) v += bias[n];
-        atomicAdd(&out[(long long)(m0 + r) * N + n], v);
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float v = warp_sum(acc[q][r][n]);
+        if (lane == ((r * N + n) & 31) && m0 + r < M) {
+          if (ks == 0 && bq != nullptr) v += bq[n];
+          atomicAdd(&oq[(long long)(m0 + r) * N + n], v);
+        }
       }
-    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,29 +317,50 @@ extern "C" int vae_heads_supported(int F, int L) { return (L >= 1 && L <= kMaxL 
 /* out[M][N] (fp32) = A[M][K] (dtype dtA) . W + bias, W(n, k) = W[n*wsn + k*wsk] (fp32).
  * replaces: aten::addmm of fc_mu / fc_var (models.py:137,141; wsn = K, wsk = 1) and the latent
  * gradient of decoder_input (train.py:650; W = weight[F, L]: wsn = 1, wsk = L) */
+static int skinny_reduce_launch(const void* A, const float* W, const float* bias, float* out, const float* W1,
+                                const float* bias1, float* out1, int M, int N, int K, long long wsn, long long wsk, int dtA,
+                                cudaStream_t st) {
+  const bool pair = W1 != nullptr;
+  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st));
+  if (pair) VAE_CUDA(cudaMemsetAsync(out1, 0, sizeof(float) * (size_t)M * N, st));
+  const int rows = pair ? 2 : 4;   // the pair keeps two accumulator sets: half the rows per warp
+  const int row_blocks = (M + 8 * rows - 1) / (8 * rows);
+  int ks_len = pair ? 512 : 1024;  // K slice per block: one wave of two blocks per SM where the shape allows it
+  while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) * 2 <= 2LL * sm_count()) ks_len /= 2;
+  const int grid = row_blocks * ((K + ks_len - 1) / ks_len);
+  const size_t smem = sizeof(float) * (size_t)N * ks_len * (pair ? 2 : 1);
+#define VAE_SR_LAUNCH(TA, ROWS, NW)                                                                                   \
+  do {                                                                                                                \
+    auto kern = skinny_reduce_kernel<TA, NN, ROWS, NW>;                                                               \
+    if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    kern<<<grid, 256, smem, st>>>((const TA*)A, W, bias, out, W1, bias1, out1, M, K, wsn, wsk, ks_len);               \
+  } while (0)
+  VAE_N_SWITCH(N, {
+    if (dtA == VAE_BF16) {
+      if (pair) VAE_SR_LAUNCH(bf16, 2, 2); else VAE_SR_LAUNCH(bf16, 4, 1);
+    } else {
+      if (pair) VAE_SR_LAUNCH(float, 2, 2); else VAE_SR_LAUNCH(float, 4, 1);
+    }
+  });
+#undef VAE_SR_LAUNCH
+  return check_launch("skinny_reduce");
+}
+
 extern "C" int vae_skinny_reduce(const void* A, const float* W, const float* bias, float* out, int M, int N, int K,
                                  long long wsn, long long wsk, int dtA, vae_stream_t stream) {
   VAE_REQUIRE(A && W && out && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL, "skinny_reduce: bad argument");
-  cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st));
-  constexpr int kRows = 4;
-  const int row_blocks = (M + 8 * kRows - 1) / (8 * kRows);
-  int ks_len = 1024;  // K slice per block: one wave of two blocks per SM where the shape allows it
-  while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) * 2 <= 2LL * sm_count()) ks_len /= 2;
-  const int grid = row_blocks * ((K + ks_len - 1) / ks_len);
-  const size_t smem = sizeof(float) * (size_t)N * ks_len;
-  VAE_N_SWITCH(N, {
-    if (dtA == VAE_BF16) {
-      auto kern = skinny_reduce_kernel<bf16, NN, kRows>;
-      if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      kern<<<grid, 256, smem, st>>>((const bf16*)A, W, bias, out, M, K, wsn, wsk, ks_len);
-    } else {
-      auto kern = skinny_reduce_kernel<float, NN, kRows>;
-      if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      kern<<<grid, 256, smem, st>>>((const float*)A, W, bias, out, M, K, wsn, wsk, ks_len);
-    }
-  });
-  return check_launch("skinny_reduce");
+  return skinny_reduce_launch(A, W, bias, out, nullptr, nullptr, nullptr, M, N, K, wsn, wsk, dtA, as_stream(stream));
+}
+
+/* Two heads that share their input in ONE pass over it: out0 = A . W0 + bias0, out1 = A . W1 + bias1 (same shapes
+ * and strides as vae_skinny_reduce).
+ * replaces: the two aten::addmm of fc_mu and fc_var (models.py:137,141) */
+extern "C" int vae_skinny_reduce_pair(const void* A, const float* W0, const float* bias0, float* out0, const float* W1,
+                                      const float* bias1, float* out1, int M, int N, int K, long long wsn, long long wsk,
+                                      int dtA, vae_stream_t stream) {
+  VAE_REQUIRE(A && W0 && out0 && W1 && out1 && M > 0 && K > 0 && K % 8 == 0 && N >= 1 && N <= kMaxL,
+              "skinny_reduce_pair: bad argument");
+  return skinny_reduce_launch(A, W0, bias0, out0, W1, bias1, out1, M, N, K, wsn, wsk, dtA, as_stream(stream));
 }
 
 /* G(n, k) = sum_m D[m][n] * A[m][k] written to G[n*gsn + k*gsk] (fp32, overwritten; the caller

@@ -135,8 +135,7 @@ class EncodeFn(torch.autograd.Function):
         pre = ops.nhwc_to_nchw(h)  # [B, C*h*w], C-major like x.flatten(1) (models.py:133)
         F_, L_ = pre.shape[1], w_mu.shape[0]
         if ops.heads_supported(F_, L_):
-            mu = ops.skinny_reduce(pre, w_mu, b_mu, F_, 1, L_)
-            log_var = ops.skinny_reduce(pre, w_var, b_var, F_, 1, L_)
+            mu, log_var = ops.skinny_reduce_pair(pre, w_mu, b_mu, w_var, b_var, F_, 1, L_)   # `pre` read once
         else:
             mu = ops.linear_fwd(pre, w_mu, b_mu, torch.float32)
             log_var = ops.linear_fwd(pre, w_var, b_var, torch.float32)

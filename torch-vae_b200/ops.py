@@ -377,6 +377,16 @@ def skinny_reduce(A, W, bias, wsn: int, wsk: int, N: int):
     return out
 
 
+def skinny_reduce_pair(A, W0, bias0, W1, bias1, wsn: int, wsk: int, N: int):
+    """(A . W0 + bias0, A . W1 + bias1) in ONE pass over A: fc_mu and fc_var share their input (models.py:137,141)."""
+    M, K = A.shape
+    out = torch.empty((2, M, N), dtype=torch.float32, device=A.device)
+    rc = _L().vae_skinny_reduce_pair(_p(A), _f32(W0, "weight"), _f32(bias0, "bias"), out[0].data_ptr(), _f32(W1, "weight"),
+                                     _f32(bias1, "bias"), out[1].data_ptr(), M, N, K, wsn, wsk, code(A), _stream())
+    _lib.check(rc, "vae_skinny_reduce_pair")
+    return out[0], out[1]
+
+
 def skinny_wgrad(D, A, g_shape, gsn: int, gsk: int, want_colsum: bool, out=None, colsum_out=None):
     """G(n,k) = sum_m D[m,n] A[m,k] laid out as G.flat[n*gsn + k*gsk]; colsum[k] = sum_m A[m,k].
     ``out`` / ``colsum_out``: optional destinations (gradient-bucket views); they are zeroed here."""

@@ -51,7 +51,10 @@ class TrainStep:
         self.opt.step()
         if self.sched is not None:
             self.sched.step()
-        return losses
+        # detached: a caller holding the loss must not keep the autograd graph -- and with it the parameters'
+        # AccumulateGrad nodes, which remember the stream they were created on -- alive into the next step (a stale
+        # node from a warm-up stream makes the capture fail with cudaErrorStreamCaptureIsolation)
+        return {k: v.detach() for k, v in losses.items()}
 
     def _capture(self, x) -> None:
         self._static_x = x.clone()
