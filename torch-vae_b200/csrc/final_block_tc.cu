@@ -17,6 +17,8 @@
 //   workers    tcgen05.ld their pixel's row of the accumulator and finish (shifted sum / BN backward)
 //
 //   warps 0-7 : workers (256 threads)      warp 8 : TMA producer      warp 9 : MMA issuer
+#include <cstdlib>
+
 #include "tma_util.cuh"
 
 namespace vae {
@@ -988,10 +990,287 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
 }
 
 // =============================================================================================
+// backward pass 1, deep-ring form of the all-GEMM kernel above.  The three-slot ring of [y | b | b*y] rows kept only
+// 48 KB of y in flight per SM (two CTAs) and a slot's turn-around (TMA -> workers -> 8 MMAs -> commit -> reload) is
+// ~2.5 us, so the kernel sat at 2.8 TB/s.  Here the LANDING ring (raw y rows, 14 x 8 KB, freed by the workers as soon
+// as they have read a row) is decoupled from the OPERAND ring (3 x [y | b | b*y], freed by the MMA commit): one CTA
+// per SM keeps 112 KB of y in flight; the workers copy y next to b and b*y (a third 16-byte store per chunk).
+// MEASURED (B200, B = 512): 288 us against 197 us for the two-CTA kernel above -- bytes in flight are not the limit;
+// the eight worker warps of ONE CTA need ~1 200 cycles per row (fences, barrier round trips, dependent shared-memory
+// accesses at ~0.1 IPC per warp), and one CTA per SM halves the number of rows being worked on.  Kept as an opt-in
+// experiment (VAE_FINAL_DEEP=1); DESIGN.md section 6.1.
+// =============================================================================================
+constexpr int kDLSlots = 14;                    // landing ring: raw y rows in flight (TMA)
+constexpr int kDOSlots = 3;                     // operand ring: [y | b | b*y] rows the MMAs read (== kA1Bufs)
+constexpr int kDOSlot = 3 * kRowBytes;          // one operand slot: three 32-channel groups, 8 KB apart (LBO)
+constexpr size_t kDeepSmemBytes = 1024 + kDLSlots * kRowBytes + kDOSlots * kDOSlot + 8192 + kA1Bufs * kRowBytes + 64 * 4 +
+                                  (3 * 32 * 9 + 16) * 4 + 8 * (2 * kDLSlots + 2 * kDOSlots + kA1Bufs + 1) + 16 + 32 * 4;
+static_assert(kA1Bufs == kDOSlots, "the dlwin tile of a row is recycled together with its operand slot");
+
+__global__ void __launch_bounds__(kFtThreads, 1)
+final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* yring = smem;                         // [kDLSlots][8 KB] landing ring (TMA)
+  uint8_t* oring = smem + kDLSlots * kRowBytes;  // [kDOSlots][y | b | b*y] operand ring; + 8 KB pad (unused M group of the last slot)
+  uint8_t* a1 = oring + kDOSlots * kDOSlot + 8192;   // [kA1Bufs][8 KB] dlwin tiles
+  float* cst = reinterpret_cast<float*>(a1 + kA1Bufs * kRowBytes);   // scale[32], shift[32]
+  float* gsm = cst + 64;                         // [3][32][9] accumulators, [16] column sums of dlwin
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(gsm + 3 * 32 * 9 + 16);
+  uint64_t* lempty_bar = full_bar + kDLSlots;      // workers -> producer: the landing slot has been read
+  uint64_t* opready_bar = lempty_bar + kDLSlots;   // workers -> MMA: operand slot written
+  uint64_t* empty_bar = opready_bar + kDOSlots;    // MMA commit -> workers: operand slot (and its dlwin tile) free
+  uint64_t* a1ready_bar = empty_bar + kDOSlots;
+  uint64_t* done_bar = a1ready_bar + kA1Bufs;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint16_t* thr_s = reinterpret_cast<uint16_t*>(tmem_ptr + 4);   // [32] branch thresholds, [32] sign-flip masks
+  uint16_t* sgn_s = thr_s + 32;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = P.H, RB = P.RB;
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int s = 0; s < kDLSlots; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&lempty_bar[s], kFtWorkers);
+      }
+      for (int s = 0; s < kDOSlots; ++s) {
+        mbar_init(&empty_bar[s], 1);
+        mbar_init(&opready_bar[s], kFtWorkers);
+      }
+      for (int a = 0; a < kA1Bufs; ++a) mbar_init(&a1ready_bar[a], 128);
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 32);
+  }
+  if (warp < 8) {
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+      const float sc = P.scale[tid];
+      const float sh = fmaf(-P.mean[tid], sc, P.beta[tid]);
+      cst[tid] = sc;
+      cst[32 + tid] = sh;
+      uint32_t thr, sgn;
+      lrelu_threshold(sc, sh, &thr, &sgn);
+      thr_s[tid] = (uint16_t)thr;
+      sgn_s[tid] = (uint16_t)sgn;
+    }
+    for (int i = tid; i < kA1Bufs * kRowBytes / 16; i += kFtWorkers) reinterpret_cast<uint4*>(a1)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (kDOSlots * kDOSlot + 8192) / 16; i += kFtWorkers) reinterpret_cast<uint4*>(oring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 16; i += kFtWorkers) gsm[3 * 32 * 9 + i] = 0.0f;
+    fence_proxy_async_smem();
+  }
+  if (warp == 8 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tmap_y) : "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  uint32_t total = 0;
+  for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) total += (uint32_t)RB;
+
+  if (warp == 8) {
+    // ============================== producer ==============================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
+        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        for (int i = 0; i < RB; ++i, ++n) {
+          const uint32_t slot = n % kDLSlots, ph = (n / kDLSlots) & 1u;
+          mbar_wait(&lempty_bar[slot], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[slot], kRowBytes);
+          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, 0, h0 + i, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================= MMA issuer =============================
+    const uint32_t idesc = make_idesc_bf16(128, 32, 1, 1);   // both operands MN-major
+    const uint32_t y_a = smem_u32(oring), a1_a = smem_u32(a1);
+    for (uint32_t n = 0; n < total; ++n) {
+      const uint32_t slot = n % kDOSlots, ph = (n / kDOSlots) & 1u, ab = n % kA1Bufs, aph = (n / kA1Bufs) & 1u;
+      mbar_wait(&a1ready_bar[ab], aph);
+      mbar_wait(&opready_bar[slot], ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
+          const uint64_t ad = make_desc_mn_tc(y_a + slot * kDOSlot + ks * 1024, kRowBytes, 512, 4);
+          const uint64_t bd = make_desc_mn_tc(a1_a + ab * kRowBytes + ks * 1024, kRowBytes, 512, 4);
+          mma_bf16_ss(tmem_base, ad, bd, idesc, (n > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty_bar[slot]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // =============================== workers ==============================
+    const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const uint32_t y_a = smem_u32(yring), o_a = smem_u32(oring), a1_a = smem_u32(a1);
+    const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
+    const uint32_t a1off0 = swz64(p, 0), a1off1 = swz64(p, 1);
+    // this thread's 16 channels (two 16-byte chunks) as 8 bf16x2 words: thresholds and sign-flip masks
+    uint32_t thr2[8], sgn2[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = half * 16 + 2 * w;
+      thr2[w] = (uint32_t)thr_s[c] | ((uint32_t)thr_s[c + 1] << 16);
+      sgn2[w] = (uint32_t)sgn_s[c] | ((uint32_t)sgn_s[c + 1] << 16);
+    }
+    float colsum[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) colsum[k] = 0.0f;
+    uint32_t n = 0;
+    for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
+      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      auto fetch3 = [&](int h, float* v) {
+        if (h >= 0 && h < H) {
+          const bf16* row = P.dl + ((long long)b * H + h) * 128;
+          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          v[1] = __bfloat162float(row[p]);
+          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+        } else {
+          v[0] = v[1] = v[2] = 0.0f;
+        }
+      };
+      // the look-ahead row stays RAW (bf16 bits) until it enters the window one iteration later: a
+      // conversion next to the load would make the thread wait for the load at once (ncu: 15 % of all
+      // stall samples of the kernel sat on that conversion)
+      auto fetch3_raw = [&](int h, unsigned short* v) {
+        v[0] = v[1] = v[2] = 0;
+        if (h >= 0 && h < H) {
+          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
+          if (p > 0) v[0] = __ldg(row + p - 1);
+          v[1] = __ldg(row + p);
+          if (p < 127) v[2] = __ldg(row + p + 1);
+        }
+      };
+      float r0[3], r1[3], r2[3];
+      unsigned short pf[3];   // 16-bit type: widening (and with it any use of the load) happens at the shift below
+      if (half == 0) {
+        fetch3(h0 - 1, r0);
+        fetch3(h0, r1);
+        fetch3(h0 + 1, r2);
+        fetch3_raw(h0 + 2, pf);
+      }
+      auto stage_a1 = [&](uint32_t nn) {   // half 0: dlwin tile of row nn from the register window
+        const uint32_t buf = nn % kA1Bufs;
+        if (nn >= (uint32_t)kA1Bufs) {     // the MMAs of row nn - kA1Bufs have finished reading this tile
+          const uint32_t m = nn - kA1Bufs;
+          mbar_wait(&empty_bar[m % kDOSlots], (m / kDOSlots) & 1u);
+        }
+        float w[16];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          w[k] = r0[k];
+          w[3 + k] = r1[k];
+          w[6 + k] = r2[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) colsum[k] += w[k];
+#pragma unroll
+        for (int k = 9; k < 16; ++k) w[k] = 0.0f;
+        const uint32_t base = a1_a + buf * kRowBytes;
+        sts128(base + a1off0, pack8(w));
+        sts128(base + a1off1, pack8(w + 8));
+        fence_proxy_async_smem();
+        mbar_arrive(&a1ready_bar[buf]);
+      };
+      if (half == 0) stage_a1(n);
+      for (int i = 0; i < RB; ++i, ++n) {
+        if (i + 1 < RB && half == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            r0[k] = r1[k];
+            r1[k] = r2[k];
+            r2[k] = __uint_as_float((uint32_t)pf[k] << 16);
+          }
+          fetch3_raw(h0 + i + 3, pf);
+          stage_a1(n + 1);
+        }
+        const uint32_t slot = n % kDLSlots, ph = (n / kDLSlots) & 1u, os = n % kDOSlots;
+        mbar_wait(&full_bar[slot], ph);
+        if (n >= (uint32_t)kDOSlots) {   // the MMAs of row n - kDOSlots have finished reading this operand slot
+          const uint32_t m = n - kDOSlots;
+          mbar_wait(&empty_bar[os], (m / kDOSlots) & 1u);
+        }
+        const uint32_t row = y_a + slot * kRowBytes, orow = o_a + os * kDOSlot;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t off = j == 0 ? off0 : off1;
+          const uint4 raw = lds128(row + off);
+          const uint32_t a = orow + off;
+          const uint32_t yw[4] = {raw.x, raw.y, raw.z, raw.w};
+          uint32_t bw[4], byw[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            // b = [u > 0] as bf16 1.0 / 0.0 for two channels at once; b * y is exact (y or +-0)
+            const uint32_t yy = yw[w] ^ sgn2[j * 4 + w];
+            asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(bw[w]) : "r"(yy), "r"(thr2[j * 4 + w]));
+            asm("mul.bf16x2 %0, %1, %2;" : "=r"(byw[w]) : "r"(bw[w]), "r"(yw[w]));
+          }
+          sts128(a, raw);
+          sts128(a + kRowBytes, make_uint4(bw[0], bw[1], bw[2], bw[3]));
+          sts128(a + 2 * kRowBytes, make_uint4(byw[0], byw[1], byw[2], byw[3]));
+        }
+        mbar_arrive(&lempty_bar[slot]);   // the landing slot may be refilled
+        fence_proxy_async_smem();
+        mbar_arrive(&opready_bar[os]);
+      }
+    }
+    // ------------------------------ reductions ------------------------------
+    if (half == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float v = warp_sum(colsum[k]);
+        if (lane == 0) atomicAdd(&gsm[3 * 32 * 9 + k], v);
+      }
+    }
+    if (warp < 3 && total > 0) {   // TMEM lanes 32w..32w+31 = rows of [y | b | b*y]^T . dlwin
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      float v[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gsm[(warp * 32 + lane) * 9 + k] = v[k];
+    }
+    named_bar_sync(1, kFtWorkers);
+    if (warp == 0 && total > 0) {
+      const int c = lane;
+      const float sl = P.slope, om = 1.0f - P.slope, sc = cst[c], sh = cst[32 + c];
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float g1 = sl * gsm[3 * 32 * 9 + k] + om * gsm[(32 + c) * 9 + k];          // q^T . dlwin
+        const float g2 = sl * gsm[c * 9 + k] + om * gsm[(64 + c) * 9 + k];               // (q*y)^T . dlwin
+        const float wf = P.w_last[c * 9 + (8 - k)];
+        s1 += (double)wf * (double)g1;
+        s2 += (double)wf * (double)g2;
+        atomicAdd(&P.dw_last[c * 9 + (8 - k)], fmaf(sc, g2, sh * g1));
+      }
+      atomicAdd(&P.dstats[c], s1);
+      atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
+      if (c == 0) atomicAdd(&P.dstats[64], (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+// =============================================================================================
 // host side
 // =============================================================================================
 static bool g_final_tc_enabled = true;
 static bool g_final_gemm_reduce = true;   // pass 1 as one accumulating GEMM (final_bwd_reduce_gemm_kernel)
+static int g_final_deep_ring = -1;        // pass 1 with the decoupled landing / operand rings (env VAE_FINAL_DEEP=1; measured slower: default 0)
 
 static bool final_tc_ok(int B, int H, int W, int C, int dtype) {
   return g_final_tc_enabled && dtype == VAE_BF16 && C == 32 && W == 128 && B > 0 && H >= 16 && H % 16 == 0 &&
@@ -1069,6 +1348,21 @@ static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
   int grid = (pass == 2 ? kP2Ctas : 2) * sm_count();
   if (grid > P.total_bands) grid = P.total_bands;
   if (pass == 1 && g_final_gemm_reduce) {
+    if (g_final_deep_ring < 0) {
+      const char* e = getenv("VAE_FINAL_DEEP");
+      g_final_deep_ring = e ? atoi(e) : 0;
+    }
+    if (g_final_deep_ring) {
+      static bool attr4 = false;
+      if (!attr4) {
+        VAE_CUDA(cudaFuncSetAttribute(final_bwd_reduce_deep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDeepSmemBytes));
+        attr4 = true;
+      }
+      int g1 = sm_count();
+      if (g1 > P.total_bands) g1 = P.total_bands;
+      final_bwd_reduce_deep_kernel<<<g1, kFtThreads, kDeepSmemBytes, st>>>(P);
+      return check_launch("final_bwd_reduce_deep");
+    }
     static bool attr3 = false;
     if (!attr3) {
       VAE_CUDA(cudaFuncSetAttribute(final_bwd_reduce_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP1SmemBytes));
