@@ -907,10 +907,14 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
         const uint32_t base = a1_a + buf * kRowBytes;
         sts128(base + a1off0, pack8(w));
         sts128(base + a1off1, pack8(w + 8));
-        fence_proxy_async_smem();
-        mbar_arrive(&a1ready_bar[buf]);
+        // no fence / arrive here: the caller publishes the tile together with the row operands (ONE proxy fence per
+        // row and thread; the fences and barrier round trips, not the arithmetic, set the per-row latency of a warp)
       };
-      if (half == 0) stage_a1(n);
+      if (half == 0) {
+        stage_a1(n);
+        fence_proxy_async_smem();
+        mbar_arrive(&a1ready_bar[n % kA1Bufs]);
+      }
       for (int i = 0; i < RB; ++i, ++n) {
         if (i + 1 < RB && half == 0) {
 #pragma unroll
@@ -943,6 +947,7 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
         }
         fence_proxy_async_smem();
         mbar_arrive(&opready_bar[slot]);
+        if (i + 1 < RB && half == 0) mbar_arrive(&a1ready_bar[(n + 1) % kA1Bufs]);   // staged above, fenced just now
       }
     }
     // ------------------------------ reductions ------------------------------
