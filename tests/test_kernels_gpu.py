@@ -356,6 +356,10 @@ FINAL_CASES = [
     (2, 128, 128, 32),
     (3, 64, 128, 32),   # tcgen05 path (bf16): two 32-row bands per image
     (5, 48, 128, 32),   # tcgen05 path: 16-row bands
+    (2, 32, 256, 32),   # tcgen05 path, rows of several 128-pixel tiles (forward: overlapping halo tiles of 126 outputs)
+    (2, 16, 128, 64),   # tcgen05 path, two groups of 32 channels (partial logits travel in the fp32 probs buffer)
+    (2, 32, 384, 64),   # both
+    (1, 128, 1024, 64), # the output block of the wide / long configuration (one image)
 ]
 
 

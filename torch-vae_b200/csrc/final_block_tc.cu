@@ -43,9 +43,17 @@ struct FinalTcParams {
   bf16* logits;          // [B][H][W]
   float* probs;          // [B][H][W] or null
   bf16* dy;              // [B][H][W][C]
-  double* dstats;        // [2C + 1]
+  double* ds1;           // [32] sum du of this launch's channels        (dstats[0 .. C) of the caller, + channel offset)
+  double* ds2;           // [32] sum du * xhat                            (dstats[C .. 2C), + channel offset)
+  double* dsdl;          // sum of dlogits (dstats[2C]); null for every channel group but the first
   float* dw_last;        // [C][9]
-  int B, H, W, RB, bands_per_img, total_bands, training;
+  const float* partial_in;   // forward, channel groups after the first: fp32 partial logits [B][H][W] to continue from
+  float* partial_out;        // forward, channel groups before the last: write the fp32 partial instead of logits / probs
+  // a launch covers ONE group of 32 channels (tensor maps and per-channel pointers are offset by the caller) and tiles
+  // of 128 pixels: tile cb of an image row starts at column cb * wstep - halo.  halo = 1 (forward, W > 128): tiles
+  // overlap by two pixels and only their inner 126 produce logits; halo = 0: the tile is the whole row (W = 128) or,
+  // in the backward kernels, an aligned block whose dlogits window is read from global memory across its edges.
+  int B, H, W, RB, bands_per_img, total_bands, training, tpr, wstep, halo;
   float slope;
 };
 
@@ -138,6 +146,9 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
 // =============================================================================================
 constexpr size_t kFwdSmemBytes = 1024 + kFtSlots * kRowBytes + 2048 + 4 * 9 * 130 * 4 + 64 * 4 + 8 * (3 * kFtSlots + 4) + 16;
 
+// WIDE = false: one 128-pixel tile per image row (W == 128): no column arithmetic, no edge masks
+// PARTIAL = true: several groups of 32 channels accumulate the logits through an fp32 partial buffer
+template <bool WIDE, bool PARTIAL>
 __global__ void __launch_bounds__(kFtThreads, 3)
 final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -199,14 +210,16 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     if (lane == 0) {
       uint32_t n = 0;
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
         for (int i = 0; i < RB + 2; ++i) {
           const int h = h0 - 1 + i;
           if (h < 0 || h >= H) continue;
           const uint32_t slot = n % kFtSlots, ph = (n / kFtSlots) & 1u;
           mbar_wait(&empty_bar[slot], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[slot], kRowBytes);
-          tma_load_4d(ring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, 0, h, b);
+          tma_load_4d(ring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, w0, h, b);
           ++n;
         }
       }
@@ -217,7 +230,7 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wimg);
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-      const int h0 = (band % P.bands_per_img) * RB;
+      const int h0 = ((WIDE ? band / P.tpr : band) % P.bands_per_img) * RB;
       for (int i = 0; i < RB + 2; ++i) {
         const int h = h0 - 1 + i;
         if (h < 0 || h >= H) continue;
@@ -242,13 +255,19 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   } else {
     // =============================== workers ==============================
     const int p = threadIdx.x & 127, half = threadIdx.x >> 7;  // pixel of the row, channel half
-    const float slope = P.slope, bias = P.b_last != nullptr ? P.b_last[0] : 0.0f;
+    const float slope = P.slope, bias = (P.b_last != nullptr && (!PARTIAL || P.partial_in == nullptr)) ? P.b_last[0] : 0.0f;
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t ring_a = smem_u32(ring), psm_a = smem_u32(psm), cst_a = smem_u32(cst);
     const uint32_t off0 = swz64(p, 2 * half), off1 = swz64(p, 2 * half + 1);
     uint32_t n_t = 0, n_e = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
+      // a halo tile (W > 128) may reach one pixel past either edge of the image: TMA zero-fills y there, but the conv's
+      // zero padding applies to the ACTIVATION, so those pixels are forced to 0 instead of lrelu(shift)
+      const bool col_ok = !WIDE || (unsigned)(w0 + p) < (unsigned)P.W;
+      const bool out_ok = !WIDE || (col_ok && (P.halo == 0 || (p >= 1 && p <= 126)));
       auto transform = [&](int i) {
         const int h = h0 - 1 + i;
         if (h < 0 || h >= H) return;
@@ -265,7 +284,7 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float u = fmaf(v[k], sc[k], sh[k]);
-            v[k] = fmaxf(u, u * slope);  // LeakyReLU for 0 < slope < 1
+            v[k] = col_ok ? fmaxf(u, u * slope) : 0.0f;  // LeakyReLU for 0 < slope < 1; zero padding outside the image
           }
           sts128(a, pack8(v));
         }
@@ -307,10 +326,17 @@ final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) acc += lds_f(pr + ((kh * 3 + kw) * 130 + kw) * 4);
           }
-          const long long o = ((long long)b * H + q) * 128 + p;
-          const bf16 lg = __float2bfloat16_rn(acc);
-          P.logits[o] = lg;
-          if (P.probs != nullptr) P.probs[o] = 1.0f / (1.0f + expf(-__bfloat162float(lg)));
+          if (out_ok) {
+            const long long o = ((long long)b * H + q) * (WIDE ? P.W : 128) + w0 + p;
+            if (PARTIAL && P.partial_in != nullptr) acc += P.partial_in[o];   // the other channel groups' share (bias is in the first)
+            if (PARTIAL && P.partial_out != nullptr) {
+              P.partial_out[o] = acc;
+            } else {
+              const bf16 lg = __float2bfloat16_rn(acc);
+              P.logits[o] = lg;
+              if (P.probs != nullptr) P.probs[o] = 1.0f / (1.0f + expf(-__bfloat162float(lg)));
+            }
+          }
         }
       }
       named_bar_sync(1, kFtWorkers);  // the next band reuses the P ring from slot 0
@@ -337,7 +363,7 @@ struct BwdSmem {
   float* dlsm;      // [4][130]
   float* cst;       // per-channel constants, [5][32]
   float* red;       // [2][32] block reduction scratch (+ 8 for the bias sum)
-  int* coord;       // [slots][2] (h, b) of the row held by a slot (pass 2 store)
+  int* coord;       // [slots][3] (h, b, w0) of the row held by a slot (pass 2 store)
   uint64_t* full_bar;     // TMA -> workers
   uint64_t* empty_bar;    // -> producer
   uint64_t* a1ready_bar;  // [2] workers -> MMA
@@ -350,7 +376,7 @@ struct BwdSmem {
 
 constexpr size_t bwd_smem_bytes(int slots) {
   return 1024 + (size_t)slots * kRowBytes + kA1Bufs * kRowBytes + 8192 /* pad: garbage M groups stay in bounds */ +
-         2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 2 * kFtSlots * 4 + 8 * (3 * kFtSlots + 8) + 16;
+         2048 + 4 * 130 * 4 + 5 * 32 * 4 + 72 * 4 + 4 * kFtSlots * 4 + 8 * (3 * kFtSlots + 8) + 16;
 }
 constexpr size_t kBwdSmemBytes = bwd_smem_bytes(kFtSlots);
 
@@ -363,7 +389,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem, int slots) {   // ba
   s.cst = s.dlsm + 4 * 130;
   s.red = s.cst + 5 * 32;
   s.coord = reinterpret_cast<int*>(s.red + 72);
-  s.full_bar = reinterpret_cast<uint64_t*>(s.coord + 2 * kFtSlots);
+  s.full_bar = reinterpret_cast<uint64_t*>(s.coord + 4 * kFtSlots);
   s.empty_bar = s.full_bar + kFtSlots;
   s.a1ready_bar = s.empty_bar + kFtSlots;
   s.d1full_bar = s.a1ready_bar + kA1Bufs;
@@ -377,7 +403,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(uint8_t* smem, int slots) {   // ba
 // PASS: 1 = reduce (BN sums + weight / bias gradient of the final conv), 2 = apply (dy)
 // SLOTS y rows in the ring, CTAS resident CTAs per SM (pass 2 is bound by issue latency, not by bytes in
 // flight: three CTAs with four slots each keep the same 12 rows per SM in flight with 50 % more warps)
-template <int PASS, int SLOTS, int CTAS>
+template <int PASS, int SLOTS, int CTAS, bool WIDE>
 __global__ void __launch_bounds__(kFtThreads, CTAS)
 final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -420,10 +446,10 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       S.cst[c] = sc;
       S.cst[32 + c] = fmaf(-mean, sc, P.beta[c]);
       if (PASS == 2) {
-        const double inv_m = 1.0 / ((double)P.B * P.H * 128.0);
+        const double inv_m = 1.0 / ((double)P.B * P.H * (double)P.W);
         const double ga = (double)P.gamma[c] * (double)P.rstd[c];
-        const double c1 = P.training ? P.dstats[c] * inv_m : 0.0;
-        const double c2 = P.training ? P.dstats[32 + c] * inv_m : 0.0;
+        const double c1 = P.training ? P.ds1[c] * inv_m : 0.0;
+        const double c2 = P.training ? P.ds2[c] * inv_m : 0.0;
         const double k2 = ga * c2 * (double)P.rstd[c];
         S.cst[64 + c] = (float)ga;
         S.cst[96 + c] = (float)(ga * c1 - k2 * (double)mean);   // k1
@@ -452,11 +478,13 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       auto store_row = [&](uint32_t m) {
         const uint32_t slot = m % SLOTS;
         mbar_wait(&S.a2ready_bar[slot], (m / SLOTS) & 1u);
-        tma_store_4d(&P.tmap_dy, S.ring + slot * kRowBytes, 0, 0, S.coord[2 * slot], S.coord[2 * slot + 1]);
+        tma_store_4d(&P.tmap_dy, S.ring + slot * kRowBytes, 0, S.coord[3 * slot + 2], S.coord[3 * slot], S.coord[3 * slot + 1]);
         bulk_commit_group();
       };
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
         for (int i = 0; i < RB; ++i, ++n) {
           const uint32_t slot = n % SLOTS, ph = (n / SLOTS) & 1u;
           if (PASS == 1) {
@@ -466,11 +494,12 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
             bulk_wait_group_read0();  // the store has finished reading the slot
           }
           if (PASS == 2) {
-            S.coord[2 * slot] = h0 + i;
-            S.coord[2 * slot + 1] = b;
+            S.coord[3 * slot] = h0 + i;
+            S.coord[3 * slot + 1] = b;
+            S.coord[3 * slot + 2] = w0;
           }
           mbar_arrive_expect_tx(&S.full_bar[slot], kRowBytes);
-          tma_load_4d(S.ring + slot * kRowBytes, &P.tmap_y, &S.full_bar[slot], 0, 0, h0 + i, b);
+          tma_load_4d(S.ring + slot * kRowBytes, &P.tmap_y, &S.full_bar[slot], 0, w0, h0 + i, b);
         }
       }
       if (PASS == 2) {
@@ -535,17 +564,19 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
     float sdl = 0.0f;
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
       // dlogits window of a pixel: rows j = 0 .. RB+1 of the band <-> image rows h0-1 .. h0+RB, columns
       // p-1, p, p+1.  Each half-0 thread keeps a sliding 3 x 3 window in registers and loads the three
       // values of the next row one iteration ahead (L1-resident after the first touch), so there is no
       // shared-memory exchange and no block barrier on the per-row path.
       auto fetch3 = [&](int h, float* v) {
         if (h >= 0 && h < H) {
-          const bf16* row = P.dl + ((long long)b * H + h) * 128;
-          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          const bf16* row = P.dl + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          v[0] = w0 + p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
           v[1] = __bfloat162float(row[p]);
-          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+          v[2] = w0 + p < (WIDE ? P.W : 128) - 1 ? __bfloat162float(row[p + 1]) : 0.0f;
         } else {
           v[0] = v[1] = v[2] = 0.0f;
         }
@@ -556,10 +587,10 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       auto fetch3_raw = [&](int h, unsigned short* v) {
         v[0] = v[1] = v[2] = 0;
         if (h >= 0 && h < H) {
-          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
-          if (p > 0) v[0] = __ldg(row + p - 1);
+          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          if (w0 + p > 0) v[0] = __ldg(row + p - 1);
           v[1] = __ldg(row + p);
-          if (p < 127) v[2] = __ldg(row + p + 1);
+          if (w0 + p < (WIDE ? P.W : 128) - 1) v[2] = __ldg(row + p + 1);
         }
       };
       float r0[3], r1[3], r2[3];
@@ -666,9 +697,9 @@ final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
       if (warp == 0) {
         const int c = lane;
         const double s1 = (double)S.red[c], s2y = (double)S.red[32 + c];
-        atomicAdd(&P.dstats[c], s1);
-        atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2y - (double)P.mean[c] * s1));   // sum du * xhat
-        if (c == 0) atomicAdd(&P.dstats[64], (double)S.red[64] + (double)S.red[65] + (double)S.red[66] + (double)S.red[67]);
+        atomicAdd(&P.ds1[c], s1);
+        atomicAdd(&P.ds2[c], (double)P.rstd[c] * (s2y - (double)P.mean[c] * s1));   // sum du * xhat
+        if (c == 0 && P.dsdl != nullptr) atomicAdd(P.dsdl, (double)S.red[64] + (double)S.red[65] + (double)S.red[66] + (double)S.red[67]);
         // weight gradient of the final conv: D2 lane c, column widx -> dw[c][8 - widx]
         mbar_wait(S.done_bar, 0);
         tc_fence_after();
@@ -744,6 +775,7 @@ constexpr int kP1Ring = kP1Slots * kRowBytes;   // L
 constexpr size_t kP1SmemBytes = 1024 + 3 * kP1Ring + kA1Bufs * kRowBytes + 8192 + 64 * 4 + (3 * 32 * 9 + 16) * 4 +
                                 8 * (3 * kP1Slots + kA1Bufs + 1) + 16 + 32 * 4;
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kFtThreads, 2)
 final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -806,12 +838,14 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
     if (lane == 0) {
       uint32_t n = 0;
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
         for (int i = 0; i < RB; ++i, ++n) {
           const uint32_t slot = n % kP1Slots, ph = (n / kP1Slots) & 1u;
           mbar_wait(&empty_bar[slot], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[slot], kRowBytes);
-          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, 0, h0 + i, b);
+          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, w0, h0 + i, b);
         }
       }
     }
@@ -856,13 +890,15 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
     for (int k = 0; k < 9; ++k) colsum[k] = 0.0f;
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
       auto fetch3 = [&](int h, float* v) {
         if (h >= 0 && h < H) {
-          const bf16* row = P.dl + ((long long)b * H + h) * 128;
-          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          const bf16* row = P.dl + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          v[0] = w0 + p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
           v[1] = __bfloat162float(row[p]);
-          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+          v[2] = w0 + p < (WIDE ? P.W : 128) - 1 ? __bfloat162float(row[p + 1]) : 0.0f;
         } else {
           v[0] = v[1] = v[2] = 0.0f;
         }
@@ -873,10 +909,10 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
       auto fetch3_raw = [&](int h, unsigned short* v) {
         v[0] = v[1] = v[2] = 0;
         if (h >= 0 && h < H) {
-          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
-          if (p > 0) v[0] = __ldg(row + p - 1);
+          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          if (w0 + p > 0) v[0] = __ldg(row + p - 1);
           v[1] = __ldg(row + p);
-          if (p < 127) v[2] = __ldg(row + p + 1);
+          if (w0 + p < (WIDE ? P.W : 128) - 1) v[2] = __ldg(row + p + 1);
         }
       };
       float r0[3], r1[3], r2[3];
@@ -981,9 +1017,9 @@ final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
         s2 += (double)wf * (double)g2;
         atomicAdd(&P.dw_last[c * 9 + (8 - k)], fmaf(sc, g2, sh * g1));
       }
-      atomicAdd(&P.dstats[c], s1);
-      atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
-      if (c == 0) atomicAdd(&P.dstats[64], (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
+      atomicAdd(&P.ds1[c], s1);
+      atomicAdd(&P.ds2[c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
+      if (c == 0 && P.dsdl != nullptr) atomicAdd(P.dsdl, (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
     }
   }
   tc_fence_before();
@@ -1014,6 +1050,7 @@ static_assert(kA1Bufs == kDOSlots, "the dlwin tile of a row is recycled together
 
 __global__ void __launch_bounds__(kFtThreads, 1)
 final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
+  constexpr bool WIDE = true;   // opt-in experiment: always the general form
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* yring = smem;                         // [kDLSlots][8 KB] landing ring (TMA)
@@ -1080,12 +1117,14 @@ final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
     if (lane == 0) {
       uint32_t n = 0;
       for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-        const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+        const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
         for (int i = 0; i < RB; ++i, ++n) {
           const uint32_t slot = n % kDLSlots, ph = (n / kDLSlots) & 1u;
           mbar_wait(&lempty_bar[slot], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[slot], kRowBytes);
-          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, 0, h0 + i, b);
+          tma_load_4d(yring + slot * kRowBytes, &P.tmap_y, &full_bar[slot], 0, w0, h0 + i, b);
         }
       }
     }
@@ -1130,13 +1169,15 @@ final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
     for (int k = 0; k < 9; ++k) colsum[k] = 0.0f;
     uint32_t n = 0;
     for (int band = blockIdx.x; band < P.total_bands; band += gridDim.x) {
-      const int b = band / P.bands_per_img, h0 = (band - b * P.bands_per_img) * RB;
+      const int cb = WIDE ? band % P.tpr : 0, rbnd = WIDE ? band / P.tpr : band;
+        const int b = rbnd / P.bands_per_img, h0 = (rbnd - b * P.bands_per_img) * RB, w0 = WIDE ? cb * P.wstep - P.halo : 0;
+        (void)w0;
       auto fetch3 = [&](int h, float* v) {
         if (h >= 0 && h < H) {
-          const bf16* row = P.dl + ((long long)b * H + h) * 128;
-          v[0] = p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
+          const bf16* row = P.dl + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          v[0] = w0 + p > 0 ? __bfloat162float(row[p - 1]) : 0.0f;
           v[1] = __bfloat162float(row[p]);
-          v[2] = p < 127 ? __bfloat162float(row[p + 1]) : 0.0f;
+          v[2] = w0 + p < (WIDE ? P.W : 128) - 1 ? __bfloat162float(row[p + 1]) : 0.0f;
         } else {
           v[0] = v[1] = v[2] = 0.0f;
         }
@@ -1147,10 +1188,10 @@ final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
       auto fetch3_raw = [&](int h, unsigned short* v) {
         v[0] = v[1] = v[2] = 0;
         if (h >= 0 && h < H) {
-          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * 128;
-          if (p > 0) v[0] = __ldg(row + p - 1);
+          const unsigned short* row = reinterpret_cast<const unsigned short*>(P.dl) + ((long long)b * H + h) * (WIDE ? P.W : 128) + w0;
+          if (w0 + p > 0) v[0] = __ldg(row + p - 1);
           v[1] = __ldg(row + p);
-          if (p < 127) v[2] = __ldg(row + p + 1);
+          if (w0 + p < (WIDE ? P.W : 128) - 1) v[2] = __ldg(row + p + 1);
         }
       };
       float r0[3], r1[3], r2[3];
@@ -1257,9 +1298,9 @@ final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
         s2 += (double)wf * (double)g2;
         atomicAdd(&P.dw_last[c * 9 + (8 - k)], fmaf(sc, g2, sh * g1));
       }
-      atomicAdd(&P.dstats[c], s1);
-      atomicAdd(&P.dstats[32 + c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
-      if (c == 0) atomicAdd(&P.dstats[64], (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
+      atomicAdd(&P.ds1[c], s1);
+      atomicAdd(&P.ds2[c], (double)P.rstd[c] * (s2 - (double)P.mean[c] * s1));   // sum du * xhat
+      if (c == 0 && P.dsdl != nullptr) atomicAdd(P.dsdl, (double)gsm[3 * 32 * 9 + 4]);                // centre tap: sum of dlogits
     }
   }
   tc_fence_before();
@@ -1278,23 +1319,33 @@ static bool g_final_gemm_reduce = true;   // pass 1 as one accumulating GEMM (fi
 static int g_final_deep_ring = -1;        // pass 1 with the decoupled landing / operand rings (env VAE_FINAL_DEEP=1; measured slower: default 0)
 
 static bool final_tc_ok(int B, int H, int W, int C, int dtype) {
-  return g_final_tc_enabled && dtype == VAE_BF16 && C == 32 && W == 128 && B > 0 && H >= 16 && H % 16 == 0 &&
-         get_encode_fn() != nullptr;
+  // bf16; channel groups of 32 (C = 32: one launch per kernel, C = 64: two); rows of whole 128-pixel tiles
+  return g_final_tc_enabled && dtype == VAE_BF16 && (C == 32 || C == 64) && W >= 128 && W % 128 == 0 && B > 0 &&
+         H >= 16 && H % 16 == 0 && (long long)B * H * W < (1LL << 31) && get_encode_fn() != nullptr;
 }
 
-static int final_tc_setup(FinalTcParams& P, const void* y, int B, int H, int W) {
+// tensor map + tiling of ONE channel group `grp` (32 channels) of an NHWC tensor with C channels per pixel.
+// halo: forward kernel with W > 128 (overlapping tiles of 126 output pixels); else aligned 128-pixel tiles.
+static int final_tc_setup(FinalTcParams& P, const void* y, int B, int H, int W, int C, int grp, bool halo) {
+  const cuuint64_t pix = (cuuint64_t)C * 2;   // bytes per pixel
   cuuint64_t gdim[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+  cuuint64_t gstr[3] = {pix, (cuuint64_t)W * pix, (cuuint64_t)H * W * pix};
   cuuint32_t box[4] = {32, 128, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = get_encode_fn()(&P.tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(y), gdim, gstr, box,
-                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+  void* base = const_cast<uint8_t*>(static_cast<const uint8_t*>(y)) + (size_t)grp * 64;
+  CUresult cr = get_encode_fn()(&P.tmap_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VAE_REQUIRE(cr == CUDA_SUCCESS, "final_block_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   P.B = B; P.H = H; P.W = W;
   P.RB = H % 32 == 0 ? 32 : 16;
   P.bands_per_img = H / P.RB;
-  P.total_bands = B * P.bands_per_img;
+  if (halo) {
+    P.halo = 1; P.wstep = 126; P.tpr = (W + 125) / 126;
+  } else {
+    P.halo = 0; P.wstep = 128; P.tpr = W / 128;
+  }
+  P.total_bands = B * P.bands_per_img * P.tpr;
   return VAE_OK;
 }
 
@@ -1320,33 +1371,48 @@ extern "C" int vae_final_conv_fwd_tc(const void* y, const float* mean, const flo
   VAE_REQUIRE(y && mean && scale && beta && w_last && logits, "final_conv_fwd_tc: null argument");
   VAE_REQUIRE(final_tc_ok(B, H, W, C, VAE_BF16), "final_conv_fwd_tc: shape not served");
   VAE_REQUIRE(slope > 0.0f && slope < 1.0f, "final_conv_fwd_tc: LeakyReLU slope must be in (0, 1)");
-  FinalTcParams P{};
-  int rc = final_tc_setup(P, y, B, H, W);
-  if (rc != VAE_OK) return rc;
-  P.mean = mean; P.scale = scale; P.beta = beta; P.w_last = w_last; P.b_last = b_last;
-  P.logits = (bf16*)logits; P.probs = probs; P.slope = slope;
+  const int groups = C / 32;
+  VAE_REQUIRE(groups == 1 || probs != nullptr, "final_conv_fwd_tc: C = 64 needs the fp32 probs buffer (it carries the partial sums)");
   const size_t smem = kFwdSmemBytes;
   static bool attr = false;
   if (!attr) {
-    VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VAE_CUDA(cudaFuncSetAttribute(final_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  int grid = 3 * sm_count();
-  if (grid > P.total_bands) grid = P.total_bands;
-  final_fwd_tc_kernel<<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
-  return check_launch("final_fwd_tc");
+  for (int g = 0; g < groups; ++g) {   // one launch per group of 32 channels; partial logits travel in `probs` (fp32)
+    FinalTcParams P{};
+    int rc = final_tc_setup(P, y, B, H, W, C, g, W > 128);
+    if (rc != VAE_OK) return rc;
+    P.mean = mean + 32 * g; P.scale = scale + 32 * g; P.beta = beta + 32 * g; P.w_last = w_last + 32 * 9 * g; P.b_last = b_last;
+    P.logits = (bf16*)logits; P.probs = probs; P.slope = slope;
+    P.partial_in = g > 0 ? probs : nullptr;
+    P.partial_out = g + 1 < groups ? probs : nullptr;
+    int grid = 3 * sm_count();
+    if (grid > P.total_bands) grid = P.total_bands;
+    if (W > 128 && groups > 1) final_fwd_tc_kernel<true, true><<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
+    else if (W > 128) final_fwd_tc_kernel<true, false><<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
+    else if (groups > 1) final_fwd_tc_kernel<false, true><<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
+    else final_fwd_tc_kernel<false, false><<<grid, kFtThreads, smem, as_stream(stream)>>>(P);
+    rc = check_launch("final_fwd_tc");
+    if (rc != VAE_OK) return rc;
+  }
+  return VAE_OK;
 }
 
-static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
+template <bool WIDE>
+static int final_bwd_tc_launch_t(int pass, FinalTcParams& P, cudaStream_t st) {
   // pass 2: <4 slots, 3 CTAs per SM> measured 254 us against 297 us for <6 slots, 2 CTAs> on the B = 512 tensor
   constexpr int kP2Slots = 4, kP2Ctas = 3;
   static bool attr1 = false, attr2 = false;
   if (pass == 1 && !attr1) {
-    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<1, kFtSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
+    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<1, kFtSlots, 2, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
     attr1 = true;
   }
   if (pass == 2 && !attr2) {
-    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<2, kP2Slots, kP2Ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VAE_CUDA(cudaFuncSetAttribute(final_bwd_tc_kernel<2, kP2Slots, kP2Ctas, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)bwd_smem_bytes(kP2Slots)));
     attr2 = true;
   }
@@ -1370,15 +1436,19 @@ static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
     }
     static bool attr3 = false;
     if (!attr3) {
-      VAE_CUDA(cudaFuncSetAttribute(final_bwd_reduce_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP1SmemBytes));
+      VAE_CUDA(cudaFuncSetAttribute(final_bwd_reduce_gemm_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kP1SmemBytes));
       attr3 = true;
     }
-    final_bwd_reduce_gemm_kernel<<<grid, kFtThreads, kP1SmemBytes, st>>>(P);
+    final_bwd_reduce_gemm_kernel<WIDE><<<grid, kFtThreads, kP1SmemBytes, st>>>(P);
     return check_launch("final_bwd_reduce_gemm");
   }
-  if (pass == 1) final_bwd_tc_kernel<1, kFtSlots, 2><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
-  else final_bwd_tc_kernel<2, kP2Slots, kP2Ctas><<<grid, kFtThreads, bwd_smem_bytes(kP2Slots), st>>>(P);
+  if (pass == 1) final_bwd_tc_kernel<1, kFtSlots, 2, WIDE><<<grid, kFtThreads, kBwdSmemBytes, st>>>(P);
+  else final_bwd_tc_kernel<2, kP2Slots, kP2Ctas, WIDE><<<grid, kFtThreads, bwd_smem_bytes(kP2Slots), st>>>(P);
   return check_launch(pass == 1 ? "final_bwd_reduce_tc" : "final_bwd_apply_tc");
+}
+
+static int final_bwd_tc_launch(int pass, FinalTcParams& P, cudaStream_t st) {
+  return P.W > 128 ? final_bwd_tc_launch_t<true>(pass, P, st) : final_bwd_tc_launch_t<false>(pass, P, st);
 }
 
 /* tcgen05 version of vae_final_bwd_reduce (same contract, bf16 only) */
@@ -1392,12 +1462,17 @@ extern "C" int vae_final_bwd_reduce_tc(const void* dlogits, const void* y, const
   cudaStream_t st = as_stream(stream);
   VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * (2 * C + 1), st));
   VAE_CUDA(cudaMemsetAsync(dw_last, 0, sizeof(float) * 9 * C, st));
-  FinalTcParams P{};
-  int rc = final_tc_setup(P, y, B, H, W);
-  if (rc != VAE_OK) return rc;
-  P.mean = mean; P.scale = scale; P.beta = beta; P.rstd = rstd; P.w_last = w_last;
-  P.dl = (const bf16*)dlogits; P.dstats = dstats; P.dw_last = dw_last; P.slope = slope;
-  return final_bwd_tc_launch(1, P, st);
+  for (int g = 0; g < C / 32; ++g) {   // the reductions are per channel: one launch per group of 32
+    FinalTcParams P{};
+    int rc = final_tc_setup(P, y, B, H, W, C, g, false);
+    if (rc != VAE_OK) return rc;
+    P.mean = mean + 32 * g; P.scale = scale + 32 * g; P.beta = beta + 32 * g; P.rstd = rstd + 32 * g; P.w_last = w_last + 32 * 9 * g;
+    P.dl = (const bf16*)dlogits; P.dw_last = dw_last + 32 * 9 * g; P.slope = slope;
+    P.ds1 = dstats + 32 * g; P.ds2 = dstats + C + 32 * g; P.dsdl = g == 0 ? dstats + 2 * C : nullptr;
+    rc = final_bwd_tc_launch(1, P, st);
+    if (rc != VAE_OK) return rc;
+  }
+  return VAE_OK;
 }
 
 /* tcgen05 version of vae_final_bwd_apply (same contract, bf16 only) */
@@ -1435,17 +1510,23 @@ extern "C" int vae_final_bwd_apply_tc(const void* dlogits, const void* y, const 
   VAE_REQUIRE(slope > 0.0f && slope < 1.0f, "final_bwd_apply_tc: LeakyReLU slope must be in (0, 1)");
   cudaStream_t st = as_stream(stream);
   final_small_grads_kernel<<<1, 64, 0, st>>>(dstats, gamma, rstd, dgamma, dbeta, dbias, db_last, C, training);
-  FinalTcParams P{};
-  int rc = final_tc_setup(P, y, B, H, W);
-  if (rc != VAE_OK) return rc;
-  P.mean = mean; P.scale = scale; P.beta = beta; P.rstd = rstd; P.gamma = gamma; P.w_last = w_last;
-  {
-    FinalTcParams Q{};
-    rc = final_tc_setup(Q, dy, B, H, W);
+  for (int g = 0; g < C / 32; ++g) {
+    FinalTcParams P{};
+    int rc = final_tc_setup(P, y, B, H, W, C, g, false);
     if (rc != VAE_OK) return rc;
-    P.tmap_dy = Q.tmap_y;
+    P.mean = mean + 32 * g; P.scale = scale + 32 * g; P.beta = beta + 32 * g; P.rstd = rstd + 32 * g; P.gamma = gamma + 32 * g;
+    P.w_last = w_last + 32 * 9 * g;
+    {
+      FinalTcParams Q{};
+      rc = final_tc_setup(Q, dy, B, H, W, C, g, false);
+      if (rc != VAE_OK) return rc;
+      P.tmap_dy = Q.tmap_y;
+    }
+    P.dl = (const bf16*)dlogits; P.dy = (bf16*)dy;
+    P.ds1 = const_cast<double*>(dstats) + 32 * g; P.ds2 = const_cast<double*>(dstats) + C + 32 * g; P.dsdl = nullptr;
+    P.slope = slope; P.training = training;
+    rc = final_bwd_tc_launch(2, P, st);
+    if (rc != VAE_OK) return rc;
   }
-  P.dl = (const bf16*)dlogits; P.dstats = const_cast<double*>(dstats); P.dy = (bf16*)dy;
-  P.slope = slope; P.training = training;
-  return final_bwd_tc_launch(2, P, st);
+  return VAE_OK;
 }
