@@ -239,6 +239,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
     const int ew = warp & 3;           // TMEM lane group = warp % 4
     const int eset = (warp - 2) >> 2;  // warps 2-5: even tiles, 6-9: odd tiles
     const int r = ew * 32 + lane;
+    const bool has_bias = P.bias != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
     float run1[BNB ? 1 : 32], run2[BNB ? 1 : 32];
 #pragma unroll
@@ -287,13 +288,19 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
         }
         // channel base of this chunk
         const int cbase = MODE == 0 ? ci * 32 : 0;
+        if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
-          v[i] = valid ? v[i] + b4.x : 0.0f;
-          v[i + 1] = valid ? v[i + 1] + b4.y : 0.0f;
-          v[i + 2] = valid ? v[i + 2] + b4.z : 0.0f;
-          v[i + 3] = valid ? v[i + 3] + b4.w : 0.0f;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
+            v[i] += b4.x;
+            v[i + 1] += b4.y;
+            v[i + 2] += b4.z;
+            v[i + 3] += b4.w;
+          }
+        }
+        if (!valid) {     // rows past the end of the tensor (last tile only): keep them out of the statistics
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
         }
         float second[32];   // what the second statistic sums: y^2 (forward) or du * xhat (fused BN backward)
         if constexpr (BNB) {

@@ -270,6 +270,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const int ew = warp & 3;           // TMEM lane group = warp % 4
     const int eset = (warp - 2) >> 2;  // warps 2-5 serve accumulator 0 (even tiles), 6-9 accumulator 1
     const int r = ew * 32 + lane;
+    const bool has_bias = P.bias != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
     constexpr int RUN = BNB ? 1 : 32;   // BNB: the y prefetch needs the registers of the running sums
     float run1[RUN], run2[RUN];
@@ -319,13 +320,20 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
           if (ew == 0) VAE_TTRACE(5, it);
         }
         const int ncol = min(32, N - c0);
+        if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
-          v[i] = (valid && i < ncol) ? v[i] + b4.x : 0.0f;
-          v[i + 1] = (valid && i + 1 < ncol) ? v[i + 1] + b4.y : 0.0f;
-          v[i + 2] = (valid && i + 2 < ncol) ? v[i + 2] + b4.z : 0.0f;
-          v[i + 3] = (valid && i + 3 < ncol) ? v[i + 3] + b4.w : 0.0f;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
+            v[i] += b4.x;
+            v[i + 1] += b4.y;
+            v[i + 2] += b4.z;
+            v[i + 3] += b4.w;
+          }
+        }
+        if (!valid || ncol < 32) {   // rows past the end of the tensor / columns past N: keep them out of the statistics
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!valid || i >= ncol) v[i] = 0.0f;
         }
         float second[32];   // second statistic: y^2 (forward) or du * xhat (fused BN backward)
         if constexpr (BNB) {
