@@ -106,6 +106,9 @@ int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out,
  * cp.async.bulk.tensor (one strided box of the NHWC tensor per filter tap, zero-filled
  * outside the image) instead of cp.async threads.  Serves layers whose extents decompose
  * into whole output rows per tile and Cin == 32 or Cin % 64 == 0; no fused prologue. */
+/* 1 / 0: use the tensor-core kernel for the single-input-channel edge layer inside vae_conv_fprop (Ci = 1, Co = 32 / 64,
+ * stride 2, fp32 in, bf16 out); returns the previous setting. */
+int vae_set_edge_tc(int enable);
 int vae_set_umma_tma(int enable);
 int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode);
 long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode);

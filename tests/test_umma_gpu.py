@@ -320,3 +320,36 @@ def test_conv_with_fused_bn_backward_epilogue(ops, case):
     assert rel_err(nchw(du.float().cpu()), want) < TOL
     assert rel_err(dstats.cpu()[:C], want.sum(dim=(0, 2, 3))) < 2e-3
     assert rel_err(dstats.cpu()[C:], (want * xhat).sum(dim=(0, 2, 3))) < 2e-3
+
+
+# ---------------------------------------------------------------------------
+# edge layer (1 input channel) on tensor cores: conv_edge_tc.cu inside vae_conv_fprop
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(4, 128, 128, 32), (3, 64, 128, 32), (2, 128, 256, 64), (64, 128, 128, 32)],
+                         ids=lambda c: "B%d-%dx%d-N%d" % c)
+def test_edge_layer_tensor_core_forward(ops, case):
+    B, H, W, N = case
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, 1, H, W, generator=g) < 0.1).float()          # piano-roll: {0, 1}
+    x[0] = torch.rand(1, H, W, generator=g)                            # one grey image: inputs are rounded to bf16 there
+    w = rnd(N, 1, 3, 3, seed=2, scale=1.0 / 3.0)
+    b = rnd(N, seed=3, scale=0.1)
+    cw = ops.ConvWeights(w.cuda(), torch.bfloat16, 2)
+    outs = []
+    for tc in (True, False):
+        old = ops.set_edge_tc(tc)
+        try:
+            stats = torch.empty(2 * N, dtype=torch.float64, device="cuda")
+            y = ops.conv_forward(x.view(B, H, W, 1).cuda(), cw, b.cuda(), stats, Ci=1)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_edge_tc(old)
+        outs.append((y.float().cpu(), stats.cpu()))
+    ref = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), b.double(), stride=2, padding=1)
+    for y, stats in outs:
+        assert y.shape == (B, H // 2, W // 2, N)
+        assert rel_err(nchw(y), ref) < TOL
+        assert rel_err(stats[:N], ref.sum(dim=(0, 2, 3))) < 2e-3
+        assert rel_err(stats[N:], (ref**2).sum(dim=(0, 2, 3))) < 2e-3
+    # binary images: both kernels see exactly the same operands
+    assert rel_err(outs[0][0][1:], outs[1][0][1:]) < 4e-3

@@ -501,6 +501,8 @@ int edge_cin1(const GatherGeom& g, bool is_dgrad, const void* in, const void* wq
               double* stats, int dt_in, int dt_out, cudaStream_t st);
 int edge_c1_wgrad(const void* mc, const void* s1, float* dw, int B, int Hm, int Wm, int N, int Hs, int Ws, int mul,
                   int flip, int dt_m, int dt_s, cudaStream_t st);
+int edge_cin1_tc(const GatherGeom& g, const void* in, const void* wq, const float* bias, void* out, double* stats,
+                 int dt_in, int dt_out, cudaStream_t st);
 }  // namespace vae
 
 extern "C" int vae_conv_fprop(const void* x, const void* wp, const float* bias, void* y,
@@ -514,6 +516,8 @@ extern "C" int vae_conv_fprop(const void* x, const void* wp, const float* bias, 
   GatherGeom g = geom_fprop(B, Hi, Wi, Ci, Co, stride);
   const bool bf = dt_out == VAE_BF16;
   if (Ci == 1 && edge_ok(Co)) {
+    const int rt = edge_cin1_tc(g, x, wp, bias, y, stats, dt_in, dt_out, st);   // tensor cores: N = 32 / 64, stride 2, bf16 out
+    if (rt != 1) return rt;
     const int rc = edge_cin1(g, false, x, wp, bias, y, stats, dt_in, dt_out, st);
     if (rc != 1) return rc;
     if (dt_in == VAE_F32 && !bf) return launch_cin1<float, float, float>(g, x, wp, bias, y, stats, st);
