@@ -21,6 +21,7 @@
 // Grid = #SMs, persistent static tile schedule.  Layers whose extents do not
 // decompose into whole rows fall back to the cp.async gather kernel.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "conv_geom.cuh"
@@ -436,11 +437,24 @@ static bool tma_plan(TmaConvParams& P, const GatherGeom& g) {
   // sub-tiles per stage: as many as keep >= 3 stages in flight (each producer / issuer iteration costs
   // several hundred cycles of single-thread issue latency, so stages should carry 32 KB or more)
   const int sub_bytes = P.sub_a_bytes + P.sub_b_elems * 2;
+  // Stage size: the pipeline's period is set by the two single-thread control loops (producer: wait + expect-tx +
+  // copies; issuer: wait + MMAs + commit -- ~800 cycles per stage whatever it carries: skipping the A loads or the
+  // weight copies in a timing-only build changed the run time by < 8 %, `profiles/r03f_skip_copies.log`), so a stage should carry as much as leaves
+  // three stages in flight (measured in the step, B = 512: 64->128 fprop 87 -> 78 us for two launches, 128->256
+  // transposed 99 -> 90 us; one sub-tile per stage everywhere: +25 .. +35 %; two stages of four sub-tiles: worse on the
+  // N = 64 and N = 256 layers).
+  const int budget = 218 * 1024;   // 227 KB - alignment slack - barriers / statistics / bias / BN vectors
   P.sps = P.kc == 32 ? 4 : 2;
-  while (P.sps > 1 && (190 * 1024) / (P.sps * sub_bytes) < 3) P.sps /= 2;
+  {
+    static int env_sps = -1;
+    if (env_sps < 0) { const char* e = getenv("VAE_TMA_SPS"); env_sps = e ? atoi(e) : 0; }
+    if (env_sps > 0) P.sps = env_sps;
+  }
+  while (P.sps > 1 && budget / (P.sps * sub_bytes) < 3) P.sps /= 2;
   P.a_stage_bytes = P.sps * P.sub_a_bytes;
   P.b_stage_bytes = (P.sps * P.sub_b_elems * 2 + 1023) / 1024 * 1024;
-  P.stages = (190 * 1024) / (P.a_stage_bytes + P.b_stage_bytes);
+  P.stages = budget / (P.a_stage_bytes + P.b_stage_bytes);
+  if (P.kc == 64 && P.stages > 3) P.stages = 3;   // a fourth stage of 48 KB measured 3 - 5 % slower in the step (N = 64, N = 256)
   if (P.stages > kTStagesMax) P.stages = kTStagesMax;
   if (P.stages < 2) return false;
   int cols = 32;
