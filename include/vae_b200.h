@@ -109,6 +109,10 @@ int vae_conv_umma(const void* in, const void* wpk, const float* bias, void* out,
 /* 1 / 0: use the tensor-core kernel for the single-input-channel edge layer inside vae_conv_fprop (Ci = 1, Co = 32 / 64,
  * stride 2, fp32 in, bf16 out); returns the previous setting. */
 int vae_set_edge_tc(int enable);
+/* Bit 0: serve transposed stride-2 convs with 64 output channels (mode 1 of vae_conv_umma_tma) by the kernel that fuses the
+ * four output-parity phases (conv_umma_tmat.cu); bit 1: also 128 output channels (measured slower; for tests).  Also selects the layout vae_umma_tma_pack_weight produces
+ * for those layers: flip it BEFORE packing.  Returns the previous setting. */
+int vae_set_umma_tmat(int enable);
 int vae_set_umma_tma(int enable);
 int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int stride, int mode);
 long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode);

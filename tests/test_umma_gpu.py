@@ -195,11 +195,22 @@ TMA_CASES = [
     (3, 16, 16, 32, 32, 1),     # stride 1
     (64, 64, 64, 32, 64, 2),    # many tiles per CTA
     (4, 16, 128, 256, 512, 2),  # wide model: 512 output channels = two 256-channel launches (UMMA N <= 256)
+    (2, 64, 512, 64, 64, 2),    # transposed form on the fused-phase kernel (conv_umma_tmat.cu): one 64-channel chunk, Wj = 256
+    (40, 32, 32, 64, 128, 2),   # fused-phase kernel, two chunks, several tiles per CTA and both accumulator sets
+    (33, 16, 16, 128, 256, 2),  # fused-phase kernel with 128 output channels: one accumulator set, epilogue sets split the rows
 ]
 
 
+@pytest.fixture
+def tmat_wide(ops):
+    """Run the fused-phase transposed-conv kernel for 128 output channels too (off by default: slower there)."""
+    old = ops.set_umma_tmat(3)
+    yield
+    ops.set_umma_tmat(old)
+
+
 @pytest.mark.parametrize("case", TMA_CASES)
-def test_umma_tma_fprop_and_dgrad(ops, case):
+def test_umma_tma_fprop_and_dgrad(ops, case, tmat_wide):
     B, H, W, Ci, Co, s = case
     x = rnd(B, Ci, H, W, seed=1)
     w = rnd(Co, Ci, 3, 3, seed=2, scale=1.0 / math.sqrt(9 * Ci))

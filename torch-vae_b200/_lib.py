@@ -30,6 +30,7 @@ PROTOTYPES = {
     "vae_umma_pack_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
     "vae_conv_umma": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_edge_tc": [_i],
+    "vae_set_umma_tmat": [_i],
     "vae_set_umma_tma": [_i],
     "vae_umma_tma_eligible": [_i, _i, _i, _i, _i, _i, _i],
     "vae_umma_tma_packed_elems": [_i, _i, _i, _i],

@@ -38,6 +38,13 @@ constexpr int kTThreads = 320;  // producer warp, MMA warp, 2 x 4 epilogue warps
 
 long long* umma_trace_ptr();
 
+// fused-phase transposed conv (conv_umma_tmat.cu): serves mode 1 with 64 / 128 output channels behind this file's entry points
+bool tmat_channels_ok(int Ci, int Co, int stride, int mode);
+long long tmat_packed_elems(int Ci, int Co);
+int tmat_pack(const float* w_oihw, void* out, int Ci, int Co, cudaStream_t st);
+int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi, int Ci,
+                int Co, cudaStream_t st, const void* bn_y, const float* const* bn_vec, float slope);
+
 struct TmaConvParams {
   CUtensorMap tmap;
   GatherGeom g;
@@ -509,6 +516,7 @@ extern "C" int vae_umma_tma_eligible(int B, int Hi, int Wi, int Ci, int Co, int 
 }
 
 extern "C" long long vae_umma_tma_packed_elems(int Ci, int Co, int stride, int mode) {
+  if (tmat_channels_ok(Ci, Co, stride, mode)) return tmat_packed_elems(Ci, Co);
   const int ns = tma_nsplit(Co, mode), co = Co / ns;
   GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, co, stride)
                            : geom_dgrad(1, 128 * stride, 128 * stride, Ci, co, stride);
@@ -521,6 +529,7 @@ extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, 
                                         vae_stream_t stream) {
   VAE_REQUIRE(w_oihw && out && (mode == 0 || mode == 1) && (stride == 1 || stride == 2),
               "umma_tma_pack_weight: bad argument");
+  if (tmat_channels_ok(Ci, Co, stride, mode)) return tmat_pack(w_oihw, out, Ci, Co, as_stream(stream));
   const int ns = tma_nsplit(Co, mode), co = Co / ns;
   GatherGeom g = mode == 0 ? geom_fprop(1, 128 * stride, 128 * stride, Ci, co, stride)
                            : geom_dgrad(1, 128 * stride, 128 * stride, Ci, co, stride);
@@ -551,6 +560,11 @@ static int tma_dispatch(const void* in, const void* wpk, const float* bias, void
   VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
                   (mode == 0 || mode == 1),
               "conv_umma_tma: bad argument");
+  if (tmat_channels_ok(Ci, Co, stride, mode)) {   // transposed conv, 64 / 128 output channels: the four phases fused
+    const int rc = tmat_launch(in, wpk, bias, out, stats, B, Hi, Wi, Ci, Co, as_stream(stream), bn_y, bn_vec, slope);
+    VAE_REQUIRE(rc != 1, "conv_umma_tma: shape not served by the fused transposed-conv kernel");
+    return rc;
+  }
   const int ns = tma_nsplit(Co, mode), co = Co / ns;
   GatherGeom g = mode == 0 ? geom_fprop(B, Hi, Wi, Ci, co, stride) : geom_dgrad(B, Hi, Wi, Ci, co, stride);
   TmaConvParams P{};
