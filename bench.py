@@ -221,6 +221,10 @@ def algorithmic_cost(name, tag):
     if name == "vae_bn_lrelu_bwd_reduce":
         n, C, d = t[:3]
         return (2 * n * C * _sz(d), 8 * n * C)
+    if name == "vae_bn_lrelu_bwd_fused":   # n_pix, C, training, dtype: d_act + y in (the second read is served by the L2), dy out
+        n, C = t[:2]
+        d = t[3] if len(t) > 3 else 0
+        return (3 * n * C * _sz(d), 18 * n * C)
     if name == "vae_bn_lrelu_bwd_apply":
         n, C = t[:2]
         d = t[3] if len(t) > 3 else 0

@@ -220,6 +220,15 @@ int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const float* scale,
                            float* dbeta, float* dbias, long long n_pix, int C, float slope,
                            int training, int dtype, vae_stream_t stream);
 
+/* Both passes in ONE cooperative launch for tensors that stay in the L2 between them (d_act + y <= 96 MB): reduce,
+ * grid-wide arrival counter, apply on the same pixels.  dstats: [2C + 1] doubles, zeroed by the call.  Returns
+ * VAE_ERR_UNSUPPORTED (-3) when the shape should take the two-pass path.
+ * replaces: aten::leaky_relu_backward + aten::native_batch_norm_backward (train.py:650) */
+int vae_bn_lrelu_bwd_fused(const void* dact, const void* y, const float* scale, const float* beta,
+                           const float* mean, const float* rstd, const float* gamma, double* dstats, void* dy,
+                           float* dgamma, float* dbeta, float* dbias, long long n_pix, int C, float slope,
+                           int training, int dtype, vae_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Fused output block of the decoder (models.py:76-82, run at :171):
  *   y = ConvT(..) [B,H,W,C] -> BatchNorm2d -> LeakyReLU -> Conv2d(C->1,k3,s1,p1) -> Sigmoid.

@@ -109,10 +109,13 @@ def test_conv_fprop_dgrad_wgrad(tv, case, dtype):
     assert rel_err(dw.cpu(), wr.grad) < (1e-5 if dtype == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize("one_launch", [True, False], ids=["cooperative_fused_backward", "two_pass_backward"])
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("C,n_pix_shape", [(32, (4, 16, 16)), (8, (2, 8, 8)), (24, (3, 4, 6)), (20, (2, 4, 4))])
-def test_batchnorm_lrelu_forward_backward(tv, C, n_pix_shape, dtype):
+@pytest.mark.parametrize("C,n_pix_shape", [(32, (4, 16, 16)), (8, (2, 8, 8)), (24, (3, 4, 6)), (20, (2, 4, 4)), (128, (64, 16, 16)),
+                                           (64, (96, 32, 32))])
+def test_batchnorm_lrelu_forward_backward(tv, C, n_pix_shape, dtype, one_launch, monkeypatch):
     ops = tv.ops
+    monkeypatch.setattr(ops, "FUSE_BN_BWD_PASSES", one_launch)   # both passes in one cooperative launch, or two kernels
     B, H, W = n_pix_shape
     y = rnd(B, C, H, W, seed=1, scale=2.0) + 0.3
     gamma, beta = rnd(C, seed=2) * 0.2 + 1.0, rnd(C, seed=3) * 0.1

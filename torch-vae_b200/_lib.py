@@ -54,6 +54,7 @@ PROTOTYPES = {
     "vae_bn_apply_lrelu": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp],
     "vae_bn_lrelu_bwd_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp],
+    "vae_bn_lrelu_bwd_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp],
     "vae_final_block_supported": [_i, _i, _i, _i],
     "vae_final_conv_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
     "vae_final_bwd_reduce": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],

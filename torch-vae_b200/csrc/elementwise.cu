@@ -413,6 +413,154 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, const T* __restrict__ y,
   }
 }
 
+// Both passes in ONE cooperative launch for tensors that fit the L2 twice over (d_act + y <= ~96 MB): every block
+// reduces its pixels, the grid meets at a counter, then every block applies the gradient to THE SAME pixels, which it
+// now finds in the L2 / L1 instead of HBM.  dstats: [2C] sums + one 64-bit arrival counter (zeroed by the caller).
+template <typename T, int V>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_fused_kernel(const T* __restrict__ dact, const T* __restrict__ y,
+                    const float* __restrict__ scale, const float* __restrict__ beta,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, double* __restrict__ dstats,
+                    T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ dbias, long long n_pix, int C, float slope, int training) {
+  extern __shared__ float red[];  // [lanes][G][2V]
+  const int G = C / V;
+  const int lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  const bool active = lane < lanes;
+  float sc[V], sh[V], mu[V], rs[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    sc[k] = active ? scale[g * V + k] : 0.0f;
+    sh[k] = active ? beta[g * V + k] : 0.0f;
+    mu[k] = active ? mean[g * V + k] : 0.0f;
+    rs[k] = active ? rstd[g * V + k] : 0.0f;
+  }
+  const long long step = (long long)gridDim.x * lanes;
+  constexpr int U = BnUnroll<T>::U;
+  // ---- pass 1: sum du, sum du * xhat
+  {
+    float s1[V], s2[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s1[k] = s2[k] = 0.0f;
+    if (active) {
+      for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * U) {
+        RawVec<T, V> d[U], yy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long p = p0 + u * step;
+          if (p < n_pix) {
+            d[u].load(dact + p * C + g * V);
+            yy[u].load(y + p * C + g * V);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (p0 + u * step < n_pix) {
+            float dv[V], yv[V];
+            d[u].get(dv);
+            yy[u].get(yv);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              const float uu = bn_affine(yv[k], mu[k], sc[k], sh[k]);
+              const float du = uu > 0.0f ? dv[k] : dv[k] * slope;
+              const float xh = (yv[k] - mu[k]) * rs[k];
+              s1[k] += du;
+              s2[k] = fmaf(du, xh, s2[k]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        red[(lane * G + g) * 2 * V + k] = s1[k];
+        red[(lane * G + g) * 2 * V + V + k] = s2[k];
+      }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * C; o += blockDim.x) {
+      const int which = o / C, c = o % C;
+      const int gg = c / V, k = c % V;
+      double acc = 0.0;
+      for (int l = 0; l < lanes; ++l) acc += (double)red[(l * G + gg) * 2 * V + which * V + k];
+      atomicAdd(&dstats[which * C + c], acc);
+    }
+  }
+  // ---- the whole grid has contributed (cooperative launch: all blocks are resident)
+  __threadfence();
+  __syncthreads();
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(dstats + 2 * C);
+  if (threadIdx.x == 0) {
+    atomicAdd(counter, 1ULL);
+    while (*reinterpret_cast<volatile unsigned long long*>(counter) < (unsigned long long)gridDim.x) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- pass 2: dy (+ the small gradients)
+  const double inv_m = 1.0 / (double)n_pix;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] = (float)__ldcg(&dstats[c]);
+      dgamma[c] = (float)__ldcg(&dstats[C + c]);
+    }
+  }
+  float sdy[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) sdy[k] = 0.0f;
+  __syncthreads();   // red is reused below
+  if (active) {
+    float c1[V], c2[V], a[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int c = g * V + k;
+      a[k] = gamma[c] * rs[k];
+      c1[k] = training ? (float)(__ldcg(&dstats[c]) * inv_m) : 0.0f;
+      c2[k] = training ? (float)(__ldcg(&dstats[C + c]) * inv_m) : 0.0f;
+    }
+    for (long long p0 = (long long)blockIdx.x * lanes + lane; p0 < n_pix; p0 += step * U) {
+      RawVec<T, V> d[U], yy[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < n_pix) {
+          d[u].load(dact + p * C + g * V);
+          yy[u].load(y + p * C + g * V);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < n_pix) {
+          float dv[V], yv[V];
+          d[u].get(dv);
+          yy[u].get(yv);
+          ChanVec<T, V> o;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            const float uu = bn_affine(yv[k], mu[k], sc[k], sh[k]);
+            const float du = uu > 0.0f ? dv[k] : dv[k] * slope;
+            const float xh = (yv[k] - mu[k]) * rs[k];
+            const float r = a[k] * (du - c1[k] - xh * c2[k]);
+            o.v[k] = r;
+            sdy[k] += r;
+          }
+          o.store(dy + p * C + g * V);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) red[(lane * G + g) * V + k] = sdy[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gg = c / V, k = c % V;
+    float acc = 0.0f;
+    for (int l = 0; l < lanes; ++l) acc += red[(l * G + gg) * V + k];
+    atomicAdd(&dbias[c], acc);
+  }
+}
+
 // ------------------------------------------------------------------ transposes
 // src[b][r][c] (R x Cc) -> dst[b][c][r]
 template <typename TS, typename TD>
@@ -772,6 +920,50 @@ extern "C" int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const flo
   }
 #undef LAUNCH
   return check_launch("bn_lrelu_bwd_apply");
+}
+
+/* Both passes of the BatchNorm + LeakyReLU backward in ONE cooperative launch (reduce, grid-wide arrival counter,
+ * apply on the same pixels, now cache-resident).  dstats: [2C + 1] doubles (the last one is the arrival counter),
+ * zeroed by this call.  Returns VAE_ERR_UNSUPPORTED when the shape should take the two-pass path (tensor too large to
+ * stay in the L2, or the grid cannot be made co-resident).
+ * replaces: aten::leaky_relu_backward + aten::native_batch_norm_backward (train.py:650) */
+extern "C" int vae_bn_lrelu_bwd_fused(const void* dact, const void* y, const float* scale, const float* beta,
+                                      const float* mean, const float* rstd, const float* gamma, double* dstats, void* dy,
+                                      float* dgamma, float* dbeta, float* dbias, long long n_pix, int C, float slope,
+                                      int training, int dtype, vae_stream_t stream) {
+  VAE_REQUIRE(dact && y && scale && beta && mean && rstd && gamma && dstats && dy && dgamma && dbeta && dbias && n_pix > 0 &&
+                  C > 0,
+              "bn_lrelu_bwd_fused: bad argument");
+  BwdCfg cfg;
+  const size_t elem = dtype == VAE_BF16 ? 2 : 4;
+  if (!bwd_cfg(n_pix, C, &cfg) || (size_t)n_pix * C * elem * 2 > (size_t)96 << 20) return VAE_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem = sizeof(float) * cfg.lanes * cfg.G * 2 * cfg.V;
+  void* kern = nullptr;
+  if (dtype == VAE_BF16) kern = cfg.V == 8 ? (void*)bn_bwd_fused_kernel<bf16, 8> : (void*)bn_bwd_fused_kernel<bf16, 1>;
+  else kern = cfg.V == 8 ? (void*)bn_bwd_fused_kernel<float, 8> : (void*)bn_bwd_fused_kernel<float, 1>;
+  int per_sm = 0;
+  VAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) return VAE_ERR_UNSUPPORTED;
+  int grid = cfg.grid;
+  if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
+  VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * (2 * C + 1), st));
+  VAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+  void* args[] = {(void*)&dact, (void*)&y, (void*)&scale, (void*)&beta, (void*)&mean, (void*)&rstd, (void*)&gamma,
+                  (void*)&dstats, (void*)&dy, (void*)&dgamma, (void*)&dbeta, (void*)&dbias, (void*)&n_pix, (void*)&C,
+                  (void*)&slope, (void*)&training};
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3(256);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // all blocks resident at once: the arrival counter cannot deadlock
+  attr[0].val.cooperative = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  VAE_CUDA(cudaLaunchKernelExC(&lc, kern, args));
+  return check_launch("bn_lrelu_bwd_fused");
 }
 
 template <typename TS, typename TD>

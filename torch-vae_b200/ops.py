@@ -219,6 +219,12 @@ def bn_apply_lrelu(y, vec, beta, slope: float = LRELU_SLOPE):
     return act
 
 
+# One cooperative launch for both passes of the BatchNorm backward when the tensors stay in the L2 (bn_lrelu_backward).
+# Measured SLOWER on the B200 (128 channels @16x16, B = 512: 69 us against 25 + 23 us for the two kernels): the
+# cooperative launch and the grid-wide arrival cost more than the second HBM read they save.  Opt-in; DESIGN.md 6.1.
+FUSE_BN_BWD_PASSES = False
+
+
 def _small_outs(outs, C, device):
     """(dgamma, dbeta, dbias) destinations: caller-provided fp32 [C] tensors (gradient-bucket views) or fresh ones."""
     if outs is not None:
@@ -237,6 +243,21 @@ def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = 
     n_pix = y.numel() // C
     lib = _L()
     is_du = dstats is not None
+    if not is_du and FUSE_BN_BWD_PASSES and 2 * y.numel() * y.element_size() <= 96 << 20:
+        # small enough to stay in the L2 between the passes: one cooperative launch (reduce, grid arrival, apply)
+        dstats = torch.empty(2 * C + 1, dtype=torch.float64, device=y.device)
+        dy = torch.empty_like(y)
+        dgamma, dbeta, dbias = _small_outs(outs, C, y.device)
+        rc = lib.vae_bn_lrelu_bwd_fused(
+            _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
+            _f32(gamma, "bn weight"), _p(dstats), _p(dy), _p(dgamma), _p(dbeta), _p(dbias), n_pix, C, slope,
+            1 if training else 0, code(y), _stream(),
+        )
+        if rc == 0:
+            return dy, dgamma, dbeta, dbias
+        if rc != -3:   # -3: VAE_ERR_UNSUPPORTED, take the two-pass path
+            _lib.check(rc, "vae_bn_lrelu_bwd_fused")
+        dstats = None
     if not is_du:
         dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
         rc = lib.vae_bn_lrelu_bwd_reduce(
