@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW instead of the fused kernel")
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager (reference class on cuda) leg")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to NCCL kernels in multi-GPU runs (persistent kernels use the rest)")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel CUDA-event breakdown here")
     return apply_workload(ap.parse_args())
 
@@ -512,6 +513,8 @@ def b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tv.load_library()
+    if world > 1 and a.reserve_sms > 0:
+        ops.set_reserved_sms(a.reserve_sms)
 
     dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     B, H, W = a.batch, a.height, a.width

@@ -40,6 +40,9 @@ extern "C" {
 
 typedef void* vae_stream_t;
 
+/* Leave `n` SMs out of the grids of the persistent kernels, for NCCL kernels that run concurrently in data-parallel runs
+ * with large gradient buckets (the persistent kernels otherwise occupy every SM completely); returns the previous value. */
+int vae_set_reserved_sms(int n);
 int vae_abi_version(void);
 const char* vae_last_error(void);
 /* 1 if the library was built with the tcgen05/TMEM (UMMA) conv kernels. */

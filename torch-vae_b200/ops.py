@@ -66,7 +66,7 @@ class _Proxy:
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
                           "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported", "vae_set_final_tc",
-                          "vae_final_tc_supported", "vae_linear_tc_supported", "vae_set_edge_tc", "vae_set_umma_tmat"})
+                          "vae_final_tc_supported", "vae_linear_tc_supported", "vae_set_edge_tc", "vae_set_umma_tmat", "vae_set_reserved_sms"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -724,6 +724,11 @@ def conv_umma_tma(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: in
 
 def umma_rw_eligible(B: int, Hi: int, Wi: int, Ci: int, Co: int, stride: int, mode: int) -> bool:
     return bool(_L().vae_umma_rw_eligible(B, Hi, Wi, Ci, Co, stride, mode))
+
+
+def set_reserved_sms(n: int) -> int:
+    """Leave ``n`` SMs to concurrent NCCL kernels (persistent kernels size their grids for the rest); returns the old value."""
+    return int(_L().vae_set_reserved_sms(int(n)))
 
 
 def set_umma_tmat(flags: int) -> int:
