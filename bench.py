@@ -175,7 +175,7 @@ def algorithmic_cost(name, tag):
         B, Hi, Wi, Ci, Co, s, dx, dy = t[:8]
         Ho, Wo = Hi // s, Wi // s
         return (B * Hi * Wi * Ci * _sz(dx) + B * Ho * Wo * Co * _sz(dy) + 9 * Ci * Co * 4, 2 * B * Ho * Wo * Co * 9 * Ci)
-    if name in ("vae_conv_umma", "vae_conv_umma_tma", "vae_conv_umma_rw"):
+    if name in ("vae_conv_umma", "vae_conv_umma_tma", "vae_conv_umma_rw", "vae_conv_umma_rw_act", "vae_conv_umma_tma_act"):
         B, Hi, Wi, Ci, Co, s = t[:6]
         Ho, Wo = Hi // s, Wi // s
         return (2 * (B * Hi * Wi * Ci + B * Ho * Wo * Co + 9 * Ci * Co), 2 * B * Ho * Wo * Co * 9 * Ci)

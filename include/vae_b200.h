@@ -149,6 +149,18 @@ int vae_conv_umma_rw(const void* in, const void* wpk, const float* bias, void* o
                      int B, int Hi, int Wi, int Ci, int Co, int stride, int mode,
                      vae_stream_t stream);
 
+/* The same two kernels for INFERENCE (model.eval() under torch.no_grad(): models.py:250-263, evaluation.py:42-65):
+ * eval-mode BatchNorm (running statistics: mean, scale = gamma / sqrt(running_var + eps), beta) + LeakyReLU applied in
+ * the epilogue, out = lrelu((acc + bias - mean) * scale + beta): the block writes its ACTIVATION, no statistics, no
+ * separate normalisation pass.
+ * replaces: aten::convolution + aten::native_batch_norm (eval) + aten::leaky_relu of one block (models.py:45-47,66-70) */
+int vae_conv_umma_rw_act(const void* in, const void* wpk, const float* bias, void* out, const float* mean,
+                         const float* scale, const float* beta, float slope, int B, int Hi, int Wi, int Ci, int Co,
+                         int stride, int mode, vae_stream_t stream);
+int vae_conv_umma_tma_act(const void* in, const void* wpk, const float* bias, void* out, const float* mean,
+                          const float* scale, const float* beta, float slope, int B, int Hi, int Wi, int Ci, int Co,
+                          int stride, int mode, vae_stream_t stream);
+
 /* The same two kernels producing the gradient w.r.t. an activation act = lrelu(bn(y)) of the layer below
  * (models.py:45-47,66-70) with the first half of that BatchNorm's backward fused into the epilogue: `y` is the
  * stored pre-normalisation tensor of the layer below (same shape as `out`), mean / scale (= gamma*rstd) / beta / rstd its

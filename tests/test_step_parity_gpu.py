@@ -293,6 +293,50 @@ def test_eval_mode_and_no_grad(tv):
     assert not torch.equal(a, b), "reparameterize must sample in eval mode too (models.py:181-183)"
 
 
+@pytest.mark.parametrize("shape", [(128, 128, [32, 64, 128, 256], 10, 16), (128, 256, [64, 128, 256, 512], 64, 4)],
+                         ids=["default_128x128", "wide_128x256"])
+def test_inference_epilogue_bf16(tv, shape, monkeypatch):
+    """model.eval() under no_grad (sample(), evaluate(): models.py:250-263, evaluation.py:42-65) in bf16: eval-mode
+    BatchNorm + LeakyReLU ride in the conv epilogues (vae_conv_umma_*_act), so the blocks write their activations in
+    one pass.  Same outputs as the two-pass path (conv -> y -> normalise), and both match the oracle."""
+    H, W, hidden, L, B = shape
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    params = vo.xavier_params(1, L, H, W, hidden, seed=0)
+    x, eps = vo.synthetic_batch(B, H, W, L, seed=1234)
+    model = build(tv, H, W, hidden, L, 1.0, torch.bfloat16, params).train()
+    with torch.no_grad():
+        model(x.cuda(), eps=eps.cuda())   # one train-mode forward: running statistics away from (0, 1)
+    ref_train = vo.step(params, x, eps, need_grads=False)
+    ref = vo.step(params, x, eps, buffers=ref_train["buffers"], training=False, need_grads=False)
+    model.eval()
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(tv.engine, "INFERENCE_EPILOGUE", fused)
+        tl = tv.ops.Timeline()
+        tv.ops.set_timeline(tl)
+        try:
+            with torch.no_grad():
+                o = model(x.cuda(), eps=eps.cuda())
+                z = torch.randn(B, L, generator=torch.Generator().manual_seed(5))
+                img = model.decode(z.cuda())
+            torch.cuda.synchronize()
+        finally:
+            tv.ops.set_timeline(None)
+        names = [k[0] for k, v in tl.summary().items() for _ in range(v[0])]
+        outs.append((o["output"].float().cpu(), o["encoded"]["mu"].cpu(), img.float().cpu(), names))
+        assert vo.rel_err(o["output"], ref["output"].reshape(o["output"].shape)) <= 2e-2
+        assert vo.rel_err(o["encoded"]["mu"], ref["mu"]) <= 2e-2
+    (out_f, mu_f, img_f, n_f), (out_u, mu_u, img_u, n_u) = outs
+    assert vo.rel_err(out_f, out_u) <= 5e-3 and vo.rel_err(mu_f, mu_u) <= 5e-3 and vo.rel_err(img_f, img_u) <= 5e-3
+    n_act = sum(n.endswith("_act") for n in n_f)
+    # encoder blocks after the first (fp32 image in) + decoder blocks of forward() and of decode(); the output block
+    # keeps its own fused kernel (BatchNorm + LeakyReLU + Conv2d + sigmoid)
+    n_blocks = 3 * (len(hidden) - 1)
+    assert n_act == n_blocks and not any(n.endswith("_act") for n in n_u), (n_f, n_u)
+    norm = lambda names: sum(n in ("vae_bn_apply_lrelu", "vae_bn_finalize_apply_lrelu") for n in names)
+    assert norm(n_u) - norm(n_f) == n_act   # those blocks no longer run a normalisation pass over y
+
+
 def test_decode_sample_and_generate(tv):
     H = W = 32
     hidden, L = [8, 16, 32, 64], 6

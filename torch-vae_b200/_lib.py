@@ -42,6 +42,8 @@ PROTOTYPES = {
     "vae_umma_rw_packed_elems": [_i, _i],
     "vae_umma_rw_pack_weight": [_vp, _vp, _i, _i, _i, _vp],
     "vae_conv_umma_rw": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_conv_umma_rw_act": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "vae_conv_umma_tma_act": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_conv_umma_rw_bnbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_conv_umma_tma_bnbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _i, _i, _vp],
     "vae_set_wgrad_tma": [_i],

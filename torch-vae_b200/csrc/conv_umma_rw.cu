@@ -43,6 +43,10 @@ struct RwParams {
   const bf16* bn_y;
   const float *bn_mean, *bn_scale, *bn_beta, *bn_rstd;   // [N] each (scale = gamma * rstd)
   float slope;
+  // Inference epilogue (optional, no statistics, no backward): eval-mode BatchNorm + LeakyReLU applied to the
+  // accumulator row, so the layer writes its ACTIVATION and the separate normalisation pass disappears:
+  //   out = lrelu((acc + bias - act_mean) * act_scale + act_beta)        (the expression of the apply kernel)
+  const float *act_mean, *act_scale, *act_beta;
 };
 
 template <int MODE, int KC, int N>
@@ -109,6 +113,8 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   for (int i = threadIdx.x; i < 64; i += kRwThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
   if constexpr (BNB)
     for (int i = threadIdx.x; i < N; i += kRwThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
+  else if (P.act_scale != nullptr)
+    for (int i = threadIdx.x; i < N; i += kRwThreads) s_bn[i] = make_float4(P.act_mean[i], P.act_scale[i], P.act_beta[i], 0.0f);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kRwMaxStages; ++s) {
@@ -240,6 +246,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
     const int eset = (warp - 2) >> 2;  // warps 2-5: even tiles, 6-9: odd tiles
     const int r = ew * 32 + lane;
     const bool has_bias = P.bias != nullptr;
+    const bool has_act = !BNB && P.act_scale != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
     float run1[BNB ? 1 : 32], run2[BNB ? 1 : 32];
 #pragma unroll
@@ -296,6 +303,14 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
             v[i + 1] += b4.y;
             v[i + 2] += b4.z;
             v[i + 3] += b4.w;
+          }
+        }
+        if (has_act) {    // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta
+            const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+            v[i] = u > 0.0f ? u : u * P.slope;
           }
         }
         if (!valid) {     // rows past the end of the tensor (last tile only): keep them out of the statistics
@@ -430,7 +445,8 @@ static bool rw_plan(RwPlan& p, int B, int Hi, int Wi, int Ci, int Co, int stride
 
 template <int MODE, int KC, int N>
 static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const float* bias, void* out, double* stats,
-                     int B, cudaStream_t st, const void* bn_y = nullptr, const float* const* bn_vec = nullptr, float slope = 0.0f) {
+                     int B, cudaStream_t st, const void* bn_y = nullptr, const float* const* bn_vec = nullptr, float slope = 0.0f,
+                     const float* const* act = nullptr) {
   using Cfg = RwCfg<MODE, KC, N>;
   RwParams P{};
   cuuint64_t gdim[4] = {(cuuint64_t)KC, (cuuint64_t)pl.Win, (cuuint64_t)pl.Hin, (cuuint64_t)B};
@@ -453,6 +469,7 @@ static int rw_launch(const RwPlan& pl, const void* in, const void* wpk, const fl
   P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;
   P.bn_y = (const bf16*)bn_y; P.slope = slope;
   if (bn_y != nullptr) { P.bn_mean = bn_vec[0]; P.bn_scale = bn_vec[1]; P.bn_beta = bn_vec[2]; P.bn_rstd = bn_vec[3]; }
+  if (act != nullptr) { P.act_mean = act[0]; P.act_scale = act[1]; P.act_beta = act[2]; }
   auto kern = bn_y != nullptr ? umma_rw_conv_kernel<MODE, KC, N, true> : umma_rw_conv_kernel<MODE, KC, N, false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[bn_y != nullptr]) {
@@ -499,16 +516,16 @@ extern "C" int vae_umma_rw_pack_weight(const float* w_oihw, void* out, int Ci, i
  * aten::convolution_backward (train.py:650) on the narrow layers */
 static int rw_dispatch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi,
                        int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* const* bn_vec,
-                       float slope) {
+                       float slope, const float* const* act = nullptr) {
   VAE_REQUIRE(in && wpk && out && (mode == 0 || mode == 1), "conv_umma_rw: bad argument");
   RwPlan pl{};
   VAE_REQUIRE(rw_plan(pl, B, Hi, Wi, Ci, Co, stride, mode), "conv_umma_rw: shape not served by this kernel");
   cudaStream_t st = as_stream(stream);
   if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * pl.n, st));
-  if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
-  if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
-  if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
-  if (mode == 1 && pl.kc == 64) return rw_launch<1, 64, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope);
+  if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
+  if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
+  if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
+  if (mode == 1 && pl.kc == 64) return rw_launch<1, 64, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
   set_error("conv_umma_rw: no instantiation");
   return VAE_ERR_UNSUPPORTED;
 }
@@ -531,4 +548,16 @@ extern "C" int vae_conv_umma_rw_bnbwd(const void* in, const void* wpk, void* out
   VAE_REQUIRE(y && mean && scale && beta && rstd && dstats, "conv_umma_rw_bnbwd: bad argument");
   const float* vec[4] = {mean, scale, beta, rstd};
   return rw_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, vec, slope);
+}
+
+/* vae_conv_umma_rw for INFERENCE: eval-mode BatchNorm (running statistics: mean, scale = gamma / sqrt(var + eps), beta)
+ * + LeakyReLU applied in the epilogue, so `out` is the block's activation and no normalisation pass follows.
+ * replaces: aten::convolution + aten::native_batch_norm (eval) + aten::leaky_relu of one block (models.py:45-47,66-70)
+ * under model.eval() / torch.no_grad() (models.py:250-263, evaluation.py:42-65) */
+extern "C" int vae_conv_umma_rw_act(const void* in, const void* wpk, const float* bias, void* out, const float* mean,
+                                    const float* scale, const float* beta, float slope, int B, int Hi, int Wi, int Ci,
+                                    int Co, int stride, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(mean && scale && beta, "conv_umma_rw_act: bad argument");
+  const float* act[3] = {mean, scale, beta};
+  return rw_dispatch(in, wpk, bias, out, nullptr, B, Hi, Wi, Ci, Co, stride, mode, stream, nullptr, nullptr, slope, act);
 }

@@ -43,7 +43,7 @@ bool tmat_channels_ok(int Ci, int Co, int stride, int mode);
 long long tmat_packed_elems(int Ci, int Co);
 int tmat_pack(const float* w_oihw, void* out, int Ci, int Co, cudaStream_t st);
 int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi, int Ci,
-                int Co, cudaStream_t st, const void* bn_y, const float* const* bn_vec, float slope);
+                int Co, cudaStream_t st, const void* bn_y, const float* const* bn_vec, float slope, const float* const* act);
 
 struct TmaConvParams {
   CUtensorMap tmap;
@@ -71,6 +71,7 @@ struct TmaConvParams {
   const bf16* bn_y;
   const float *bn_mean, *bn_scale, *bn_beta, *bn_rstd;   // [N] each (scale = gamma * rstd)
   float slope;
+  const float *act_mean, *act_scale, *act_beta;   // inference epilogue: eval-mode BatchNorm + LeakyReLU (see conv_umma_rw.cu)
   long long* trace;  // optional [6][512] clock64 samples of CTA 0 (tuning aid)
 };
 
@@ -139,6 +140,8 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   for (int i = threadIdx.x; i < 256; i += kTThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
   if constexpr (BNB)
     for (int i = threadIdx.x; i < N; i += kTThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
+  else if (P.act_scale != nullptr)
+    for (int i = threadIdx.x; i < N; i += kTThreads) s_bn[i] = make_float4(P.act_mean[i], P.act_scale[i], P.act_beta[i], 0.0f);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kTStagesMax; ++s) {
@@ -279,6 +282,7 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const int eset = (warp - 2) >> 2;  // warps 2-5 serve accumulator 0 (even tiles), 6-9 accumulator 1
     const int r = ew * 32 + lane;
     const bool has_bias = P.bias != nullptr;
+    const bool has_act = !BNB && P.act_scale != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
     constexpr int RUN = BNB ? 1 : 32;   // BNB: the y prefetch needs the registers of the running sums
     float run1[RUN], run2[RUN];
@@ -336,6 +340,14 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
             v[i + 1] += b4.y;
             v[i + 2] += b4.z;
             v[i + 3] += b4.w;
+          }
+        }
+        if (has_act) {   // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 16));   // mean, scale, beta
+            const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+            v[i] = u > 0.0f ? u : u * P.slope;
           }
         }
         if (!valid || ncol < 32) {   // rows past the end of the tensor / columns past N: keep them out of the statistics
@@ -556,12 +568,12 @@ extern "C" int vae_umma_tma_pack_weight(const float* w_oihw, void* out, int Ci, 
  * wpk from vae_umma_tma_pack_weight. */
 static int tma_dispatch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi,
                         int Ci, int Co, int stride, int mode, vae_stream_t stream, const void* bn_y, const float* const* bn_vec,
-                        float slope) {
+                        float slope, const float* const* act = nullptr) {
   VAE_REQUIRE(in && wpk && out && B > 0 && (stride == 1 || stride == 2) && Hi % stride == 0 && Wi % stride == 0 &&
                   (mode == 0 || mode == 1),
               "conv_umma_tma: bad argument");
   if (tmat_channels_ok(Ci, Co, stride, mode)) {   // transposed conv, 64 / 128 output channels: the four phases fused
-    const int rc = tmat_launch(in, wpk, bias, out, stats, B, Hi, Wi, Ci, Co, as_stream(stream), bn_y, bn_vec, slope);
+    const int rc = tmat_launch(in, wpk, bias, out, stats, B, Hi, Wi, Ci, Co, as_stream(stream), bn_y, bn_vec, slope, act);
     VAE_REQUIRE(rc != 1, "conv_umma_tma: shape not served by the fused transposed-conv kernel");
     return rc;
   }
@@ -589,7 +601,7 @@ static int tma_dispatch(const void* in, const void* wpk, const float* bias, void
   P.ldo = n_total;
   P.trace = umma_trace_ptr();
   size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64 +
-                (bn_y != nullptr ? 256 * 16 : 0);
+                ((bn_y != nullptr || act != nullptr) ? 256 * 16 : 0);
   auto kern = bn_y != nullptr ? umma_tma_conv_kernel<true> : umma_tma_conv_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[bn_y != nullptr]) {
@@ -606,6 +618,9 @@ static int tma_dispatch(const void* in, const void* wpk, const float* bias, void
     P.out = (bf16*)out + s * g.Nout;
     P.stats = stats ? stats + s * g.Nout : nullptr;
     P.stats2 = stats ? stats + n_total + s * g.Nout : nullptr;
+    if (act != nullptr) {
+      P.act_mean = act[0] + s * g.Nout; P.act_scale = act[1] + s * g.Nout; P.act_beta = act[2] + s * g.Nout;
+    }
     if (bn_y != nullptr) {
       P.bn_y = (const bf16*)bn_y + s * g.Nout;
       P.bn_mean = bn_vec[0] + s * g.Nout; P.bn_scale = bn_vec[1] + s * g.Nout;
@@ -633,4 +648,15 @@ extern "C" int vae_conv_umma_tma_bnbwd(const void* in, const void* wpk, void* ou
   VAE_REQUIRE(y && mean && scale && beta && rstd && dstats, "conv_umma_tma_bnbwd: bad argument");
   const float* vec[4] = {mean, scale, beta, rstd};
   return tma_dispatch(in, wpk, nullptr, out, dstats, B, Hi, Wi, Ci, Co, stride, mode, stream, y, vec, slope);
+}
+
+/* vae_conv_umma_tma for INFERENCE: eval-mode BatchNorm + LeakyReLU in the epilogue (same contract as
+ * vae_conv_umma_rw_act).
+ * replaces: aten::convolution + aten::native_batch_norm (eval) + aten::leaky_relu of one block under model.eval() */
+extern "C" int vae_conv_umma_tma_act(const void* in, const void* wpk, const float* bias, void* out, const float* mean,
+                                     const float* scale, const float* beta, float slope, int B, int Hi, int Wi, int Ci,
+                                     int Co, int stride, int mode, vae_stream_t stream) {
+  VAE_REQUIRE(mean && scale && beta, "conv_umma_tma_act: bad argument");
+  const float* act[3] = {mean, scale, beta};
+  return tma_dispatch(in, wpk, bias, out, nullptr, B, Hi, Wi, Ci, Co, stride, mode, stream, nullptr, nullptr, slope, act);
 }

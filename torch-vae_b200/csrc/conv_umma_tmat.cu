@@ -46,6 +46,7 @@ struct TmatParams {
   const bf16* bn_y;      // fused BatchNorm-backward prologue of the next hop (see conv_umma_rw.cu), or null
   const float *bn_mean, *bn_scale, *bn_beta, *bn_rstd;
   float slope;
+  const float *act_mean, *act_scale, *act_beta;   // inference epilogue: eval-mode BatchNorm + LeakyReLU (see conv_umma_rw.cu)
 };
 
 // images of box (dh, dw): phases (ph, pw) with ph >= dh, pw >= dw, ph-major
@@ -96,6 +97,8 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
   for (int i = threadIdx.x; i < 128; i += kMtThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
   if constexpr (BNB)
     for (int i = threadIdx.x; i < N; i += kMtThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
+  else if (P.act_scale != nullptr)
+    for (int i = threadIdx.x; i < N; i += kMtThreads) s_bn[i] = make_float4(P.act_mean[i], P.act_scale[i], P.act_beta[i], 0.0f);
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kMtStagesMax; ++s) {
@@ -197,6 +200,7 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
     const int eset = (warp - 2) >> 2;  // double-buffered: set = accumulator set (tile parity); else: set = output-row parity
     const int r = ew * 32 + lane;
     const bool has_bias = P.bias != nullptr;
+    const bool has_act = !BNB && P.act_scale != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
     const int it0 = dbl ? eset : 0, it_step = dbl ? 2 : 1;
     const int php0 = dbl ? 0 : eset, php1 = dbl ? 2 : eset + 1;
@@ -237,6 +241,14 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + i]);
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
+            if (has_act) {   // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((c0 + i) * 16));   // mean, scale, beta
+                const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+                v[i] = u > 0.0f ? u : u * P.slope;
               }
             }
             if (!valid) {
@@ -323,7 +335,7 @@ int tmat_pack(const float* w_oihw, void* out, int Ci, int Co, cudaStream_t st) {
 
 // returns 1 if the geometry is not served (whole-row tiles), 0 / negative otherwise.  in: [B, Hi/2, Wi/2, Co] -> out [B, Hi, Wi, Ci]
 int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, double* stats, int B, int Hi, int Wi, int Ci,
-                int Co, cudaStream_t st, const void* bn_y, const float* const* bn_vec, float slope) {
+                int Co, cudaStream_t st, const void* bn_y, const float* const* bn_vec, float slope, const float* const* act) {
   GatherGeom g = geom_dgrad(B, Hi, Wi, Ci, Co, 2);
   int rw, rh, rn;
   if (!tile_rows(g, &rw, &rh, &rn) || rw > 256 || rh > 256 || rn > 256) return 1;
@@ -355,6 +367,7 @@ int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, d
   P.stats = stats; P.stats2 = stats ? stats + N : nullptr;
   P.bn_y = (const bf16*)bn_y; P.slope = slope;
   if (bn_y != nullptr) { P.bn_mean = bn_vec[0]; P.bn_scale = bn_vec[1]; P.bn_beta = bn_vec[2]; P.bn_rstd = bn_vec[3]; }
+  if (act != nullptr) { P.act_mean = act[0]; P.act_scale = act[1]; P.act_beta = act[2]; }
   if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st) != cudaSuccess) {
     set_error("conv_umma_tmat: memset");
     return VAE_ERR_CUDA;

@@ -75,6 +75,19 @@ def _bn_forward(y, stats, gamma, beta, bn, training: bool):
 # persistent conv kernels are issue / latency bound), so the step does not use it.
 FUSE_BN_BACKWARD = False
 
+# Inference (model.eval() and nothing requires a gradient: sample(), evaluate()): eval-mode BatchNorm + LeakyReLU are
+# applied in the epilogue of the conv that produces the block (vae_conv_umma_{rw,tma}_act), so ConvTranspose2d + BN +
+# LeakyReLU is ONE pass and the pre-normalisation tensor is never written.
+INFERENCE_EPILOGUE = True
+
+
+def inference_mode(module_training: bool, *tensors) -> bool:
+    """True when the call is a pure inference: eval mode and autograd will record nothing (no_grad, or no input /
+    parameter requires a gradient).  Evaluated by the caller -- inside Function.forward grad mode is always off."""
+    if module_training:
+        return False
+    return not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors))
+
 
 def _bnbwd(saved_prev, beta_prev):
     return (saved_prev[1], saved_prev[2], beta_prev) if FUSE_BN_BACKWARD else None
@@ -112,9 +125,10 @@ class EncodeFn(torch.autograd.Function):
     """encoder convs -> flatten -> fc_mu / fc_var  (models.py:107-145)."""
 
     @staticmethod
-    def forward(ctx, specs: List[ConvBlockSpec], dtype, training, sink, cws, x, w_mu, b_mu, w_var, b_var, *conv_params):
+    def forward(ctx, specs: List[ConvBlockSpec], dtype, training, infer, sink, cws, x, w_mu, b_mu, w_var, b_var, *conv_params):
         ctx.set_materialize_grads(False)
         ctx.sink = sink
+        infer = bool(infer) and INFERENCE_EPILOGUE and not training   # eval mode and no backward will follow (see inference_mode)
         B, Cin = x.shape[0], x.shape[1]
         h = x.contiguous()
         if h.dtype != torch.float32:
@@ -126,6 +140,12 @@ class EncodeFn(torch.autograd.Function):
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
             cw = cws[i] if cws is not None else ops.ConvWeights(w, dtype, 2)
+            if infer and sp.bn.running_mean is not None and h.dtype == torch.bfloat16:
+                # eval-mode BatchNorm + LeakyReLU ride in the conv's epilogue: the block writes its activation
+                vec = _bn_vectors(h, None, gamma, beta, sp.bn, False)
+                h = ops.conv_forward(h, cw, b, None, Ci=sp.ci, act=(vec, beta))
+                Hi, Wi = Hi // 2, Wi // 2
+                continue
             stats = torch.empty(2 * sp.co, dtype=torch.float64, device=h.device) if training else None
             y = ops.conv_forward(h, cw, b, stats, Ci=sp.ci)
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
@@ -206,8 +226,8 @@ class EncodeFn(torch.autograd.Function):
         if sink is not None:
             # the sink owns the parameter gradients (it exposes them as p.grad after the all-reduce); handing
             # them to autograd as well would let AccumulateGrad add into a bucket that is being reduced
-            return (None, None, None, None, None, dx, None, None, None, None, *([None] * len(conv_grads)))
-        return (None, None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
+            return (None, None, None, None, None, None, dx, None, None, None, None, *([None] * len(conv_grads)))
+        return (None, None, None, None, None, None, dx, g_w_mu, g_b_mu, g_w_var, g_b_var, *conv_grads)
 
 
 class ReparamFn(torch.autograd.Function):
@@ -238,9 +258,10 @@ class DecodeFn(torch.autograd.Function):
     (models.py:147-175).  Returns (probabilities fp32, logits in compute dtype)."""
 
     @staticmethod
-    def forward(ctx, specs: List[ConvBlockSpec], feat, dtype, training, sink, cws, z, w_in, b_in, w_last, b_last, *conv_params):
+    def forward(ctx, specs: List[ConvBlockSpec], feat, dtype, training, infer, sink, cws, z, w_in, b_in, w_last, b_last, *conv_params):
         ctx.set_materialize_grads(False)
         ctx.sink = sink
+        infer = bool(infer) and INFERENCE_EPILOGUE and not training   # eval mode and no backward will follow (see inference_mode)
         z = z.contiguous()
         if z.dtype != torch.float32:
             z = z.float()
@@ -257,6 +278,11 @@ class DecodeFn(torch.autograd.Function):
         for i, sp in enumerate(specs):
             w, b, gamma, beta = conv_params[4 * i : 4 * i + 4]
             cw = cws[i] if cws is not None else ops.ConvWeights(w, dtype, 2)
+            last_fused = i == len(specs) - 1 and ops.final_block_supported(B, h.shape[1] * 2, h.shape[2] * 2, sp.ci)
+            if infer and not last_fused and sp.bn.running_mean is not None and h.dtype == torch.bfloat16:
+                vec = _bn_vectors(h, None, gamma, beta, sp.bn, False)
+                h = ops.conv_data_grad(h, cw, b, None, act=(vec, beta))  # ConvTranspose2d + eval BatchNorm + LeakyReLU, one pass
+                continue
             stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
             y = ops.conv_data_grad(h, cw, b, stats)  # ConvTranspose2d forward
             if i == len(specs) - 1 and ops.final_block_supported(B, y.shape[1], y.shape[2], sp.ci):
@@ -375,8 +401,8 @@ class DecodeFn(torch.autograd.Function):
         ctx.saved = None
         ctx.last = None
         if sink is not None:  # see EncodeFn.backward: the sink owns the parameter gradients
-            return (None, None, None, None, None, None, dz, None, None, None, None, *([None] * len(conv_grads)))
-        return (None, None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
+            return (None, None, None, None, None, None, None, dz, None, None, None, None, *([None] * len(conv_grads)))
+        return (None, None, None, None, None, None, None, dz, g_w_in, g_b_in, g_w_last, g_b_last, *conv_grads)
 
 
 class ElboFn(torch.autograd.Function):

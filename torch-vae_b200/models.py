@@ -191,10 +191,12 @@ class VanillaVAE(nn.Module):
 
     def encode(self, x: Tensor, _cws=None) -> EncoderOutput:
         self._check_input(x)
+        params = self._block_params(self.encoder)
+        infer = engine.inference_mode(self.training, x, *self.fc_mu.parameters(), *self.fc_var.parameters(), *params)
         mu, log_var, pre = engine.EncodeFn.apply(
-            self._enc_specs(), self.compute_dtype, self.training, self._grad_sink, _cws, x,
+            self._enc_specs(), self.compute_dtype, self.training, infer, self._grad_sink, _cws, x,
             self.fc_mu.weight, self.fc_mu.bias, self.fc_var.weight, self.fc_var.bias,
-            *self._block_params(self.encoder),
+            *params,
         )
         return EncoderOutput(mu=mu, log_var=log_var, pre_latents=pre)
 
@@ -205,10 +207,12 @@ class VanillaVAE(nn.Module):
             raise RuntimeError(f"expected latents [B, {self.latent_dim}], got {tuple(z.shape)}")
         blocks = list(self.decoder) + [self.final_layer]
         last = self.final_layer[3]
+        params = self._block_params(blocks)
+        infer = engine.inference_mode(self.training, z, *self.decoder_input.parameters(), *last.parameters(), *params)
         return engine.DecodeFn.apply(
-            self._dec_specs(), self._feat, self.compute_dtype, self.training, self._grad_sink, _cws, z,
+            self._dec_specs(), self._feat, self.compute_dtype, self.training, infer, self._grad_sink, _cws, z,
             self.decoder_input.weight, self.decoder_input.bias, last.weight, last.bias,
-            *self._block_params(blocks),
+            *params,
         )
 
     def decode(self, z: Tensor) -> Tensor:

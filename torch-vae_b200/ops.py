@@ -772,6 +772,25 @@ def conv_umma_rw(inp, wpk, bias, stats, Ci: int, Co: int, stride: int, mode: int
     return out
 
 
+def conv_umma_act(kind: str, inp, wpk, bias, vec, beta, Ci: int, Co: int, stride: int, mode: int, slope: float = LRELU_SLOPE):
+    """conv_umma_rw / conv_umma_tma with eval-mode BatchNorm + LeakyReLU in the epilogue (inference only): returns the
+    block's ACTIVATION.  ``vec`` = the layer's (scale, shift, mean, rstd) rows from the running statistics."""
+    if inp.dtype != torch.bfloat16:
+        raise RuntimeError("conv_umma_act: bf16 activations only")
+    B = inp.shape[0]
+    if mode == 0:
+        Hi, Wi = inp.shape[1], inp.shape[2]
+        out = torch.empty((B, Hi // stride, Wi // stride, Co), dtype=torch.bfloat16, device=inp.device)
+    else:
+        Hi, Wi = inp.shape[1] * stride, inp.shape[2] * stride
+        out = torch.empty((B, Hi, Wi, Ci), dtype=torch.bfloat16, device=inp.device)
+    fn = _L().vae_conv_umma_rw_act if kind == "rw" else _L().vae_conv_umma_tma_act
+    rc = fn(_p(inp), _p(wpk), _f32(bias, "bias"), _p(out), vec[2].data_ptr(), vec[0].data_ptr(), _f32(beta, "bn bias"), slope,
+            B, Hi, Wi, Ci, Co, stride, mode, _stream())
+    _lib.check(rc, f"vae_conv_umma_{kind}_act")
+    return out
+
+
 def conv_umma_bnbwd(kind: str, inp, wpk, y, vec, beta, Ci: int, Co: int, stride: int, mode: int, slope: float = LRELU_SLOPE):
     """conv_umma_rw / conv_umma_tma producing the gradient w.r.t. act = lrelu(bn(y)) with LeakyReLU' and the two
     BatchNorm-backward reductions fused into the epilogue -> (du, dstats[2C] fp64).  ``vec`` = the layer's
@@ -906,12 +925,20 @@ class PackBatch:
             self._event = None
 
 
-def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None, bnbwd=None):
+def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None, pro=None, bnbwd=None, act=None):
     """Conv2d(k3, stride, p1) forward: tcgen05 kernel when the layer qualifies.
 
     ``bnbwd`` = (y, vec, beta) of the BatchNorm block whose activation gradient this call produces (the conv runs
     as the backward of a ConvTranspose2d): when a tcgen05 kernel serves the layer the result is (du, dstats) with
     LeakyReLU' and the BatchNorm-backward reductions fused into the epilogue, else (d_act, None)."""
+    if act is not None:   # inference: (vec, beta) of the block's eval-mode BatchNorm -> the result is the ACTIVATION
+        vec_, beta_ = act
+        if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == cw.Ci and pro is None and umma_available():
+            if umma_rw_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+                return conv_umma_act("rw", x, cw.rw(0), bias, vec_, beta_, cw.Ci, cw.Co, cw.stride, 0)
+            if umma_tma_eligible(x.shape[0], x.shape[1], x.shape[2], cw.Ci, cw.Co, cw.stride, 0):
+                return conv_umma_act("tma", x, cw.umma(0, tma=True), bias, vec_, beta_, cw.Ci, cw.Co, cw.stride, 0)
+        return bn_apply_lrelu(conv_forward(x, cw, bias, None, Ci, pro), vec_, beta_)
     if bnbwd is not None:
         y_, vec_, beta_ = bnbwd
         if x.dtype == torch.bfloat16 and pro is None and bias is None and umma_available() and y_.dtype == torch.bfloat16:
@@ -933,9 +960,18 @@ def conv_forward(x, cw: ConvWeights, bias, stats=None, Ci: Optional[int] = None,
     return conv_fprop(x, cw.simt()[0], bias, cw.stride, cw.dtype, stats, Ci=Ci if Ci is not None else cw.Ci)
 
 
-def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None, bnbwd=None):
+def conv_data_grad(dy, cw: ConvWeights, bias=None, stats=None, pro=None, bnbwd=None, act=None):
     """Data gradient of that conv == ConvTranspose2d(k3, stride, p1, op=stride-1) forward.
     ``bnbwd``: see conv_forward."""
+    if act is not None:   # inference: see conv_forward
+        vec_, beta_ = act
+        s_ = cw.stride
+        if dy.dtype == torch.bfloat16 and pro is None and umma_available():
+            if umma_rw_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+                return conv_umma_act("rw", dy, cw.rw(1), bias, vec_, beta_, cw.Ci, cw.Co, s_, 1)
+            if umma_tma_eligible(dy.shape[0], dy.shape[1] * s_, dy.shape[2] * s_, cw.Ci, cw.Co, s_, 1):
+                return conv_umma_act("tma", dy, cw.umma(1, tma=True), bias, vec_, beta_, cw.Ci, cw.Co, s_, 1)
+        return bn_apply_lrelu(conv_data_grad(dy, cw, bias, None, pro), vec_, beta_)
     if bnbwd is not None:
         y_, vec_, beta_ = bnbwd
         s_ = cw.stride
