@@ -15,6 +15,8 @@
 //   warp 1     MMA issuer: stage (chunk c, box (dh,dw)) -> for every phase (ph >= dh, pw >= dw): 4 x tcgen05.mma (K = 64)
 //   warps 2-9  epilogue: two sets of four warps.  8N <= 512 TMEM columns (N = 64): accumulator sets double-buffered,
 //              a set takes every other tile; else (N = 128) one accumulator set, the two epilogue sets split its output rows.
+//              (Both sets on every tile, splitting the channel chunks, measured slower: 463 vs 415 us at the wide shape.)
+//              Output rows leave through a swizzled shared-memory slab: one store instruction = 8 rows x 64 contiguous B.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -88,6 +90,7 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
   float* s_stats = reinterpret_cast<float*>(tmem_ptr + 4);   // [2][128]
   float* s_bias = s_stats + 256;                             // [128]
   float4* s_bn = reinterpret_cast<float4*>(s_bias + 128);    // [128] {mean, scale, beta, rstd} (BNB only)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bn + 128); // [8 epilogue warps][32 rows][64 B], 16-byte pieces XOR-swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = P.N, kStages = P.stages, chunks = P.chunks;
@@ -219,6 +222,91 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 4 * N);
+      if constexpr (!BNB) {
+        // Channel chunk outermost: the statistics of a chunk accumulate over its four phases in registers (one transpose
+        // pair per chunk, not per phase), and every 32 x 64 B piece goes through a swizzled shared-memory slab so that a
+        // store instruction writes 8 rows x 64 contiguous bytes (whole sectors) instead of 32 rows x 16 bytes.
+        const uint32_t stg = smem_u32(s_stage) + (uint32_t)(warp - 2) * 2048u;
+        const uint32_t st_w = stg + (uint32_t)lane * 64u, wx = ((uint32_t)lane >> 1) & 3u;
+        const uint32_t st_r = stg + ((uint32_t)lane >> 2) * 64u + ((((uint32_t)lane & 3u) ^ (((uint32_t)lane >> 3) & 3u)) << 4);
+        bf16* drow[4];   // output base of rows (lane / 4) + 8k: the rows this lane stores
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          drow[k] = reinterpret_cast<bf16*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst0), (lane >> 2) + 8 * k));
+        // One flat loop over (channel chunk, phase): the TMEM load of the NEXT piece is issued as soon as this one is packed
+        // to bf16, so it flies under the shared-memory round trip and the stores.
+        const int pcs = dbl ? 2 : 1, per_c = 1 << pcs;   // pieces per channel chunk: 4 phases, or this set's 2
+        const int n_it = (N >> 5) << pcs;
+        const uint32_t s_bias_a = smem_u32(s_bias);
+        float v[32], s1[32], s2[32];
+        tmem_ld_32x32(t_row + (uint32_t)(php0 * 2 * N), v);
+        for (int idx = 0; idx < n_it; ++idx) {
+          const int c0 = (idx >> pcs) << 5, rem = idx & (per_c - 1);
+          const int php = php0 + (rem >> 1), pwp = rem & 1;
+          if (rem == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.0f;
+          }
+          tmem_ld_wait_regs(v);
+          if (idx == n_it - 1) {   // last read of this set's accumulators
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = lds_f4_ro(s_bias_a + (uint32_t)((c0 + i) * 4));
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+          }
+          if (has_act) {   // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 c4 = lds_f4_ro(s_bn_a + (uint32_t)((c0 + i) * 16));   // mean, scale, beta
+              const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+              v[i] = u > 0.0f ? u : u * P.slope;
+            }
+          }
+          if (P.stats != nullptr && valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s1[i] += v[i];
+              s2[i] = fmaf(v[i], v[i], s2[i]);
+            }
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          if (idx + 1 < n_it) {
+            const int c0n = ((idx + 1) >> pcs) << 5, remn = (idx + 1) & (per_c - 1);
+            tmem_ld_32x32(t_row + (uint32_t)(((php0 + (remn >> 1)) * 2 + (remn & 1)) * N + c0n), v);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(st_w + (((uint32_t)q ^ wx) << 4)), "r"(w[4 * q]),
+                         "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
+          __syncwarp();
+          const long long off = ((long long)php * P.Wout + pwp) * P.ldo + c0 + (lane & 3) * 8;
+          uint4 pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[k].x), "=r"(pk[k].y), "=r"(pk[k].z), "=r"(pk[k].w) : "r"(st_r + (uint32_t)k * 512u));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (drow[k] != nullptr) *reinterpret_cast<uint4*>(drow[k] + off) = pk[k];
+          __syncwarp();
+          if (rem == per_c - 1 && P.stats != nullptr) {
+            warp_transpose_reduce32(s1, lane);
+            warp_transpose_reduce32(s2, lane);
+            atomicAdd(&s_stats[c0 + lane], s1[0]);
+            atomicAdd(&s_stats[128 + c0 + lane], s2[0]);
+          }
+        }
+        continue;
+      }
       for (int php = php0; php < php1; ++php) {
         for (int pwp = 0; pwp < 2; ++pwp) {
           bf16* dst = dst0 != nullptr ? dst0 + ((long long)php * P.Wout + pwp) * P.ldo : nullptr;
@@ -359,7 +447,7 @@ int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, d
   P.total_tiles = (int)((M + 127) / 128);
   P.img_bytes = N * 64 * 2;
   P.slot_bytes = 16384 + 4 * P.img_bytes;
-  P.stages = (218 * 1024) / P.slot_bytes;
+  P.stages = (202 * 1024) / P.slot_bytes;   // 16 KB of the budget is the epilogue's store slab
   if (P.stages > kMtStagesMax) P.stages = kMtStagesMax;
   if (P.stages < 2) return 1;
   P.double_buf = 8 * N <= 512 ? 1 : 0;
@@ -372,7 +460,7 @@ int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, d
     set_error("conv_umma_tmat: memset");
     return VAE_ERR_CUDA;
   }
-  const size_t smem = 1024 + (size_t)P.stages * P.slot_bytes + 8 * (2 * kMtStagesMax + 4) + 16 + (256 + 128) * 4 + 128 * 16 + 64;
+  const size_t smem = 1024 + (size_t)P.stages * P.slot_bytes + 8 * (2 * kMtStagesMax + 4) + 16 + (256 + 128) * 4 + 128 * 16 + 8 * 2048 + 64;
   auto kern = bn_y != nullptr ? umma_tmat_conv_kernel<true> : umma_tmat_conv_kernel<false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[bn_y != nullptr]) {

@@ -33,6 +33,13 @@ __device__ __forceinline__ float4 lds_f4_addr(uint32_t a) {   // LDS.128 by 32-b
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+// the same for data that never changes after the kernel's set-up barrier (bias, BatchNorm vectors): not volatile, so the
+// compiler may hoist it above waits
+__device__ __forceinline__ float4 lds_f4_ro(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // shared-memory matrix descriptor with a selectable swizzle (2 = 128B, 4 = 64B)
