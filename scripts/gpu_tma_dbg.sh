@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+TAG=${1:-r03y}
+for d in 0 8; do
+  VAE_TMA_DBG=$d timeout 300 python bench.py --workload wide_long --steps 5 --warmup 3 --no-cpu-baseline --no-eager-baseline --profile-json gpurun_out/${TAG}_dbg${d}_wide.json > /dev/null 2> gpurun_out/${TAG}_dbg${d}_wide.err
+  VAE_TMA_DBG=$d timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eager-baseline --profile-json gpurun_out/${TAG}_dbg${d}_train.json > /dev/null 2> gpurun_out/${TAG}_dbg${d}_train.err
+done
+ls gpurun_out/${TAG}_*

@@ -114,7 +114,9 @@ __global__ void pack_tma_weight_kernel(const float* __restrict__ w, bf16* __rest
       P.trace[(role) * 512 + (idx)] = clock64();                                          \
   } while (0)
 
-template <bool BNB>
+// EPI (plain epilogue, !BNB): 0 = nothing added (data gradients), 1 = bias + per-chunk BatchNorm statistics, 2 = bias +
+// eval-mode BatchNorm + LeakyReLU (inference), 3 = bias + statistics kept in registers for the whole kernel (N <= 32).
+template <bool BNB, int EPI>
 __global__ void __launch_bounds__(kTThreads, 1)
 umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -140,8 +142,9 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   for (int i = threadIdx.x; i < 256; i += kTThreads) s_bias[i] = (P.bias != nullptr && i < N) ? P.bias[i] : 0.0f;
   if constexpr (BNB)
     for (int i = threadIdx.x; i < N; i += kTThreads) s_bn[i] = make_float4(P.bn_mean[i], P.bn_scale[i], P.bn_beta[i], P.bn_rstd[i]);
-  else if (P.act_scale != nullptr)
-    for (int i = threadIdx.x; i < N; i += kTThreads) s_bn[i] = make_float4(P.act_mean[i], P.act_scale[i], P.act_beta[i], 0.0f);
+  else if (EPI == 2)   // inference: u = y * scale + shift, two channels per float4
+    for (int i = threadIdx.x; i < N; i += kTThreads)
+      reinterpret_cast<float2*>(s_bn)[i] = make_float2(P.act_scale[i], fmaf(-P.act_mean[i], P.act_scale[i], P.act_beta[i]));
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kTStagesMax; ++s) {
@@ -282,9 +285,8 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
     const int eset = (warp - 2) >> 2;  // warps 2-5 serve accumulator 0 (even tiles), 6-9 accumulator 1
     const int r = ew * 32 + lane;
     const bool has_bias = P.bias != nullptr;
-    const bool has_act = !BNB && P.act_scale != nullptr;
     const uint32_t s_bn_a = smem_u32(s_bn);
-    constexpr int RUN = BNB ? 1 : 32;   // BNB: the y prefetch needs the registers of the running sums
+    constexpr int RUN = (!BNB && EPI == 3) ? 32 : 1;   // sums kept for the whole kernel: only when one chunk covers N
     float run1[RUN], run2[RUN];
 #pragma unroll
     for (int i = 0; i < RUN; ++i) run1[i] = run2[i] = 0.0f;
@@ -316,102 +318,178 @@ umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
       if (ew == 0) VAE_TTRACE(4, it);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        if constexpr (BNB) {
-          if (c0 + 32 < N) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ynext[q] = ldg_nc_v4_pinned(reinterpret_cast<const uint4*>(ysrc + c0 + 32) + q);
-          }
-        }
-        float v[32];
-        tmem_ld_32x32(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
-          if (ew == 0) VAE_TTRACE(5, it);
-        }
-        const int ncol = min(32, N - c0);
-        if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
-            v[i] += b4.x;
-            v[i + 1] += b4.y;
-            v[i + 2] += b4.z;
-            v[i + 3] += b4.w;
-          }
-        }
-        if (has_act) {   // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 16));   // mean, scale, beta
-            const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
-            v[i] = u > 0.0f ? u : u * P.slope;
-          }
-        }
-        if (!valid || ncol < 32) {   // rows past the end of the tensor / columns past N: keep them out of the statistics
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!valid || i >= ncol) v[i] = 0.0f;
-        }
-        float second[32];   // second statistic: y^2 (forward) or du * xhat (fused BN backward)
-        if constexpr (BNB) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w4[4] = {ycur[q].x, ycur[q].y, ycur[q].z, ycur[q].w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int i = q * 8 + k;
-              const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
-              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 16));   // mean, scale, beta, rstd
-              const float t = yv - c4.x;
-              const float u = fmaf(t, c4.y, c4.z);           // same expression as the forward apply (bn_affine)
-              const float du = u > 0.0f ? v[i] : v[i] * P.slope;
-              v[i] = du;
-              second[i] = du * (t * c4.w);
+      if constexpr (BNB) {
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          if constexpr (BNB) {
+            if (c0 + 32 < N) {
+  #pragma unroll
+              for (int q = 0; q < 4; ++q) ynext[q] = ldg_nc_v4_pinned(reinterpret_cast<const uint4*>(ysrc + c0 + 32) + q);
             }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) ycur[q] = ynext[q];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
-        }
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            if (i < ncol) {
-              uint4 pk;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
-              *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+          float v[32];
+          tmem_ld_32x32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (c0 + 32 >= N) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (ew == 0) VAE_TTRACE(5, it);
+          }
+          const int ncol = min(32, N - c0);
+          if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
+  #pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[(c0 + i) & 255]);
+              v[i] += b4.x;
+              v[i + 1] += b4.y;
+              v[i + 2] += b4.z;
+              v[i + 3] += b4.w;
             }
           }
-        }
-        if (P.stats != nullptr) {
-          if (!BNB && N <= 32) {
-            if constexpr (!BNB) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                run1[i] += v[i];
-                run2[i] += second[i];
+          if (!valid || ncol < 32) {   // rows past the end of the tensor / columns past N: keep them out of the statistics
+  #pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!valid || i >= ncol) v[i] = 0.0f;
+          }
+          float second[32];   // second statistic: y^2 (forward) or du * xhat (fused BN backward)
+          if constexpr (BNB) {
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t w4[4] = {ycur[q].x, ycur[q].y, ycur[q].z, ycur[q].w};
+  #pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int i = q * 8 + k;
+                const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
+                const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 16));   // mean, scale, beta, rstd
+                const float t = yv - c4.x;
+                const float u = fmaf(t, c4.y, c4.z);           // same expression as the forward apply (bn_affine)
+                const float du = u > 0.0f ? v[i] : v[i] * P.slope;
+                v[i] = du;
+                second[i] = du * (t * c4.w);
               }
             }
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) ycur[q] = ynext[q];
           } else {
-            warp_transpose_reduce32(v, lane);
-            warp_transpose_reduce32(second, lane);
-            if (lane < ncol) {
-              atomicAdd(&s_stats[c0 + lane], v[0]);
-              atomicAdd(&s_stats[256 + c0 + lane], second[0]);
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
+          }
+          if (valid) {
+  #pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i < ncol) {
+                uint4 pk;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+  #pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+                *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+              }
+            }
+          }
+          if (P.stats != nullptr) {
+            if (!BNB && N <= 32) {
+              if constexpr (!BNB) {
+  #pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  run1[i] += v[i];
+                  run2[i] += second[i];
+                }
+              }
+            } else {
+              warp_transpose_reduce32(v, lane);
+              warp_transpose_reduce32(second, lane);
+              if (lane < ncol) {
+                atomicAdd(&s_stats[c0 + lane], v[0]);
+                atomicAdd(&s_stats[256 + c0 + lane], second[0]);
+              }
+            }
+          }
+        }
+      } else {
+        // Plain epilogue, one flat pipeline over the 32-column chunks: bias requested before the TMEM wait, the NEXT
+        // chunk's TMEM load issued as soon as this one is packed, 32-byte stores (whole sectors) from registers.
+        const uint32_t s_bias_a = smem_u32(s_bias);
+        const int n_ch = (N + 31) >> 5;
+        float v[32];
+        tmem_ld_32x32(t_row, v);
+        for (int ch = 0; ch < n_ch; ++ch) {
+          const int c0 = ch << 5;
+          float4 b4[8];
+          if constexpr (EPI != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b4[i] = lds_f4_addr(s_bias_a + (uint32_t)(((c0 + 4 * i) & 255) * 4));
+          }
+          tmem_ld_wait_regs(v);
+          if (ch == n_ch - 1) {   // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (ew == 0) VAE_TTRACE(5, it);
+          }
+          const int ncol = min(32, N - c0);
+          if constexpr (EPI != 0) {   // zeros when the launch has no bias
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
+            }
+          }
+          if constexpr (EPI == 2) {   // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)(((c0 + i) & 255) * 8));   // scale, shift of two channels
+              const float u0 = fmaf(v[i], c4.x, c4.y), u1 = fmaf(v[i + 1], c4.z, c4.w);
+              v[i] = u0 > 0.0f ? u0 : u0 * P.slope;
+              v[i + 1] = u1 > 0.0f ? u1 : u1 * P.slope;
+            }
+          }
+          if (!valid || ncol < 32) {   // rows past the end of the tensor / columns past N: keep them out of the statistics
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!valid || i >= ncol) v[i] = 0.0f;
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          float t1[32], t2[32];
+          if constexpr (EPI == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              t1[i] = v[i];
+              t2[i] = v[i] * v[i];
+            }
+          }
+          if constexpr (EPI == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              run1[i] += v[i];
+              run2[i] = fmaf(v[i], v[i], run2[i]);
+            }
+          }
+          if (ch + 1 < n_ch) tmem_ld_32x32(t_row + (uint32_t)(c0 + 32), v);
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (16 * q < ncol)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0 + 16 * q), "r"(w[8 * q]),
+                             "r"(w[8 * q + 1]), "r"(w[8 * q + 2]), "r"(w[8 * q + 3]), "r"(w[8 * q + 4]), "r"(w[8 * q + 5]),
+                             "r"(w[8 * q + 6]), "r"(w[8 * q + 7]) : "memory");
+          }
+          if constexpr (EPI == 1) {
+            if (P.stats != nullptr) {
+              warp_transpose_reduce32(t1, lane);
+              warp_transpose_reduce32(t2, lane);
+              if (lane < ncol) {
+                atomicAdd(&s_stats[c0 + lane], t1[0]);
+                atomicAdd(&s_stats[256 + c0 + lane], t2[0]);
+              }
             }
           }
         }
       }
     }
-    if constexpr (!BNB) {
-      if (P.stats != nullptr && N <= 32) {
+    if constexpr (!BNB && EPI == 3) {
+      if (P.stats != nullptr) {
         warp_transpose_reduce32(run1, lane);
         warp_transpose_reduce32(run2, lane);
         if (lane < N) {
@@ -602,11 +680,14 @@ static int tma_dispatch(const void* in, const void* wpk, const float* bias, void
   P.trace = umma_trace_ptr();
   size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64 +
                 ((bn_y != nullptr || act != nullptr) ? 256 * 16 : 0);
-  auto kern = bn_y != nullptr ? umma_tma_conv_kernel<true> : umma_tma_conv_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bn_y != nullptr]) {
+  VAE_REQUIRE(!(act != nullptr && (stats != nullptr || bn_y != nullptr)), "conv_umma_tma: the inference epilogue takes no statistics");
+  const int which = bn_y != nullptr ? 4 : act != nullptr ? 2 : (stats == nullptr && bias == nullptr) ? 0 : (stats != nullptr && g.Nout <= 32) ? 3 : 1;
+  auto kern = which == 4 ? umma_tma_conv_kernel<true, 1> : which == 3 ? umma_tma_conv_kernel<false, 3>
+            : which == 2 ? umma_tma_conv_kernel<false, 2> : which == 1 ? umma_tma_conv_kernel<false, 1> : umma_tma_conv_kernel<false, 0>;
+  static bool attr_set[5] = {false, false, false, false, false};
+  if (!attr_set[which]) {
     VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[bn_y != nullptr] = true;
+    attr_set[which] = true;
   }
   P.bn_y = nullptr; P.slope = slope;
   int grid = sm_count();
