@@ -267,120 +267,233 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
           dst = P.out + (((long long)b * P.Hout + 2 * jh) * P.Wout + 2 * jw) * N;
       }
       constexpr int NCHUNK = Cfg::ACC_COLS / 32;
-      // fused BN backward: this thread's y values (same element offsets as the row it writes), requested
-      // BEFORE the wait for the accumulator so that the loads fly while the MMAs of the tile run
-      uint4 yraw[BNB ? NCHUNK : 1][4];
       if constexpr (BNB) {
-        const long long eoff = dst != nullptr ? (long long)(dst - P.out) : 0;
-#pragma unroll
-        for (int ci = 0; ci < NCHUNK; ++ci) {
-          // MODE 0: chunk ci = channels 32ci..; MODE 1: chunk ci = output pixel (2jh + (ci>>1), 2jw + (ci&1)), N = 32
-          const long long o = MODE == 0 ? eoff + ci * 32 : eoff + (long long)(ci >> 1) * P.Wout * N + (ci & 1) * N;
-          const uint4* src = reinterpret_cast<const uint4*>(P.bn_y + o);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) yraw[ci][q] = ldg_nc_v4_pinned(src + q);
-        }
-      }
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
-#pragma unroll
-      for (int ci = 0; ci < NCHUNK; ++ci) {
-        float v[32];
-        tmem_ld_32x32(t_row + (uint32_t)(ci * 32), v);
-        tmem_ld_wait();
-        if (ci == NCHUNK - 1) {  // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
-        }
-        // channel base of this chunk
-        const int cbase = MODE == 0 ? ci * 32 : 0;
-        if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
-            v[i] += b4.x;
-            v[i + 1] += b4.y;
-            v[i + 2] += b4.z;
-            v[i + 3] += b4.w;
-          }
-        }
-        if (has_act) {    // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta
-            const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
-            v[i] = u > 0.0f ? u : u * P.slope;
-          }
-        }
-        if (!valid) {     // rows past the end of the tensor (last tile only): keep them out of the statistics
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-        }
-        float second[32];   // what the second statistic sums: y^2 (forward) or du * xhat (fused BN backward)
+        // fused BN backward: this thread's y values (same element offsets as the row it writes), requested
+        // BEFORE the wait for the accumulator so that the loads fly while the MMAs of the tile run
+        uint4 yraw[BNB ? NCHUNK : 1][4];
         if constexpr (BNB) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t w4[4] = {yraw[ci][q].x, yraw[ci][q].y, yraw[ci][q].z, yraw[ci][q].w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int i = q * 8 + k;
-              const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
-              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta, rstd
-              const float t = yv - c4.x;
-              const float u = fmaf(t, c4.y, c4.z);          // same expression as the forward apply (bn_affine)
-              const float du = u > 0.0f ? v[i] : v[i] * P.slope;
-              v[i] = du;
-              second[i] = du * (t * c4.w);
+          const long long eoff = dst != nullptr ? (long long)(dst - P.out) : 0;
+  #pragma unroll
+          for (int ci = 0; ci < NCHUNK; ++ci) {
+            // MODE 0: chunk ci = channels 32ci..; MODE 1: chunk ci = output pixel (2jh + (ci>>1), 2jw + (ci&1)), N = 32
+            const long long o = MODE == 0 ? eoff + ci * 32 : eoff + (long long)(ci >> 1) * P.Wout * N + (ci & 1) * N;
+            const uint4* src = reinterpret_cast<const uint4*>(P.bn_y + o);
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) yraw[ci][q] = ldg_nc_v4_pinned(src + q);
+          }
+        }
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+  #pragma unroll
+        for (int ci = 0; ci < NCHUNK; ++ci) {
+          float v[32];
+          tmem_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+          tmem_ld_wait();
+          if (ci == NCHUNK - 1) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          // channel base of this chunk
+          const int cbase = MODE == 0 ? ci * 32 : 0;
+          if (has_bias) {   // uniform: the data-gradient launches of the backward pass have no bias
+  #pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + i]);
+              v[i] += b4.x;
+              v[i + 1] += b4.y;
+              v[i + 2] += b4.z;
+              v[i + 3] += b4.w;
             }
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
+          if (has_act) {    // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta
+              const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+              v[i] = u > 0.0f ? u : u * P.slope;
+            }
+          }
+          if (!valid) {     // rows past the end of the tensor (last tile only): keep them out of the statistics
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+          float second[32];   // what the second statistic sums: y^2 (forward) or du * xhat (fused BN backward)
+          if constexpr (BNB) {
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t w4[4] = {yraw[ci][q].x, yraw[ci][q].y, yraw[ci][q].z, yraw[ci][q].w};
+  #pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int i = q * 8 + k;
+                const float yv = __uint_as_float((k & 1) ? (w4[k >> 1] & 0xFFFF0000u) : (w4[k >> 1] << 16));
+                const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta, rstd
+                const float t = yv - c4.x;
+                const float u = fmaf(t, c4.y, c4.z);          // same expression as the forward apply (bn_affine)
+                const float du = u > 0.0f ? v[i] : v[i] * P.slope;
+                v[i] = du;
+                second[i] = du * (t * c4.w);
+              }
+            }
+          } else {
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) second[i] = v[i] * v[i];
+          }
+          {
+            // A thread's accumulator row is ROWB contiguous bytes of the output (MODE 0: its pixel's N channels;
+            // MODE 1: the two column-parity pixels of one output row) and the 32 threads of a warp own 32 such
+            // rows back to back.  Stage them, then let consecutive lanes store consecutive 16-byte pieces.
+            uint8_t* st = s_epi + (warp - 2) * (32 * Cfg::EPI_PITCH);
+            const int cpos = MODE == 1 ? (ci & 1) * 64 : ci * 64;   // byte position of this chunk in the row
+  #pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+              *reinterpret_cast<uint4*>(st + lane * Cfg::EPI_PITCH + cpos + i * 2) = pk;
+            }
+            const bool row_done = MODE == 1 ? (ci & 1) != 0 : ci == NCHUNK - 1;
+            if (row_done) {
+              __syncwarp();
+              const unsigned long long my = reinterpret_cast<unsigned long long>(dst);  // 0 when the row is out of range
+              const long long roff = MODE == 1 ? (long long)(ci >> 1) * P.Wout * N : 0;
+              constexpr int PPR = Cfg::ROWB / 16;   // 16-byte pieces per row
+  #pragma unroll
+              for (int j = 0; j < PPR; ++j) {
+                const int c = lane + 32 * j;
+                const int src = c / PPR, sub = c % PPR;
+                const unsigned long long d = __shfl_sync(0xffffffffu, my, src);
+                const uint4 pk = *reinterpret_cast<const uint4*>(st + src * Cfg::EPI_PITCH + sub * 16);
+                if (d != 0ull) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d) + roff + sub * 8) = pk;
+              }
+              __syncwarp();
+            }
+          }
+          if (P.stats != nullptr) {
+            if constexpr (N <= 32 && !BNB) {   // BNB: the y prefetch needs the registers of the running sums
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                run1[i] += v[i];
+                run2[i] += second[i];
+              }
+            } else {
+              warp_transpose_reduce32(v, lane);
+              warp_transpose_reduce32(second, lane);
+              atomicAdd(&s_stats[cbase + lane], v[0]);
+              atomicAdd(&s_stats[64 + cbase + lane], second[0]);
+            }
+          }
         }
-        {
-          // A thread's accumulator row is ROWB contiguous bytes of the output (MODE 0: its pixel's N channels;
-          // MODE 1: the two column-parity pixels of one output row) and the 32 threads of a warp own 32 such
-          // rows back to back.  Stage them, then let consecutive lanes store consecutive 16-byte pieces.
-          uint8_t* st = s_epi + (warp - 2) * (32 * Cfg::EPI_PITCH);
+      } else {
+        // Plain epilogue.  One pipeline over the 32-column chunks: bias requested before the TMEM wait, the next chunk's
+        // TMEM load issued as soon as this one is packed, the staging slab addressed as shared memory (st.shared /
+        // ld.shared, not generic accesses), the output rows of the lanes this lane stores for fetched once per tile.
+        constexpr int PPR = Cfg::ROWB / 16;   // 16-byte pieces per output row
+        const uint32_t st_a = smem_u32(s_epi) + (uint32_t)((warp - 2) * (32 * Cfg::EPI_PITCH));
+        const uint32_t s_bias_a = smem_u32(s_bias);
+        // this thread's row as a 16-byte index into the output (all ones: out of range); rows (lane + 32 j) / PPR are
+        // the ones this lane stores
+        const uint32_t my16 = valid ? (uint32_t)((reinterpret_cast<const uint8_t*>(dst) - reinterpret_cast<const uint8_t*>(P.out)) >> 4) : 0xFFFFFFFFu;
+        uint32_t d16[PPR];
+#pragma unroll
+        for (int j = 0; j < PPR; ++j) d16[j] = __shfl_sync(0xffffffffu, my16, (lane + 32 * j) / PPR);
+        mbar_wait(&tfull_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::ACC_COLS);
+        float v[32];
+        tmem_ld_32x32(t_row, v);
+#pragma unroll
+        for (int ci = 0; ci < NCHUNK; ++ci) {
+          const int cbase = MODE == 0 ? ci * 32 : 0;   // channel base of this chunk
+          // bias (uniform: the data-gradient launches of the backward pass have none): requested before the wait when
+          // the registers allow it (N > 32: no kernel-long running sums), else right after it
+          constexpr bool kEarlyBias = N > 32;
+          float4 b4[8];
+          if (kEarlyBias && has_bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b4[i] = lds_f4_addr(s_bias_a + (uint32_t)((cbase + 4 * i) * 4));
+          }
+          tmem_ld_wait_regs(v);
+          if (ci == NCHUNK - 1) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (!kEarlyBias) b4[i] = lds_f4_addr(s_bias_a + (uint32_t)((cbase + 4 * i) * 4));
+              v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w;
+            }
+          }
+          if (has_act) {    // inference: eval-mode BatchNorm + LeakyReLU on the accumulator row
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float4 c4 = lds_f4_addr(s_bn_a + (uint32_t)((cbase + i) * 16));   // mean, scale, beta
+              const float u = fmaf(v[i] - c4.x, c4.y, c4.z);
+              v[i] = u > 0.0f ? u : u * P.slope;
+            }
+          }
+          if (!valid) {     // rows past the end of the tensor (last tile only): keep them out of the statistics
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          float t1[N <= 32 ? 1 : 32], t2[N <= 32 ? 1 : 32];
+          if (P.stats != nullptr) {
+            if constexpr (N <= 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                run1[i] += v[i];
+                run2[i] = fmaf(v[i], v[i], run2[i]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                t1[i] = v[i];
+                t2[i] = v[i] * v[i];
+              }
+            }
+          }
+          if (ci + 1 < NCHUNK) tmem_ld_32x32(t_row + (uint32_t)((ci + 1) * 32), v);
           const int cpos = MODE == 1 ? (ci & 1) * 64 : ci * 64;   // byte position of this chunk in the row
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 pk;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
-            *reinterpret_cast<uint4*>(st + lane * Cfg::EPI_PITCH + cpos + i * 2) = pk;
-          }
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(st_a + (uint32_t)(lane * Cfg::EPI_PITCH + cpos + 16 * q)),
+                         "r"(w[4 * q]), "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
           const bool row_done = MODE == 1 ? (ci & 1) != 0 : ci == NCHUNK - 1;
           if (row_done) {
             __syncwarp();
-            const unsigned long long my = reinterpret_cast<unsigned long long>(dst);  // 0 when the row is out of range
-            const long long roff = MODE == 1 ? (long long)(ci >> 1) * P.Wout * N : 0;
-            constexpr int PPR = Cfg::ROWB / 16;   // 16-byte pieces per row
+            const uint32_t roff16 = MODE == 1 ? (uint32_t)(ci >> 1) * (uint32_t)(P.Wout * N * 2 / 16) : 0u;
+            constexpr int G = PPR > 4 ? 4 : PPR;   // pieces in flight at a time (register budget)
 #pragma unroll
-            for (int j = 0; j < PPR; ++j) {
-              const int c = lane + 32 * j;
-              const int src = c / PPR, sub = c % PPR;
-              const unsigned long long d = __shfl_sync(0xffffffffu, my, src);
-              const uint4 pk = *reinterpret_cast<const uint4*>(st + src * Cfg::EPI_PITCH + sub * 16);
-              if (d != 0ull) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(d) + roff + sub * 8) = pk;
+            for (int j0 = 0; j0 < PPR; j0 += G) {
+              uint4 pk[G];
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                const int c = lane + 32 * (j0 + j);
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[j].x), "=r"(pk[j].y), "=r"(pk[j].z), "=r"(pk[j].w)
+                             : "r"(st_a + (uint32_t)((c / PPR) * Cfg::EPI_PITCH + (c % PPR) * 16)));
+              }
+#pragma unroll
+              for (int j = 0; j < G; ++j)
+                if (d16[j0 + j] != 0xFFFFFFFFu)
+                  reinterpret_cast<uint4*>(P.out)[(size_t)d16[j0 + j] + roff16 + (uint32_t)((lane + 32 * (j0 + j)) % PPR)] = pk[j];
             }
             __syncwarp();
           }
-        }
-        if (P.stats != nullptr) {
-          if constexpr (N <= 32 && !BNB) {   // BNB: the y prefetch needs the registers of the running sums
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              run1[i] += v[i];
-              run2[i] += second[i];
+          if constexpr (N > 32) {
+            if (P.stats != nullptr) {
+              warp_transpose_reduce32(t1, lane);
+              warp_transpose_reduce32(t2, lane);
+              atomicAdd(&s_stats[cbase + lane], t1[0]);
+              atomicAdd(&s_stats[64 + cbase + lane], t2[0]);
             }
-          } else {
-            warp_transpose_reduce32(v, lane);
-            warp_transpose_reduce32(second, lane);
-            atomicAdd(&s_stats[cbase + lane], v[0]);
-            atomicAdd(&s_stats[64 + cbase + lane], second[0]);
           }
         }
       }
