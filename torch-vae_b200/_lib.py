@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvae_b200.so")
+# VAE_B200_LIB: another build of the same library (A/B timing of compile-time variants on one GPU box)
+LIB_PATH = os.environ.get("VAE_B200_LIB") or os.path.join(_HERE, "libvae_b200.so")
 
 _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 umma_gather_gemm_kernel(const __grid_constant__ UmmaGatherParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B b_stage_bytes] | barriers | tmem ptr | stats | prologue vectors
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   const int stage_bytes = kABytes + P.b_stage_bytes;
   const int kStages = P.stages;
   uint8_t* tail = smem + kStages * stage_bytes;

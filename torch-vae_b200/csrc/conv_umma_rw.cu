@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kRwThreads, 1)
 umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
   using Cfg = RwCfg<MODE, KC, N>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   const int kStages = P.stages;
   uint8_t* wsm = smem + kStages * Cfg::STAGE;
   uint8_t* tail = wsm + Cfg::WBYTES;
@@ -483,7 +483,7 @@ umma_rw_conv_kernel(const __grid_constant__ RwParams P) {
 #pragma unroll
               for (int j = 0; j < G; ++j)
                 if (d16[j0 + j] != 0xFFFFFFFFu)
-                  reinterpret_cast<uint4*>(P.out)[(size_t)d16[j0 + j] + roff16 + (uint32_t)((lane + 32 * (j0 + j)) % PPR)] = pk[j];
+                  stg_v4(reinterpret_cast<uint4*>(P.out) + ((size_t)d16[j0 + j] + roff16 + (uint32_t)((lane + 32 * (j0 + j)) % PPR)), pk[j]);
             }
             __syncwarp();
           }

@@ -120,7 +120,7 @@ template <bool BNB, int EPI>
 __global__ void __launch_bounds__(kTThreads, 1)
 umma_tma_conv_kernel(const __grid_constant__ TmaConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   const int stage_bytes = P.a_stage_bytes + P.b_stage_bytes;
   uint8_t* tail = smem + P.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);

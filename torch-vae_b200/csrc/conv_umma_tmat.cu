@@ -83,7 +83,7 @@ template <bool BNB, int EPI>
 __global__ void __launch_bounds__(kMtThreads, 1)
 umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* tail = smem + P.stages * P.slot_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMtStagesMax;
@@ -241,10 +241,11 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
         const uint32_t stg = smem_u32(s_stage) + (uint32_t)(warp - 2) * 2048u;
         const uint32_t st_w = stg + (uint32_t)lane * 64u, wx = ((uint32_t)lane >> 1) & 3u;
         const uint32_t st_r = stg + ((uint32_t)lane >> 2) * 64u + ((((uint32_t)lane & 3u) ^ (((uint32_t)lane >> 3) & 3u)) << 4);
-        bf16* drow[4];   // output base of rows (lane / 4) + 8k: the rows this lane stores
+        // output rows (lane / 4) + 8k are the ones this lane stores: their bases as 16-byte indices (all ones: out of range)
+        const uint32_t my16 = valid ? (uint32_t)((reinterpret_cast<const uint8_t*>(dst0) - reinterpret_cast<const uint8_t*>(P.out)) >> 4) : 0xFFFFFFFFu;
+        uint32_t d16[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          drow[k] = reinterpret_cast<bf16*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst0), (lane >> 2) + 8 * k));
+        for (int k = 0; k < 4; ++k) d16[k] = __shfl_sync(0xffffffffu, my16, (lane >> 2) + 8 * k);
         // One flat loop over (channel chunk, phase): the TMEM load of the NEXT piece is issued as soon as this one is packed
         // to bf16, so it flies under the shared-memory round trip and the stores.
         const int pcs = dbl ? 2 : 1, per_c = 1 << pcs;   // pieces per channel chunk: 4 phases, or this set's 2
@@ -300,14 +301,14 @@ umma_tmat_conv_kernel(const __grid_constant__ TmatParams P) {
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(st_w + (((uint32_t)q ^ wx) << 4)), "r"(w[4 * q]),
                          "r"(w[4 * q + 1]), "r"(w[4 * q + 2]), "r"(w[4 * q + 3]) : "memory");
           __syncwarp();
-          const long long off = ((long long)php * Wout + pwp) * ldo + c0 + (lane & 3) * 8;
+          const uint32_t off16 = (uint32_t)(((php * Wout + pwp) * ldo + c0) >> 3) + (uint32_t)(lane & 3);
           uint4 pk[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[k].x), "=r"(pk[k].y), "=r"(pk[k].z), "=r"(pk[k].w) : "r"(st_r + (uint32_t)k * 512u));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (drow[k] != nullptr) *reinterpret_cast<uint4*>(drow[k] + off) = pk[k];
+            if (d16[k] != 0xFFFFFFFFu) stg_v4(reinterpret_cast<uint4*>(P.out) + ((size_t)d16[k] + off16), pk[k]);
           __syncwarp();
           if (EPI == 1 && !split && rem == per_c - 1) {
             warp_transpose_reduce32(s1, lane);

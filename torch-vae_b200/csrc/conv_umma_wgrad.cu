@@ -58,7 +58,7 @@ constexpr int kAStage = 2 * 8192;  // two 64-channel groups x 64 pixel rows x 12
 __global__ void __launch_bounds__(kWgThreads, 1)
 umma_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* tail = smem + P.stages * P.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + 4;

@@ -75,7 +75,7 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_base, uint32_t hi_x, u
 __global__ void __launch_bounds__(kWtThreads, 2)
 umma_wgrad_tma_kernel(const __grid_constant__ WgradTmaParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* tail = smem + P.stages * P.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kWtMaxStages;

@@ -152,7 +152,7 @@ template <bool WIDE, bool PARTIAL>
 __global__ void __launch_bounds__(kFtThreads, 3)
 final_fwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* ring = smem;                                   // [slots][8 KB]
   uint8_t* wimg = ring + kFtSlots * kRowBytes;            // [32 taps][64 B] swizzled, taps 9..31 zero
   float* psm = reinterpret_cast<float*>(wimg + 2048);     // [4][9][130]
@@ -407,7 +407,7 @@ template <int PASS, int SLOTS, int CTAS, bool WIDE>
 __global__ void __launch_bounds__(kFtThreads, CTAS)
 final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024_shared(smem_raw);
   BwdSmem S = carve_bwd(smem, SLOTS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = P.H, RB = P.RB;
@@ -779,7 +779,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(kFtThreads, 2)
 final_bwd_reduce_gemm_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* yring = smem;                         // [slots][8 KB]   (b ring at +L, b*y ring at +2L)
   uint8_t* a1 = smem + 3 * kP1Ring;              // [kA1Bufs][8 KB] dlwin tiles; + 8 KB pad (unused M group of the last slot)
   float* cst = reinterpret_cast<float*>(a1 + kA1Bufs * kRowBytes + 8192);   // scale[32], shift[32]
@@ -1052,7 +1052,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
 final_bwd_reduce_deep_kernel(const __grid_constant__ FinalTcParams P) {
   constexpr bool WIDE = true;   // opt-in experiment: always the general form
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align1024(smem_raw);
   uint8_t* yring = smem;                         // [kDLSlots][8 KB] landing ring (TMA)
   uint8_t* oring = smem + kDLSlots * kRowBytes;  // [kDOSlots][y | b | b*y] operand ring; + 8 KB pad (unused M group of the last slot)
   uint8_t* a1 = oring + kDOSlots * kDOSlot + 8192;   // [kA1Bufs][8 KB] dlwin tiles

@@ -40,6 +40,10 @@ __device__ __forceinline__ float4 lds_f4_ro(uint32_t a) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+// 16-byte store to GLOBAL memory (a pointer rebuilt from integers / shuffles would otherwise be stored through generically)
+__device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // shared-memory matrix descriptor with a selectable swizzle (2 = 128B, 4 = 64B)

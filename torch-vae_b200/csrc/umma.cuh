@@ -14,6 +14,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- mbarrier ---------------------------------------------------------------
+// 1024-byte aligned start of the dynamic shared memory, two ways.
+// align1024_shared: pointer arithmetic on the array itself -- the compiler keeps the shared address space and every derived
+// access is an LDS / STS.  align1024: rounding through uintptr_t -- derived accesses become generic LD / ST.
+// Measured on one B200 with two builds of the library (profiles/r04h_lib_ab.txt): the shared-space form takes the
+// output block's backward apply kernel from 232 to 209 us, but makes the warp-specialised tcgen05 conv kernels SLOWER
+// (conv_umma_rw 181 -> 214 us, 114 -> 132 us, 93 -> 116 us; conv_umma_tma +2 .. 4 %): with the address space known the
+// compiler moves the epilogue's shared-memory traffic across the volatile barrier / TMEM sequences.  Their hot
+// shared-memory accesses are explicit ld.shared / st.shared asm already, so those kernels keep the generic form.
+__device__ __forceinline__ uint8_t* align1024_shared(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+__device__ __forceinline__ uint8_t* align1024(uint8_t* raw) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
