@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-chunk", type=int, default=512, help="sample workload, e2e leg: images per decode / copy chunk")
     ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW instead of the fused kernel")
     ap.add_argument("--cpu-batch", type=int, default=64)
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager (reference class on cuda) leg")
@@ -824,10 +825,8 @@ def b200_sample_arm(a):
 
     def e2e_step():
         torch.randn((B, LATENT), out=z_host)  # models.py:258
-        with torch.no_grad():
-            img = model.decode(z_host.to(dev, non_blocking=True))
-        img_host.copy_(img, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller owns the images when the call returns
+        # decode in chunks, each chunk's D2H copy under the next chunk's kernels; returns with the images on the host
+        model.sample_to_host(B, out=img_host, z=z_host, chunk=a.sample_chunk)
 
     for _ in range(3):
         e2e_step()
@@ -843,7 +842,8 @@ def b200_sample_arm(a):
             "clocks": clk,
             "e2e": {"value": B * world * a.steps / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": z_host.numel() * 4 * world,
                     "d2h_bytes_per_step": img_host.numel() * 4 * world, "ms_per_step": ms_e2e / a.steps,
-                    "input": "z = torch.randn on the host (models.py:258) -> H2D -> decode -> fp32 images D2H into pinned memory"},
+                    "input": f"z = torch.randn on the host (models.py:258) -> H2D -> VanillaVAE.sample_to_host: decode in chunks of {a.sample_chunk}, "
+                             "fp32 images D2H into pinned memory on a copy stream under the next chunk's decode"},
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
             "roofline": roofline,
             "step_tflops": WORKLOADS[a.workload]["flops_decode"] * value / 1e12 if (H, W) == (128, 128) else None,

@@ -407,7 +407,9 @@ template <int PASS, int SLOTS, int CTAS, bool WIDE>
 __global__ void __launch_bounds__(kFtThreads, CTAS)
 final_bwd_tc_kernel(const __grid_constant__ FinalTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = align1024_shared(smem_raw);
+  // shared-space base at C = 32 (apply pass 232 -> 209 us); at C = 64 (WIDE) that form measured slower (590 -> 611 us)
+  uint8_t* smem;
+  if constexpr (WIDE) smem = align1024(smem_raw); else smem = align1024_shared(smem_raw);
   BwdSmem S = carve_bwd(smem, SLOTS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = P.H, RB = P.RB;

@@ -259,5 +259,32 @@ class VanillaVAE(nn.Module):
             z = torch.randn(num_samples, self.latent_dim).to(current_device)
         return self.decode(z)
 
+    def sample_to_host(self, num_samples: int, out: Optional[Tensor] = None, chunk: int = 512, z: Optional[Tensor] = None) -> Tensor:
+        """``sample(n, device).cpu()`` (models.py:250-263 and the copy its callers make) as one pipelined call: z is drawn on
+        the host with ``torch.randn`` like the reference, the batch is decoded in chunks, and each chunk's device->host
+        copy runs on a side stream under the next chunk's decode.  ``out``: pinned fp32 [n, C, H, W] buffer to fill
+        (allocated when absent).  Returns when the images are in host memory."""
+        dev = self.decoder_input.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("torch_vae_b200.VanillaVAE runs on CUDA only (no CPU fallback)")
+        if z is None:
+            z = torch.randn(num_samples, self.latent_dim)
+        if z.shape[0] != num_samples or chunk <= 0:
+            raise RuntimeError("sample_to_host: z must hold num_samples rows and chunk must be positive")
+        main = torch.cuda.current_stream(dev)
+        copy = ops.copy_stream(dev)
+        zd = z.to(dev, non_blocking=True)
+        with torch.no_grad():
+            for i in range(0, num_samples, chunk):
+                img = self.decode(zd[i : i + chunk])
+                if out is None:
+                    out = torch.empty((num_samples,) + tuple(img.shape[1:]), dtype=torch.float32).pin_memory()
+                copy.wait_stream(main)
+                with torch.cuda.stream(copy):
+                    out[i : i + chunk].copy_(img, non_blocking=True)
+                img.record_stream(copy)
+        copy.synchronize()
+        return out
+
     def generate(self, x: Tensor, **kwargs) -> Tensor:
         return self.forward(x)["output"]

@@ -876,6 +876,19 @@ def aux_stream(device) -> "torch.cuda.Stream":
     return _AUX_STREAMS[idx]
 
 
+_COPY_STREAMS = {}
+
+
+def copy_stream(device) -> "torch.cuda.Stream":
+    """Side stream for device->host result copies that overlap the next chunk's kernels (VanillaVAE.sample_to_host)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _COPY_STREAMS:
+        _COPY_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return _COPY_STREAMS[idx]
+
+
 class PackBatch:
     """All weight images of one step, packed on a side stream while the first (CUDA-core) layer runs.
 
