@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grad-sink", action="store_true", help="N = 1: let autograd allocate / accumulate the gradients instead of the flat bucket sink")
     ap.add_argument("--sample-chunk", type=int, default=512, help="sample workload, e2e leg: images per decode / copy chunk")
     ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW instead of the fused kernel")
     ap.add_argument("--cpu-batch", type=int, default=64)
@@ -534,8 +535,11 @@ def b200_arm(a):
         # train.py:232-238: OneCycleLR over the groups' lrs, stepped per batch (:659); here advanced on the
         # device so that the captured step follows it.  1000 epochs x 100 steps: the schedule never runs out.
         sched = tv.optim.FusedOneCycleLR(opt, [g["lr"] for g in opt.param_groups], epochs=1000, steps_per_epoch=100)
+    # gradient sink: the backward kernels write every gradient straight into flat buckets (no per-parameter
+    # AccumulateGrad launches); at N > 1 the buckets are all-reduced (NCCL AVG) under the rest of backward, at N = 1 the
+    # sink is local.  --no-grad-sink at N = 1: plain autograd gradient tensors.
     buckets = None
-    if world > 1:
+    if world > 1 or not a.no_grad_sink:
         buckets = GradientBuckets(model)
         buckets.broadcast_parameters(0)
 
@@ -695,6 +699,9 @@ def b200_arm(a):
                        "parallelism": f"dp{world}", "cuda_graph": bool(graph is not None),
                        "optimizer": ("torch.optim.AdamW" if a.torch_adamw else "FusedAdamW + FusedOneCycleLR (device-resident lr/beta1, torch.optim.AdamW state layout)")
                                     + " over encoder+decoder groups (train.py:210-238), optimizer.step and scheduler.step inside the timed step",
+                       "gradients": (("backward kernels write straight into flat buckets (parallel.GradientBuckets: "
+                                      + ("NCCL AVG all-reduce per bucket under the rest of backward)" if world > 1 else "local sink, no collective)"))
+                                     if buckets is not None else "autograd gradient tensors"),
                        "l2": f"per-step activation working set {activation_bytes(H, W, HIDDEN) * B / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rolls_host.numel() * world, "d2h_bytes_per_step": 4 * world,

@@ -55,11 +55,13 @@ def execution_order_reversed(model) -> List[torch.nn.Parameter]:
 class GradientBuckets:
     def __init__(self, model, process_group=None, bucket_cap_mb: float = 25.0,
                  first_bucket_cap_mb: float = 1.0, average: bool = True):
-        if not dist.is_initialized():
-            raise RuntimeError("GradientBuckets needs torch.distributed to be initialised")
+        # Without an initialised process group the sink is LOCAL (one process, one GPU): the backward schedules still
+        # write every gradient straight into its bucket slice and autograd gets None, so the step runs the same
+        # gradient path as the N-GPU job, minus the collective (no per-parameter AccumulateGrad launches).
+        self.local = not dist.is_initialized()
         self.model = model
         self.group = process_group
-        self.world = dist.get_world_size(process_group)
+        self.world = 1 if self.local else dist.get_world_size(process_group)
         self.average = average
         params = [p for p in execution_order_reversed(model) if p.requires_grad]
         missing = set(id(p) for p in model.parameters() if p.requires_grad) - set(id(p) for p in params)
@@ -93,9 +95,9 @@ class GradientBuckets:
             self.pending.append(len(grp))
         self._count = list(self.pending)
         self._staged = [([], []) for _ in self.buckets]
-        self._nccl_avg = self.is_cuda and dist.get_backend(process_group) == "nccl"
+        self._nccl_avg = (not self.local) and self.is_cuda and dist.get_backend(process_group) == "nccl"
         self._works: List[Optional[object]] = [None] * len(self.buckets)
-        self.comm_stream = torch.cuda.Stream(device=self.device) if self.is_cuda else None
+        self.comm_stream = torch.cuda.Stream(device=self.device) if (self.is_cuda and not self.local) else None
         self.bytes_per_step = 4 * sum(b.numel() for b in self.buckets)
         model._grad_sink = self
 
@@ -131,6 +133,8 @@ class GradientBuckets:
         if dst:  # gradients that were produced elsewhere: one multi-tensor copy, not one copy each
             torch._foreach_copy_(dst, src)
         self._staged[bi] = ([], [])
+        if self.local:
+            return
         op = dist.ReduceOp.SUM
         if self.is_cuda:
             ready = torch.cuda.Event()
@@ -156,16 +160,20 @@ class GradientBuckets:
         for w in self._works:
             if w is not None:
                 w.wait()
-        if self.is_cuda:
+        if self.is_cuda and self.comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         for _, (bi, off, p) in self.slot.items():
             p.grad = self.view(p)
 
     def broadcast_buffers(self, src: int = 0) -> None:
         """DDP's ``broadcast_buffers`` equivalent: running stats follow rank ``src``."""
+        if self.local:
+            return
         for b in self.model.buffers():
             dist.broadcast(b, src=src, group=self.group)
 
     def broadcast_parameters(self, src: int = 0) -> None:
+        if self.local:
+            return
         for p in self.model.parameters():
             dist.broadcast(p.data, src=src, group=self.group)

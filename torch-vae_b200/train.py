@@ -189,11 +189,10 @@ def run(config: argparse.Namespace) -> dict:
     data = DeviceRollDataset(rolls, train_tf, config.batch_size_per_gpu, rank, world, shuffle=True, seed=config.seed)
     scheduler = tv.optim.FusedOneCycleLR(optimizer, [g["lr"] for g in optimizer.param_groups], epochs=config.epochs,
                                          steps_per_epoch=len(data))                          # train.py:232-238
-    buckets = None
-    if world > 1:
-        buckets = GradientBuckets(model)
-        buckets.broadcast_parameters(0)
-        buckets.broadcast_buffers(0)
+    # gradient sink for every world size (local at one GPU: same gradient path, no collective)
+    buckets = GradientBuckets(model)
+    buckets.broadcast_parameters(0)
+    buckets.broadcast_buffers(0)
 
     start_epoch, total_step, n_samples_seen = 1, 0, 0
     if config.checkpoint_path and os.path.isfile(config.checkpoint_path):
