@@ -259,13 +259,13 @@ def algorithmic_cost(name, tag):
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels that can dominate
 # the B=512 step, from ONE `ncu --set full` capture per kernel (scripts/profile_top.py): the output-block
-# kernels from profiles/r02i_ncu_full_output_block.csv (final code of round 2), the conv kernels from
+# kernels from profiles/r04k_ncu_full_output_block.csv (final code of round 2), the conv kernels from
 # profiles/r01e_ncu_full_top_kernels.csv.
 # Keyed by (C-ABI entry point, leading integer arguments).
 NCU_TRAFFIC_BYTES = {
-    ("vae_final_conv_fwd_tc", (512, 128, 128, 32)): 559.65e6 + 46.16e6,
-    ("vae_final_bwd_reduce_tc", (512, 128, 128, 32)): 553.81e6 + 3.85e6,
-    ("vae_final_bwd_apply_tc", (512, 128, 128, 32)): 554.86e6 + 495.68e6,
+    ("vae_final_conv_fwd_tc", (512, 128, 128, 32)): 559.68e6 + 45.58e6,     # profiles/r04k_ncu_full_output_block.csv
+    ("vae_final_bwd_reduce_tc", (512, 128, 128, 32)): 553.80e6 + 4.50e6,
+    ("vae_final_bwd_apply_tc", (512, 128, 128, 32)): 556.37e6 + 499.85e6,
     ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 1)): 134.33e6 + 477.68e6,
     ("vae_conv_umma_rw", (512, 128, 128, 32, 32, 2, 0)): 536.98e6 + 118.08e6,
     ("vae_conv_wgrad_tma", (512, 128, 128, 32, 32, 2)): 671.55e6 + 6.52e6,
