@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-cap-mb", type=float, default=25.0, help="gradient bucket size (parallel.GradientBuckets)")
     ap.add_argument("--no-grad-sink", action="store_true", help="N = 1: let autograd allocate / accumulate the gradients instead of the flat bucket sink")
     ap.add_argument("--sample-chunk", type=int, default=512, help="sample workload, e2e leg: images per decode / copy chunk")
     ap.add_argument("--torch-adamw", action="store_true", help="step with torch.optim.AdamW instead of the fused kernel")
@@ -540,7 +541,7 @@ def b200_arm(a):
     # sink is local.  --no-grad-sink at N = 1: plain autograd gradient tensors.
     buckets = None
     if world > 1 or not a.no_grad_sink:
-        buckets = GradientBuckets(model)
+        buckets = GradientBuckets(model, bucket_cap_mb=a.bucket_cap_mb, first_bucket_cap_mb=min(1.0, a.bucket_cap_mb))
         buckets.broadcast_parameters(0)
 
     x_host, _ = vo.synthetic_batch(B, H, W, LATENT, seed=1234 + rank)
