@@ -66,49 +66,17 @@ template <typename TA, int N, int ROWS, int NW>
 __global__ void __launch_bounds__(256, 2)
 skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                      float* __restrict__ out, const float* __restrict__ W1, const float* __restrict__ bias1,
-                     float* __restrict__ out1, int M, int K, long long wsn, long long wsk, int ks_len) {
+                     float* __restrict__ out1, int M, int K, long long wsn, long long wsk, int ks_len, int nslice) {
   extern __shared__ __align__(16) float w_s[];  // [NW][N][2][ks_len / 2]
+  // A block walks `nslice` consecutive K slices with the same 8 x ROWS rows and keeps the accumulators across them:
+  // the warp reductions and the atomics at the end are paid once per block, not once per slice (with one slice per
+  // block the M = 512, K = 16384 pair launch spent as long reducing as multiplying: 44 us).
   const int kslices = (K + ks_len - 1) / ks_len;
-  const int ks = blockIdx.x % kslices, mb = blockIdx.x / kslices;
-  const int k_begin = ks * ks_len, k_len = min(ks_len, K - k_begin);  // multiples of 8
+  const int kgroups = (kslices + nslice - 1) / nslice;
+  const int kg = blockIdx.x % kgroups, mb = blockIdx.x / kgroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (mb * 8 + warp) * ROWS;
   const int half_len = ks_len >> 1;
-  const TA* a_base = A + (long long)m0 * K + k_begin;
-  Vec8<TA> a[ROWS];
-  auto load_rows = [&](int kk) {
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      if (m0 + r < M && kk < k_len) a[r].load(a_base + (long long)r * K + kk);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[r].v[j] = 0.0f;
-      }
-    }
-  };
-  load_rows(lane * 8);
-#pragma unroll
-  for (int q = 0; q < NW; ++q) {
-    const float* __restrict__ Wq = q == 0 ? W : W1;
-    float* ws = w_s + q * N * ks_len;
-    if (wsk == 1 && (wsn & 3) == 0) {
-      for (int kk = threadIdx.x * 4; kk < k_len; kk += 1024) {
-        const int dst = ((kk >> 2) & 1) * half_len + (kk >> 3) * 4;
-        float4 v[N];
-#pragma unroll
-        for (int n = 0; n < N; ++n) v[n] = *reinterpret_cast<const float4*>(Wq + n * wsn + k_begin + kk);
-#pragma unroll
-        for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(&ws[n * ks_len + dst]) = v[n];
-      }
-    } else {
-      for (int i = threadIdx.x; i < N * k_len; i += 256) {
-        const int kk = i / N, n = i - kk * N;
-        ws[n * ks_len + ((kk >> 2) & 1) * half_len + (kk >> 3) * 4 + (kk & 3)] = Wq[n * wsn + (long long)(k_begin + kk) * wsk];
-      }
-    }
-  }
-  __syncthreads();
-  if (m0 >= M) return;
   float acc[NW][ROWS][N];
 #pragma unroll
   for (int q = 0; q < NW; ++q)
@@ -116,22 +84,65 @@ skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, cons
     for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int n = 0; n < N; ++n) acc[q][r][n] = 0.0f;
-  for (int kk = lane * 8; kk < k_len; kk += 256) {
-    if (kk != lane * 8) load_rows(kk);
+  for (int s = 0; s < nslice; ++s) {
+    const int ks = kg * nslice + s;
+    if (ks >= kslices) break;   // uniform over the block
+    const int k_begin = ks * ks_len, k_len = min(ks_len, K - k_begin);  // multiples of 8
+    const TA* a_base = A + (long long)m0 * K + k_begin;
+    Vec8<TA> a[ROWS];
+    auto load_rows = [&](int kk) {
 #pragma unroll
-    for (int q = 0; q < NW; ++q)
+      for (int r = 0; r < ROWS; ++r) {
+        if (m0 + r < M && kk < k_len) a[r].load(a_base + (long long)r * K + kk);
+        else {
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        const float* ws = w_s + (q * N + n) * ks_len;
-        const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk >> 1]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&ws[half_len + (kk >> 1)]);
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[q][r][n] = fmaf(a[r].v[j], w[j], acc[q][r][n]);
+          for (int j = 0; j < 8; ++j) a[r].v[j] = 0.0f;
+        }
       }
+    };
+    load_rows(lane * 8);
+    if (s > 0) __syncthreads();   // every warp is done reading the previous slice's weights
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      const float* __restrict__ Wq = q == 0 ? W : W1;
+      float* ws = w_s + q * N * ks_len;
+      if (wsk == 1 && (wsn & 3) == 0) {
+        for (int kk = threadIdx.x * 4; kk < k_len; kk += 1024) {
+          const int dst = ((kk >> 2) & 1) * half_len + (kk >> 3) * 4;
+          float4 v[N];
+#pragma unroll
+          for (int n = 0; n < N; ++n) v[n] = *reinterpret_cast<const float4*>(Wq + n * wsn + k_begin + kk);
+#pragma unroll
+          for (int n = 0; n < N; ++n) *reinterpret_cast<float4*>(&ws[n * ks_len + dst]) = v[n];
+        }
+      } else {
+        for (int i = threadIdx.x; i < N * k_len; i += 256) {
+          const int kk = i / N, n = i - kk * N;
+          ws[n * ks_len + ((kk >> 2) & 1) * half_len + (kk >> 3) * 4 + (kk & 3)] = Wq[n * wsn + (long long)(k_begin + kk) * wsk];
+        }
+      }
+    }
+    __syncthreads();
+    if (m0 < M) {
+      for (int kk = lane * 8; kk < k_len; kk += 256) {
+        if (kk != lane * 8) load_rows(kk);
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            const float* ws = w_s + (q * N + n) * ks_len;
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk >> 1]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&ws[half_len + (kk >> 1)]);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[q][r][n] = fmaf(a[r].v[j], w[j], acc[q][r][n]);
+          }
+      }
+    }
   }
+  if (m0 >= M) return;
 #pragma unroll
   for (int q = 0; q < NW; ++q) {
     const float* __restrict__ bq = q == 0 ? bias : bias1;
@@ -142,7 +153,7 @@ skinny_reduce_kernel(const TA* __restrict__ A, const float* __restrict__ W, cons
       for (int n = 0; n < N; ++n) {
         float v = warp_sum(acc[q][r][n]);
         if (lane == ((r * N + n) & 31) && m0 + r < M) {
-          if (ks == 0 && bq != nullptr) v += bq[n];
+          if (kg == 0 && bq != nullptr) v += bq[n];
           atomicAdd(&oq[(long long)(m0 + r) * N + n], v);
         }
       }
@@ -327,13 +338,18 @@ static int skinny_reduce_launch(const void* A, const float* W, const float* bias
   const int row_blocks = (M + 8 * rows - 1) / (8 * rows);
   int ks_len = pair ? 512 : 1024;  // K slice per block: one wave of two blocks per SM where the shape allows it
   while (ks_len > 256 && (long long)row_blocks * ((K + ks_len - 1) / ks_len) * 2 <= 2LL * sm_count()) ks_len /= 2;
-  const int grid = row_blocks * ((K + ks_len - 1) / ks_len);
+  const int kslices = (K + ks_len - 1) / ks_len;
+  // slices per block: as many as still leave one full wave of two resident blocks per SM
+  int nslice = (int)(((long long)row_blocks * kslices + 2LL * sm_count() - 1) / (2LL * sm_count()));
+  if (nslice < 1) nslice = 1;
+  if (nslice > kslices) nslice = kslices;
+  const int grid = row_blocks * ((kslices + nslice - 1) / nslice);
   const size_t smem = sizeof(float) * (size_t)N * ks_len * (pair ? 2 : 1);
 #define VAE_SR_LAUNCH(TA, ROWS, NW)                                                                                   \
   do {                                                                                                                \
     auto kern = skinny_reduce_kernel<TA, NN, ROWS, NW>;                                                               \
     if (smem > 48 * 1024) VAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
-    kern<<<grid, 256, smem, st>>>((const TA*)A, W, bias, out, W1, bias1, out1, M, K, wsn, wsk, ks_len);               \
+    kern<<<grid, 256, smem, st>>>((const TA*)A, W, bias, out, W1, bias1, out1, M, K, wsn, wsk, ks_len, nslice);               \
   } while (0)
   VAE_N_SWITCH(N, {
     if (dtA == VAE_BF16) {
