@@ -142,6 +142,38 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_gradient_buckets_local_sink_without_process_group():
+    """Without torch.distributed the sink is local (one GPU): same slots and views, no collective, p.grad = the bucket
+    views holding exactly what was pushed; an incomplete step is still reported."""
+    import torch_vae_b200 as tv
+    from torch_vae_b200.parallel import GradientBuckets, execution_order_reversed
+
+    assert not dist.is_initialized()
+    torch.manual_seed(0)
+    model = tv.VanillaVAE(1, 6, 32, hidden_dims=[8, 16, 32, 64])
+    buckets = GradientBuckets(model, bucket_cap_mb=0.02, first_bucket_cap_mb=0.001)
+    assert buckets.local and buckets.world == 1 and buckets.comm_stream is None and model._grad_sink is buckets
+    order = execution_order_reversed(model)
+    for step in range(2):
+        buckets.begin()
+        for k, p in enumerate(order):
+            if k % 2:   # written in place by a "kernel" (engine._dst) ...
+                buckets.view(p).fill_(float((k + 1) * (step + 1)))
+                buckets.push(p, buckets.view(p))
+            else:       # ... or produced elsewhere and staged
+                buckets.push(p, torch.full_like(p, float((k + 1) * (step + 1))))
+        buckets.finish()
+        for k, p in enumerate(order):
+            assert torch.equal(p.grad, torch.full_like(p, float((k + 1) * (step + 1))))   # overwritten, not accumulated
+            assert p.grad.data_ptr() == buckets.view(p).data_ptr()
+    buckets.broadcast_parameters(0)   # no-ops locally
+    buckets.broadcast_buffers(0)
+    buckets.begin()
+    buckets.push(order[0], torch.zeros_like(order[0]))
+    with pytest.raises(RuntimeError):
+        buckets.finish()
+
+
 def test_gradient_buckets_two_ranks_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
