@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay of the step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-zero-arena", action="store_true", help="let the library clear every statistics / split-K buffer with its own memset")
     ap.add_argument("--bucket-cap-mb", type=float, default=25.0, help="gradient bucket size (parallel.GradientBuckets)")
     ap.add_argument("--no-grad-sink", action="store_true", help="N = 1: let autograd allocate / accumulate the gradients instead of the flat bucket sink")
     ap.add_argument("--sample-chunk", type=int, default=512, help="sample workload, e2e leg: images per decode / copy chunk")
@@ -549,7 +550,11 @@ def b200_arm(a):
     x_dev = x_host.to(dev)
     losses_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
+    if not a.no_zero_arena:
+        ops.enable_zero_arena(dev)   # statistics / split-K scratch from one arena, cleared once per step
+
     def train_step(x):
+        ops.zero_arena_reset(dev)
         out = model.forward(x)  # train.py:635
         opt.zero_grad(set_to_none=True)  # :642
         losses = model.loss(out)  # :644

@@ -43,6 +43,9 @@ typedef void* vae_stream_t;
 /* Leave `n` SMs out of the grids of the persistent kernels, for NCCL kernels that run concurrently in data-parallel runs
  * with large gradient buckets (the persistent kernels otherwise occupy every SM completely); returns the previous value. */
 int vae_set_reserved_sms(int n);
+/* Scratch arena the caller keeps zeroed (current device): buffers inside it that a kernel accumulates into are not cleared
+ * by the library; base = NULL removes the registration.  Host-side only, no kernel launch. */
+int vae_set_zero_arena(void* base, long long bytes);
 int vae_abi_version(void);
 const char* vae_last_error(void);
 /* 1 if the library was built with the tcgen05/TMEM (UMMA) conv kernels. */

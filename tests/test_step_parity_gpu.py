@@ -360,8 +360,43 @@ def test_local_gradient_sink_matches_autograd(tv):
         assert p.grad is not None and p.grad.untyped_storage().data_ptr() in flat_ptrs, name
         floor = vo.grad_floor({k: v for k, v in grads.items()}, name)
         # two runs differ by the order of floating-point atomics, amplified by BatchNorm backward on a few parameters
-        # (test_run_twice_determinism measures up to 2e-2 between identical bf16 runs)
-        assert vo.rel_err(p.grad.cpu(), grads[name], floor) <= 5e-2, name
+        # (test_run_twice_determinism measures up to 2e-2 between identical bf16 runs at B = 64, ~7e-2 at B = 16)
+        assert vo.rel_err(p.grad.cpu(), grads[name], floor) <= 0.15, name
+
+
+@pytest.mark.parametrize("nbytes", [64 << 20, 4096], ids=["arena_64MB", "arena_4KB_falls_back"])
+def test_zero_arena_step_matches(tv, nbytes):
+    """ops.ZeroArena: statistics / split-K scratch carved from a caller-zeroed arena (the library skips its own clears for
+    pointers inside it) gives the same step as per-buffer memsets -- over several steps, so that a buffer which the
+    once-per-step clear missed would show up as statistics accumulated across steps.  A 4 KB arena serves the first few
+    small buffers and falls back to fresh tensors for the rest."""
+    H = W = 128
+    hidden, L, B = [32, 64, 128, 256], 10, 16
+    params = vo.xavier_params(1, L, H, W, hidden, seed=0)
+    x, eps = vo.synthetic_batch(B, H, W, L, seed=1234)
+    ref = build(tv, H, W, hidden, L, 1.0, torch.bfloat16, params)
+    _, ref_losses, ref_grads, ref_bufs = run_cuda(ref, x, eps)
+    model = build(tv, H, W, hidden, L, 1.0, torch.bfloat16, params)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    arena = tv.ops.enable_zero_arena(dev, nbytes)
+    try:
+        used = []
+        for _ in range(3):
+            tv.ops.zero_arena_reset(dev)
+            _, losses, grads, _ = run_cuda(model, x, eps)   # no optimizer: the three steps are the same step
+            used.append(arena.off)
+            assert abs(float(losses["loss"]) - float(ref_losses["loss"])) <= 1e-5 * abs(float(ref_losses["loss"]))
+            for k in grads:
+                floor = vo.grad_floor(ref_grads, k)
+                # run-to-run atomics noise only: at B = 16 BatchNorm backward amplifies it to ~7e-2 on decoder_input.weight
+                # (measured between two plain runs); a scratch buffer that was not cleared gives O(1) errors and moves the loss
+                assert vo.rel_err(grads[k], ref_grads[k], floor) <= 0.15, k
+        assert used[0] > 0 and used[0] == used[1] == used[2] and used[0] <= max(nbytes, 256)
+        if nbytes > (1 << 20):
+            assert used[0] > 100_000   # the weight-gradient workspaces came from the arena too
+    finally:
+        tv.ops.disable_zero_arena(dev)
+    assert tv.ops.scratch(4, torch.float64, dev).data_ptr() != 0   # plain tensors again
 
 
 def test_sample_to_host_pipelined(tv):

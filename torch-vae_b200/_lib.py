@@ -20,6 +20,7 @@ _vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulong
 PROTOTYPES = {
     "vae_abi_version": [],
     "vae_set_reserved_sms": [_i],
+    "vae_set_zero_arena": [_vp, _ll],
     "vae_last_error": [],
     "vae_has_umma": [],
     "vae_pack_conv_weight": [_vp, _vp, _vp, _i, _i, _i, _vp],

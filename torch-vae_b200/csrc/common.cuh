@@ -35,6 +35,10 @@ static inline cudaStream_t as_stream(vae_stream_t s) { return reinterpret_cast<c
 
 int sm_count();
 
+// Zero a scratch buffer (statistics, split-K workspaces) before a kernel accumulates into it -- unless it lies inside the
+// caller's pre-zeroed arena (vae_set_zero_arena), whose one clear per step replaces ~25 memset nodes of a train step.
+cudaError_t zero_scratch(void* p, size_t bytes, cudaStream_t st);
+
 // ---- scalar type traits ---------------------------------------------------
 typedef __nv_bfloat16 bf16;
 

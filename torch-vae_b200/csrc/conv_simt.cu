@@ -512,7 +512,7 @@ extern "C" int vae_conv_fprop(const void* x, const void* wp, const float* bias, 
                   Hi > 0 && Wi > 0 && Hi % stride == 0 && Wi % stride == 0,
               "conv_fprop: bad argument (B=%d Hi=%d Wi=%d Ci=%d Co=%d s=%d)", B, Hi, Wi, Ci, Co, stride);
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Co, st));
+  if (stats) VAE_CUDA(zero_scratch(stats, sizeof(double) * 2 * Co, st));
   GatherGeom g = geom_fprop(B, Hi, Wi, Ci, Co, stride);
   const bool bf = dt_out == VAE_BF16;
   if (Ci == 1 && edge_ok(Co)) {
@@ -552,7 +552,7 @@ extern "C" int vae_conv_dgrad(const void* dy, const void* wt, const float* bias,
                   Hi > 0 && Wi > 0 && Hi % stride == 0 && Wi % stride == 0,
               "conv_dgrad: bad argument (B=%d Hi=%d Wi=%d Ci=%d Co=%d s=%d)", B, Hi, Wi, Ci, Co, stride);
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Ci, st));
+  if (stats) VAE_CUDA(zero_scratch(stats, sizeof(double) * 2 * Ci, st));
   GatherGeom g = geom_dgrad(B, Hi, Wi, Ci, Co, stride);
   const bool bf = dtype == VAE_BF16;
   if (Co == 1 && stride == 1 && edge_ok(Ci)) {
@@ -575,7 +575,7 @@ extern "C" int vae_conv_wgrad(const void* x, const void* dy, float* dw, int B, i
                   Hi > 0 && Wi > 0 && Hi % stride == 0 && Wi % stride == 0,
               "conv_wgrad: bad argument (B=%d Hi=%d Wi=%d Ci=%d Co=%d s=%d)", B, Hi, Wi, Ci, Co, stride);
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
+  VAE_CUDA(zero_scratch(dw, sizeof(float) * 9 * (size_t)Ci * Co, st));
   const int Ho = Hi / stride, Wo = Wi / stride;
   if (Ci == 1 && edge_ok(Co) && Co <= 64) {  // enc.conv0: Mc = dY, S1 = x
     const int rc = edge_c1_wgrad(dy, x, dw, B, Ho, Wo, Co, Hi, Wi, stride, 0, dt_dy, dt_x, st);

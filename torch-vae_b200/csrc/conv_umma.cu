@@ -674,7 +674,7 @@ extern "C" int vae_conv_umma(const void* in, const void* wpk, const float* bias,
   VAE_REQUIRE((long long)g.B * g.Hin * g.Win * g.Cin < (1LL << 32) && (long long)g.B * g.Hj * g.Wj < (1LL << 31),
               "conv_umma: tensor too large for 32-bit row offsets");
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * g.Nout, st));
+  if (stats) VAE_CUDA(zero_scratch(stats, sizeof(double) * 2 * g.Nout, st));
   UmmaGatherParams P{};
   fill_params(P, g);
   P.in = (const bf16*)in; P.wpk = (const bf16*)wpk; P.bias = bias; P.out = (bf16*)out; P.stats = stats;

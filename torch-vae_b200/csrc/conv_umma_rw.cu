@@ -634,7 +634,7 @@ static int rw_dispatch(const void* in, const void* wpk, const float* bias, void*
   RwPlan pl{};
   VAE_REQUIRE(rw_plan(pl, B, Hi, Wi, Ci, Co, stride, mode), "conv_umma_rw: shape not served by this kernel");
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * pl.n, st));
+  if (stats) VAE_CUDA(zero_scratch(stats, sizeof(double) * 2 * pl.n, st));
   if (mode == 0 && pl.n == 32) return rw_launch<0, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
   if (mode == 0 && pl.n == 64) return rw_launch<0, 32, 64>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);
   if (mode == 1 && pl.kc == 32) return rw_launch<1, 32, 32>(pl, in, wpk, bias, out, stats, B, st, bn_y, bn_vec, slope, act);

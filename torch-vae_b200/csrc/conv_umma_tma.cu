@@ -675,7 +675,7 @@ static int tma_dispatch(const void* in, const void* wpk, const float* bias, void
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VAE_REQUIRE(cr == CUDA_SUCCESS, "conv_umma_tma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   cudaStream_t st = as_stream(stream);
-  if (stats) VAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n_total, st));
+  if (stats) VAE_CUDA(zero_scratch(stats, sizeof(double) * 2 * n_total, st));
   P.ldo = n_total;
   P.trace = umma_trace_ptr();
   size_t smem = 1024 + (size_t)P.stages * (P.a_stage_bytes + P.b_stage_bytes) + 256 + 16 + 768 * 4 + 64 +

@@ -470,7 +470,7 @@ int tmat_launch(const void* in, const void* wpk, const float* bias, void* out, d
   P.bn_y = (const bf16*)bn_y; P.slope = slope;
   if (bn_y != nullptr) { P.bn_mean = bn_vec[0]; P.bn_scale = bn_vec[1]; P.bn_beta = bn_vec[2]; P.bn_rstd = bn_vec[3]; }
   if (act != nullptr) { P.act_mean = act[0]; P.act_scale = act[1]; P.act_beta = act[2]; }
-  if (stats && cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N, st) != cudaSuccess) {
+  if (stats && zero_scratch(stats, sizeof(double) * 2 * N, st) != cudaSuccess) {
     set_error("conv_umma_tmat: memset");
     return VAE_ERR_CUDA;
   }

@@ -256,7 +256,7 @@ extern "C" int vae_conv_wgrad_umma(const void* x, const void* dy, float* dw, int
   VAE_REQUIRE(wgrad_plan(P), "conv_wgrad_umma: shape (Ci=%d, Co=%d) not served by the tcgen05 path", Ci, Co);
   VAE_REQUIRE(P.J < (1LL << 31), "conv_wgrad_umma: too many pixels for 32-bit indexing");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
+  VAE_CUDA(zero_scratch(dw, sizeof(float) * 9 * (size_t)Ci * Co, st));
   const int m_tiles = (Co + 127) / 128;
   const int combos = m_tiles * P.n_tap_groups;
   long long kblocks = (P.J + 63) / 64;

@@ -377,7 +377,7 @@ extern "C" int vae_conv_wgrad_tma(const void* x, const void* dy, float* dw, floa
     VAE_REQUIRE(cr == CUDA_SUCCESS, "conv_wgrad_tma: tensor map (y) failed (%d)", (int)cr);
   }
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st));
+  VAE_CUDA(zero_scratch(ws, sizeof(float) * 9 * (size_t)Ci * Co, st));
   P.ws = ws;
   const int combos = P.n_tap_groups * P.n_co_tiles;
   int splits = P.ctas_per_sm * sm_count() / combos;

@@ -331,7 +331,7 @@ extern "C" int vae_elbo_fwd(const void* logits, const float* target, const float
   VAE_REQUIRE(logits && target && mu && logvar && losses && scratch && n_elem > 0 && B > 0 && L > 0,
               "elbo_fwd: bad argument");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
+  VAE_CUDA(zero_scratch(scratch, 4 * sizeof(double), st));
   int grid = elbo_grid(n_elem);
   if (dtype == VAE_BF16)
     elbo_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)logits, target, mu, logvar, losses,
@@ -374,7 +374,7 @@ extern "C" int vae_elbo_fused(const void* logits, const float* target, const flo
                   B > 0 && L > 0,
               "elbo_fused: bad argument");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(scratch, 0, 4 * sizeof(double), st));
+  VAE_CUDA(zero_scratch(scratch, 4 * sizeof(double), st));
   // every thread walks the same number (+-1) of vector pairs; 4 blocks per SM stay resident
   long long blocks = (n_elem / 16 + 255) / 256;
   const long long cap = (long long)sm_count() * 4;

@@ -880,7 +880,7 @@ extern "C" int vae_bn_lrelu_bwd_reduce(const void* dact, const void* y, const fl
   BwdCfg cfg;
   VAE_REQUIRE(bwd_cfg(n_pix, C, &cfg), "bn_lrelu_bwd_reduce: unsupported channel count %d", C);
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * C, st));
+  VAE_CUDA(zero_scratch(dstats, sizeof(double) * 2 * C, st));
   size_t smem = sizeof(float) * cfg.lanes * cfg.G * 2 * cfg.V;
 #define LAUNCH(T, V)                                                                       \
   bn_bwd_reduce_kernel<T, V><<<cfg.grid, 256, smem, st>>>((const T*)dact, (const T*)y, scale, \
@@ -906,7 +906,7 @@ extern "C" int vae_bn_lrelu_bwd_apply(const void* dact, const void* y, const flo
   BwdCfg cfg;
   VAE_REQUIRE(bwd_cfg(n_pix, C, &cfg), "bn_lrelu_bwd_apply: unsupported channel count %d", C);
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+  VAE_CUDA(zero_scratch(dbias, sizeof(float) * C, st));
   size_t smem = sizeof(float) * cfg.lanes * cfg.G * cfg.V;
 #define LAUNCH(T, V)                                                                          \
   bn_bwd_apply_kernel<T, V><<<cfg.grid, 256, smem, st>>>((const T*)dact, (const T*)y, scale,    \
@@ -947,8 +947,8 @@ extern "C" int vae_bn_lrelu_bwd_fused(const void* dact, const void* y, const flo
   if (per_sm < 1) return VAE_ERR_UNSUPPORTED;
   int grid = cfg.grid;
   if (grid > per_sm * sm_count()) grid = per_sm * sm_count();
-  VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * (2 * C + 1), st));
-  VAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+  VAE_CUDA(zero_scratch(dstats, sizeof(double) * (2 * C + 1), st));
+  VAE_CUDA(zero_scratch(dbias, sizeof(float) * C, st));
   void* args[] = {(void*)&dact, (void*)&y, (void*)&scale, (void*)&beta, (void*)&mean, (void*)&rstd, (void*)&gamma,
                   (void*)&dstats, (void*)&dy, (void*)&dgamma, (void*)&dbeta, (void*)&dbias, (void*)&n_pix, (void*)&C,
                   (void*)&slope, (void*)&training};
@@ -1062,7 +1062,7 @@ extern "C" int vae_pack_conv_weight(const float* w_oihw, void* wp, void* wt, int
 extern "C" int vae_colsum(const void* A, float* out, int M, int N, int dtype, vae_stream_t stream) {
   VAE_REQUIRE(A && out && M > 0 && N > 0, "colsum: bad argument");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  VAE_CUDA(zero_scratch(out, sizeof(float) * N, st));
   int col_blocks = ceil_div(N, 32);
   int want = ceil_div(4 * sm_count(), col_blocks);
   int row_blocks = want < 1 ? 1 : want;

@@ -501,8 +501,8 @@ extern "C" int vae_final_bwd_reduce(const void* dlogits, const void* y, const fl
   VAE_REQUIRE(final_shape_ok(B, H, W, C), "final_bwd_reduce: shape B=%d H=%d W=%d C=%d not served", B, H, W, C);
   VAE_REQUIRE(dtype == VAE_F32 || dtype == VAE_BF16, "final_bwd_reduce: bad dtype");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * (2 * C + 1), st));
-  VAE_CUDA(cudaMemsetAsync(dw_last, 0, sizeof(float) * 9 * C, st));
+  VAE_CUDA(zero_scratch(dstats, sizeof(double) * (2 * C + 1), st));
+  VAE_CUDA(zero_scratch(dw_last, sizeof(float) * 9 * C, st));
   VAE_FINAL_DISPATCH(reduce_launch, dlogits, y, mean, scale, beta, rstd, w_last, dstats, dw_last, B, H, W, slope, st);
   return VAE_ERR_UNSUPPORTED;
 }
@@ -518,7 +518,7 @@ extern "C" int vae_final_bwd_apply(const void* dlogits, const void* y, const flo
   VAE_REQUIRE(final_shape_ok(B, H, W, C), "final_bwd_apply: shape B=%d H=%d W=%d C=%d not served", B, H, W, C);
   VAE_REQUIRE(dtype == VAE_F32 || dtype == VAE_BF16, "final_bwd_apply: bad dtype");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+  VAE_CUDA(zero_scratch(dbias, sizeof(float) * C, st));
   VAE_FINAL_DISPATCH(apply_launch, dlogits, y, mean, scale, beta, rstd, gamma, w_last, dstats, dy, dgamma, dbeta,
                      dbias, db_last, B, H, W, slope, training, st);
   return VAE_ERR_UNSUPPORTED;

@@ -1462,8 +1462,8 @@ extern "C" int vae_final_bwd_reduce_tc(const void* dlogits, const void* y, const
   VAE_REQUIRE(final_tc_ok(B, H, W, C, VAE_BF16), "final_bwd_reduce_tc: shape not served");
   VAE_REQUIRE(slope > 0.0f && slope < 1.0f, "final_bwd_reduce_tc: LeakyReLU slope must be in (0, 1)");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(dstats, 0, sizeof(double) * (2 * C + 1), st));
-  VAE_CUDA(cudaMemsetAsync(dw_last, 0, sizeof(float) * 9 * C, st));
+  VAE_CUDA(zero_scratch(dstats, sizeof(double) * (2 * C + 1), st));
+  VAE_CUDA(zero_scratch(dw_last, sizeof(float) * 9 * C, st));
   for (int g = 0; g < C / 32; ++g) {   // the reductions are per channel: one launch per group of 32
     FinalTcParams P{};
     int rc = final_tc_setup(P, y, B, H, W, C, g, false);

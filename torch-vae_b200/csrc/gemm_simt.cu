@@ -122,7 +122,7 @@ int gemm_launch(const void* A, const void* Bm, void* C, const float* bias, int M
   int use_atomics = splits > 1;
   if (use_atomics && !accumulate) {
     if (scn == 1 && scm == N) {
-      cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
+      cudaError_t e = zero_scratch(C, sizeof(float) * (size_t)M * N, st);
       if (e != cudaSuccess) {
         set_error("gemm: memset failed: %s", cudaGetErrorString(e));
         return VAE_ERR_CUDA;

@@ -332,8 +332,8 @@ static int skinny_reduce_launch(const void* A, const float* W, const float* bias
                                 const float* bias1, float* out1, int M, int N, int K, long long wsn, long long wsk, int dtA,
                                 cudaStream_t st) {
   const bool pair = W1 != nullptr;
-  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * N, st));
-  if (pair) VAE_CUDA(cudaMemsetAsync(out1, 0, sizeof(float) * (size_t)M * N, st));
+  VAE_CUDA(zero_scratch(out, sizeof(float) * (size_t)M * N, st));
+  if (pair) VAE_CUDA(zero_scratch(out1, sizeof(float) * (size_t)M * N, st));
   const int rows = pair ? 2 : 4;   // the pair keeps two accumulator sets: half the rows per warp
   const int row_blocks = (M + 8 * rows - 1) / (8 * rows);
   int ks_len = pair ? 512 : 1024;  // K slice per block: one wave of two blocks per SM where the shape allows it

@@ -491,7 +491,7 @@ extern "C" int vae_linear_reduce_tc(const void* A, const float* W, const float* 
   VAE_REQUIRE(A && W && out && (w_layout == 0 || w_layout == 1), "linear_reduce_tc: bad argument");
   VAE_REQUIRE(linear_tc_ok(M, L, F), "linear_reduce_tc: shape not served");
   cudaStream_t st = as_stream(stream);
-  VAE_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M * L, st));
+  VAE_CUDA(zero_scratch(out, sizeof(float) * (size_t)M * L, st));
   const int tiles = F / kRedKT;
   const int w_bytes = w_layout == 0 ? L * 40 * 4 : kRedKT * (L + 4) * 4;
   const size_t smem = (size_t)kRedStages * (w_bytes + 64 * 64);

@@ -41,7 +41,33 @@ int sm_count() {
   return left >= 8 ? left : 8;
 }
 
+constexpr int kMaxDevices = 64;
+static uintptr_t g_arena_lo[kMaxDevices] = {0}, g_arena_hi[kMaxDevices] = {0};
+
+cudaError_t zero_scratch(void* p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if (a >= g_arena_lo[dev] && a + bytes <= g_arena_hi[dev]) return cudaSuccess;   // the caller cleared it with its arena
+  }
+  return cudaMemsetAsync(p, 0, bytes, st);
+}
+
 }  // namespace vae
+
+/* Register [base, base + bytes) on the CURRENT device as a scratch arena the caller keeps zeroed: buffers inside it that
+ * a kernel accumulates into (BatchNorm statistics, split-K workspaces, loss scratch) are NOT cleared by the library --
+ * the caller clears what it handed out once per step (ops.ZeroArena).  base = NULL removes the registration. */
+extern "C" int vae_set_zero_arena(void* base, long long bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= vae::kMaxDevices || bytes < 0) {
+    vae::set_error("vae_set_zero_arena: bad device or size");
+    return VAE_ERR_ARG;
+  }
+  vae::g_arena_lo[dev] = reinterpret_cast<uintptr_t>(base);
+  vae::g_arena_hi[dev] = base ? reinterpret_cast<uintptr_t>(base) + (uintptr_t)bytes : 0;
+  return VAE_OK;
+}
 
 /* Leave `n` SMs out of the grids of the persistent kernels (for concurrent NCCL kernels in data-parallel runs with large
  * gradient buckets); returns the previous setting.  0 (default): every SM. */

@@ -146,7 +146,7 @@ class EncodeFn(torch.autograd.Function):
                 h = ops.conv_forward(h, cw, b, None, Ci=sp.ci, act=(vec, beta))
                 Hi, Wi = Hi // 2, Wi // 2
                 continue
-            stats = torch.empty(2 * sp.co, dtype=torch.float64, device=h.device) if training else None
+            stats = ops.scratch(2 * sp.co, torch.float64, h.device) if training else None
             y = ops.conv_forward(h, cw, b, stats, Ci=sp.ci)
             vec, act = _bn_forward(y, stats, gamma, beta, sp.bn, training)
             saved.append((h, y, vec, cw, Hi, Wi))
@@ -283,7 +283,7 @@ class DecodeFn(torch.autograd.Function):
                 vec = _bn_vectors(h, None, gamma, beta, sp.bn, False)
                 h = ops.conv_data_grad(h, cw, b, None, act=(vec, beta))  # ConvTranspose2d + eval BatchNorm + LeakyReLU, one pass
                 continue
-            stats = torch.empty(2 * sp.ci, dtype=torch.float64, device=z.device) if training else None
+            stats = ops.scratch(2 * sp.ci, torch.float64, z.device) if training else None
             y = ops.conv_data_grad(h, cw, b, stats)  # ConvTranspose2d forward
             if i == len(specs) - 1 and ops.final_block_supported(B, y.shape[1], y.shape[2], sp.ci):
                 # output block: BatchNorm apply + LeakyReLU ride in the final conv's operand load

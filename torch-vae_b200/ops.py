@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import math
+
 import torch
 
 from . import _lib
@@ -66,7 +68,7 @@ class _Proxy:
                           "vae_set_umma_tma", "vae_umma_tma_eligible", "vae_umma_tma_packed_elems",
                           "vae_final_block_supported", "vae_set_umma_rw", "vae_umma_rw_eligible",
                           "vae_umma_rw_packed_elems", "vae_set_wgrad_tma", "vae_wgrad_tma_eligible", "vae_heads_supported", "vae_set_final_tc",
-                          "vae_final_tc_supported", "vae_linear_tc_supported", "vae_set_edge_tc", "vae_set_umma_tmat", "vae_set_reserved_sms"})
+                          "vae_final_tc_supported", "vae_linear_tc_supported", "vae_set_edge_tc", "vae_set_umma_tmat", "vae_set_reserved_sms", "vae_set_zero_arena"})
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
@@ -259,7 +261,7 @@ def bn_lrelu_backward(dact, y, vec, gamma, beta, training: bool, slope: float = 
             _lib.check(rc, "vae_bn_lrelu_bwd_fused")
         dstats = None
     if not is_du:
-        dstats = torch.empty(2 * C, dtype=torch.float64, device=y.device)
+        dstats = scratch(2 * C, torch.float64, y.device)
         rc = lib.vae_bn_lrelu_bwd_reduce(
             _p(dact), _p(y), vec[0].data_ptr(), _f32(beta, "bn bias"), vec[2].data_ptr(), vec[3].data_ptr(),
             _p(dstats), n_pix, C, slope, code(y), _stream(),
@@ -318,7 +320,7 @@ def final_block_backward(dlogits, y, vec, gamma, beta, w_last, training: bool, s
     destinations, ``last_outs`` = optional (dw_last [1,C,3,3], db_last [1]) destinations."""
     B, H, W, C = y.shape
     lib = _L()
-    dstats = torch.empty(2 * C + 1, dtype=torch.float64, device=y.device)
+    dstats = scratch(2 * C + 1, torch.float64, y.device)
     dw_last = last_outs[0] if last_outs is not None else torch.empty((1, C, 3, 3), dtype=torch.float32, device=y.device)
     mean, scale, rstd = vec[2].data_ptr(), vec[0].data_ptr(), vec[3].data_ptr()
     tc = final_tc_supported(y)
@@ -550,11 +552,11 @@ def reparam_bwd(dz, eps, logvar):
 # ------------------------------------------------------------------------ ELBO
 def elbo_fwd(logits, target, mu, logvar, kld_weight: float, input_is_prob: bool):
     losses = torch.empty(3, dtype=torch.float32, device=logits.device)
-    scratch = torch.empty(4, dtype=torch.float64, device=logits.device)
+    scratch_ = scratch(4, torch.float64, logits.device)
     B, L = mu.shape
     rc = _L().vae_elbo_fwd(
         _p(logits), _f32(target, "input"), _f32(mu, "mu"), _f32(logvar, "log_var"), _p(losses),
-        _p(scratch), logits.numel(), B, L, kld_weight, code(logits), 1 if input_is_prob else 0, _stream(),
+        _p(scratch_), logits.numel(), B, L, kld_weight, code(logits), 1 if input_is_prob else 0, _stream(),
     )
     _lib.check(rc, "vae_elbo_fwd")
     return losses
@@ -577,13 +579,13 @@ def elbo_bwd(logits, target, mu, logvar, gscale, kld_weight: float, input_is_pro
 def elbo_fused(logits, target, mu, logvar, kld_weight: float, input_is_prob: bool):
     """Losses and, for an upstream gradient of 1, (dlogits, dmu, dlogvar) in one pass."""
     losses = torch.empty(3, dtype=torch.float32, device=logits.device)
-    scratch = torch.empty(4, dtype=torch.float64, device=logits.device)
+    scratch_ = scratch(4, torch.float64, logits.device)
     dlogits = torch.empty_like(logits)
     dmu = torch.empty_like(mu)
     dlv = torch.empty_like(mu)
     B, L = mu.shape
     rc = _L().vae_elbo_fused(
-        _p(logits), _f32(target, "input"), _f32(mu, "mu"), _f32(logvar, "log_var"), _p(losses), _p(scratch),
+        _p(logits), _f32(target, "input"), _f32(mu, "mu"), _f32(logvar, "log_var"), _p(losses), _p(scratch_),
         _p(dlogits), _p(dmu), _p(dlv), logits.numel(), B, L, kld_weight, code(logits),
         1 if input_is_prob else 0, _stream(),
     )
@@ -876,6 +878,81 @@ def aux_stream(device) -> "torch.cuda.Stream":
     return _AUX_STREAMS[idx]
 
 
+class ZeroArena:
+    """Per-device scratch arena kept ZERO by its owner: the buffers kernels accumulate into (BatchNorm statistics, split-K
+    weight-gradient workspaces, loss scratch) are carved from it and the library skips its own clear for pointers
+    inside it (``vae_set_zero_arena``).  ``reset()`` -- called once at the start of every step by the step driver
+    (trainer.TrainStep, bench.py) -- clears what the previous step handed out with ONE memset instead of ~25 memset
+    nodes spread between the kernels of the step.  Everything past the cursor is zero at all times; a request that
+    does not fit falls back to a fresh tensor (which the library clears as before)."""
+
+    ALIGN = 256
+
+    def __init__(self, device, nbytes: int):
+        self.device = torch.device(device)
+        self.buf = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+        self.off = 0
+        with torch.cuda.device(self.device):
+            _lib.check(_L().vae_set_zero_arena(self.buf.data_ptr(), self.buf.numel()), "vae_set_zero_arena")
+
+    def take(self, shape, dtype):
+        n = int(math.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if self.off + n > self.buf.numel():
+            return None
+        t = self.buf[self.off : self.off + n].view(dtype).view(shape)
+        self.off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return t
+
+    def reset(self) -> None:
+        if self.off:
+            self.buf[: min(self.off, self.buf.numel())].zero_()
+            self.off = 0
+
+    def close(self) -> None:
+        with torch.cuda.device(self.device):
+            _L().vae_set_zero_arena(None, 0)
+
+
+_ZERO_ARENAS = {}
+
+
+def _dev_index(device) -> int:
+    idx = torch.device(device).index if device is not None else None
+    return torch.cuda.current_device() if idx is None else idx
+
+
+def enable_zero_arena(device=None, nbytes: int = 64 << 20) -> ZeroArena:
+    """Turn the scratch arena on for ``device``.  Only for callers that run whole steps and call
+    ``zero_arena_reset`` at the start of each one (scratch handed out in a step must be dead by the next reset)."""
+    idx = _dev_index(device)
+    if idx not in _ZERO_ARENAS:
+        _ZERO_ARENAS[idx] = ZeroArena(torch.device("cuda", idx), nbytes)
+    return _ZERO_ARENAS[idx]
+
+
+def disable_zero_arena(device=None) -> None:
+    a = _ZERO_ARENAS.pop(_dev_index(device), None)
+    if a is not None:
+        a.close()
+
+
+def zero_arena_reset(device=None) -> None:
+    a = _ZERO_ARENAS.get(_dev_index(device))
+    if a is not None:
+        a.reset()
+
+
+def scratch(shape, dtype, device):
+    """Buffer a kernel accumulates into (the library clears it first -- or the arena already did)."""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    a = _ZERO_ARENAS.get(_dev_index(device)) if _ZERO_ARENAS else None
+    if a is not None:
+        t = a.take(shape, dtype)
+        if t is not None:
+            return t
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
 _COPY_STREAMS = {}
 
 
@@ -1018,7 +1095,7 @@ def conv_weight_grad(x, dy, stride: int, Ci: int, Co: int, Hi: int, Wi: int, out
             _L().vae_wgrad_tma_eligible(dy.shape[0], Hi, Wi, Ci, Co, stride):
         B = dy.shape[0]
         dw = out if out is not None else torch.empty((Co, Ci, 3, 3), dtype=torch.float32, device=dy.device)
-        ws = torch.empty(9 * Co * Ci, dtype=torch.float32, device=dy.device)
+        ws = scratch(9 * Co * Ci, torch.float32, dy.device)
         rc = _L().vae_conv_wgrad_tma(_p(x), _p(dy), _p(dw), _p(ws), B, Hi, Wi, Ci, Co, stride, _stream())
         _lib.check(rc, "vae_conv_wgrad_tma")
         return dw

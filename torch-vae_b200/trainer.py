@@ -19,6 +19,7 @@ from typing import Dict, Iterator, Optional
 
 import torch
 
+from . import ops
 from .data_transformations import RollTransform
 from .optim import FusedAdamW, FusedOneCycleLR
 from .parallel import GradientBuckets
@@ -26,8 +27,12 @@ from .parallel import GradientBuckets
 
 class TrainStep:
     def __init__(self, model, optimizer, scheduler=None, buckets: Optional[GradientBuckets] = None, use_graph: bool = True,
-                 warm_steps: int = 3):
+                 warm_steps: int = 3, zero_arena: bool = True):
         self.model, self.opt, self.sched, self.buckets = model, optimizer, scheduler, buckets
+        # statistics / split-K scratch of the step from one arena cleared once per step (ops.ZeroArena)
+        self._arena_dev = next(model.parameters()).device if zero_arena else None
+        if self._arena_dev is not None:
+            ops.enable_zero_arena(self._arena_dev)
         self.use_graph = use_graph
         self.warm_steps = max(1, int(warm_steps))   # >= 1: the optimizer's device tables must exist before capture
         self._graph = None
@@ -40,6 +45,8 @@ class TrainStep:
 
     # train.py:635-659
     def _step(self, x) -> Dict[str, torch.Tensor]:
+        if self._arena_dev is not None:
+            ops.zero_arena_reset(self._arena_dev)
         out = self.model.forward(x)
         self.opt.zero_grad(set_to_none=True)
         losses = self.model.loss(out)
