@@ -142,6 +142,24 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_inference_mode_rule():
+    """engine.inference_mode: the conv epilogues may apply eval-mode BatchNorm + LeakyReLU (one pass, no stored
+    pre-normalisation tensor) only when the module is in eval mode AND autograd will record nothing."""
+    import torch_vae_b200 as tv
+
+    im = tv.engine.inference_mode
+    w = torch.zeros(3, requires_grad=True)
+    x = torch.zeros(3)
+    assert not im(True, x, w)                      # training: batch statistics, activations are kept
+    assert not im(False, x, w)                     # eval, but a parameter requires grad and grad mode is on
+    assert im(False, x, w.detach())                # eval, nothing requires grad
+    assert im(False, x, None, w.detach())          # None entries (absent biases) are ignored
+    with torch.no_grad():
+        assert im(False, x, w)                     # eval under no_grad: sample(), evaluate()
+        assert not im(True, x, w)
+    assert not im(False, x.requires_grad_(True), w.detach())   # gradient w.r.t. the input (e.g. latent optimisation)
+
+
 def test_gradient_buckets_local_sink_without_process_group():
     """Without torch.distributed the sink is local (one GPU): same slots and views, no collective, p.grad = the bucket
     views holding exactly what was pushed; an incomplete step is still reported."""
