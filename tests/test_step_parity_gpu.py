@@ -378,7 +378,9 @@ def test_zero_arena_step_matches(tv, nbytes):
     _, ref_losses, ref_grads, ref_bufs = run_cuda(ref, x, eps)
     model = build(tv, H, W, hidden, L, 1.0, torch.bfloat16, params)
     dev = torch.device("cuda", torch.cuda.current_device())
+    tv.ops.disable_zero_arena(dev)   # an arena left by an earlier TrainStep in this process would ignore `nbytes`
     arena = tv.ops.enable_zero_arena(dev, nbytes)
+    assert arena.buf.numel() == nbytes
     try:
         used = []
         for _ in range(3):
